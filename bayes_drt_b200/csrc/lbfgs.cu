@@ -1,0 +1,361 @@
+// Batched on-device L-BFGS MAP driver.
+//
+// Replaces StanModel.optimizing(dat, iter=max_iter, seed, init) (bayes_drt/inversion.py:1216): Stan 2.19.1's
+// L-BFGS [Stan-upstream] on the unconstrained vector, objective f = -log_prob(jacobian=false): two-loop recursion
+// with history 5, bracketing + cubic-zoom strong-Wolfe line search, Stan's convergence tests in Stan's order.
+//
+// Mapping: persistent CTAs (one per SM) pull spectra from an atomic queue; each of the 8 warps of a CTA runs the
+// whole optimiser for one spectrum with warp-uniform control flow (vectors distributed over lanes, dot products by
+// shuffle), and all 8 meet in engine_eval() for every objective/gradient evaluation (see engine.cuh).  A warp that
+// finishes refills its slot from the queue, so slots never idle while work remains.
+#include <math.h>
+
+#include "engine.cuh"
+
+#define MAXHIST 16
+
+namespace {
+
+struct Ctl {  // shared control block
+  int n_active;
+};
+
+__device__ __forceinline__ double vdot(const double* a, const double* b, int D, int lane) {
+  double s = 0.0;
+  for (int i = lane; i < D; i += 32) s = fma(a[i], b[i], s);
+  return warp_sum(s);
+}
+
+struct LS {  // per-warp optimiser state living in registers (warp-uniform)
+  double f1, dfp1, alpha;
+  int neval;
+};
+
+// cubic_interp of Stan's bfgs_linesearch.hpp [Stan-upstream]; see oracle/lbfgs.py:cubic_interp
+__device__ double cubic_interp(double df0, double x1, double f1, double df1, double lo, double hi) {
+  const double c3 = (-12.0 * f1 + 6.0 * x1 * (df0 + df1)) / (x1 * x1 * x1);
+  const double c2 = -(4.0 * df0 + 2.0 * df1) / x1 + 6.0 * f1 / (x1 * x1);
+  const double c1 = df0;
+  const double t_s = sqrt(c2 * c2 - 2.0 * c1 * c3);
+  const double s1 = -(c2 + t_s) / c3, s2 = -(c2 - t_s) / c3;
+  auto val = [&](double s) { return s * (s * (s * c3 / 3.0 + c2) / 2.0 + c1); };
+  double minF = val(lo), minX = lo;
+  double tmp = val(hi);
+  if (tmp < minF) { minF = tmp; minX = hi; }
+  if (lo < s1 && s1 < hi) { tmp = val(s1); if (tmp < minF) { minF = tmp; minX = s1; } }
+  if (lo < s2 && s2 < hi) { tmp = val(s2); if (tmp < minF) { minF = tmp; minX = s2; } }
+  return minX;
+}
+
+}  // namespace
+
+__global__ void __launch_bounds__(NTHREADS, 1)
+lbfgs_kernel(BdrtModel m, bdrt_lbfgs_opts o, double* __restrict__ U, double* lp_out, int* iters_out, int* neval_out,
+             int* status_out, int* queue, double* hist, double* gvec, int nvec_smem, int Dpad) {
+  extern __shared__ double sm[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int D = m.D;
+  const int H = o.history;
+  volatile int* n_active = (volatile int*)(sm + m.oUser);
+  double* suser = sm + m.oUser + 2;
+  if (threadIdx.x == 0) *n_active = NWARP;
+  engine_load(m, sm, 0);
+
+  // the slot's five work vectors: the first nvec_smem live in shared memory, the rest in global scratch
+  double* vec[5];
+  {
+    double* gbase = gvec + ((long long)blockIdx.x * NSLOT + warp) * 5 * Dpad;
+    for (int i = 0; i < 5; ++i)
+      vec[i] = (i < nvec_smem) ? (suser + ((long long)warp * nvec_smem + i) * Dpad) : (gbase + (long long)i * Dpad);
+  }
+  double *xk = vec[0], *gk = vec[1], *pk = vec[2], *xn = vec[3], *gn = vec[4];
+  double* S = hist + ((long long)blockIdx.x * NSLOT + warp) * 2 * MAXHIST * Dpad;
+  double* Y = S + (long long)MAXHIST * Dpad;
+  int snap;
+
+  const double EPS = 2.220446049250313e-16;
+  int neval = 0;
+  const double* Zs = m.Z;
+
+  // f(xn) -> f, gn = grad f ; returns false when not finite
+  auto feval = [&](double& f) -> bool {
+    const double lp = engine_eval(m, sm, true, xn, gn, Zs, 0);
+    ++neval;
+    int fin = isfinite(lp);
+    for (int i = lane; i < D; i += 32) {
+      const double v = -gn[i];
+      gn[i] = v;
+      fin &= isfinite(v);
+    }
+    __syncwarp();
+    f = -lp;
+    return warp_and(fin);
+  };
+  auto step_to = [&](double alpha) {
+    for (int i = lane; i < D; i += 32) xn[i] = fma(alpha, pk[i], xk[i]);
+    __syncwarp();
+  };
+
+  while (true) {
+    int b = 0;
+    if (lane == 0) b = atomicAdd(queue, 1);
+    b = __shfl_sync(0xffffffffu, b, 0);
+    if (b >= m.B) break;
+    Zs = m.Z + (long long)b * m.N2;
+    double* ub = U + (long long)b * D;
+    for (int i = lane; i < D; i += 32) xn[i] = ub[i];
+    __syncwarp();
+    neval = 0;
+    double fk = nan("");
+    int code = BDRT_TERM_RUNNING, it = 0;
+    if (!feval(fk)) {
+      code = BDRT_TERM_BADINIT;
+    } else {
+      { double* t_ = xk; xk = xn; xn = t_; t_ = gk; gk = gn; gn = t_; }
+      for (int i = lane; i < D; i += 32) pk[i] = -gk[i];
+      __syncwarp();
+      int nh = 0, head = 0;  // history: entries head-nh .. head-1 (mod H), newest = head-1
+      double rho[MAXHIST], al[MAXHIST];
+      double gamma = 1.0, alpha = o.init_alpha;
+      double fk_1 = 0.0, dfp_old = 0.0, dfp_new = 0.0;
+
+      while (code == BDRT_TERM_RUNNING) {
+        ++it;
+        bool reset = (it == 1);
+        bool ls_ok = false;
+        double f1 = 0.0, newDFp = 0.0;
+        while (true) {
+          if (reset) {
+            for (int i = lane; i < D; i += 32) pk[i] = -gk[i];
+            __syncwarp();
+          }
+          if (it > 1 && !reset)
+            alpha = fmin(1.0, 1.01 * cubic_interp(dfp_old, alpha, fk - fk_1, dfp_new, 1e-12, 1.0));
+          else
+            alpha = o.init_alpha;
+          // ---------------- WolfeLineSearch (c1 = 1e-4, c2 = 0.9, minAlpha = 1e-12, <= 20 its, <= 10 restarts)
+          const double dfp = vdot(gk, pk, D, lane);
+          const double c1dfp = 1e-4 * dfp, c2dfp = 0.9 * dfp;
+          double alpha0 = 1e-12, prevF = fk, prevDFp = dfp;
+          int nits = 0, restarts = 0, ret = -1;  // ret: 0 ok, 1 fail
+          // zoom bracket
+          bool zoom = false;
+          double alo = 0, aloF = 0, aloDFp = 0, ahi = 0, ahiF = 0, ahiDFp = 0;
+          while (ret < 0 && !zoom) {
+            if (nits >= 20) { ret = 1; break; }
+            step_to(alpha);
+            if (!feval(f1)) {
+              if (restarts >= 10) { ret = 1; break; }
+              alpha = 0.5 * (alpha0 + alpha);
+              ++restarts;
+              continue;
+            }
+            restarts = 0;
+            newDFp = vdot(gn, pk, D, lane);
+            if (f1 > fk + alpha * c1dfp || (f1 >= prevF && nits > 0)) {
+              alo = alpha0; aloF = prevF; aloDFp = prevDFp; ahi = alpha; ahiF = f1; ahiDFp = newDFp;
+              zoom = true;
+              break;
+            }
+            if (fabs(newDFp) <= -c2dfp) { ret = 0; break; }
+            if (newDFp >= 0) {
+              alo = alpha; aloF = f1; aloDFp = newDFp; ahi = alpha0; ahiF = prevF; ahiDFp = prevDFp;
+              zoom = true;
+              break;
+            }
+            alpha0 = alpha; prevF = f1; prevDFp = newDFp;
+            alpha *= 10.0;
+            ++nits;
+          }
+          if (zoom) {
+            // ---------------- WolfLSZoom (min_range 1e-16)
+            int itn = 0;
+            ret = -1;
+            while (ret < 0) {
+              ++itn;
+              if (fabs(alo - ahi) < 1e-16) { ret = 1; break; }
+              if (itn % 5 == 0) {
+                alpha = 0.5 * (alo + ahi);
+              } else {
+                const double d1 = aloDFp + ahiDFp - 3.0 * (aloF - ahiF) / (alo - ahi);
+                double d2 = sqrt(d1 * d1 - aloDFp * ahiDFp);
+                if (ahi < alo) d2 = -d2;
+                alpha = ahi - (ahi - alo) * (ahiDFp + d2 - d1) / (ahiDFp - aloDFp + 2.0 * d2);
+                const double lo = fmin(alo, ahi), hi = fmax(alo, ahi), rng = fabs(alo - ahi);
+                if (!isfinite(alpha) || alpha < lo + 0.01 * rng || alpha > hi - 0.01 * rng) alpha = 0.5 * (alo + ahi);
+              }
+              bool okev;
+              while (true) {
+                step_to(alpha);
+                okev = feval(f1);
+                if (okev) break;
+                alpha = 0.5 * (alpha + fmin(alo, ahi));
+                if (fabs(fmin(alo, ahi) - alpha) < 1e-16) break;
+              }
+              if (!okev) { ret = 1; break; }
+              newDFp = vdot(gn, pk, D, lane);
+              if (f1 > (fk + alpha * c1dfp) || f1 >= aloF) {
+                ahi = alpha; ahiF = f1; ahiDFp = newDFp;
+              } else {
+                if (fabs(newDFp) <= -c2dfp) { ret = 0; break; }
+                if (newDFp * (ahi - alo) >= 0) { ahi = alo; ahiF = aloF; ahiDFp = aloDFp; }
+                alo = alpha; aloF = f1; aloDFp = newDFp;
+              }
+            }
+          }
+          if (ret != 0) {
+            if (reset) break;  // failed even from steepest descent
+            reset = true;
+            continue;
+          }
+          ls_ok = true;
+          dfp_old = dfp;
+          break;
+        }
+        if (!ls_ok) { code = BDRT_TERM_LSFAIL; break; }
+
+        // accepted: xn, gn, f1, newDFp.  s = xn - xk, y = gn - gk
+        double* Sn = S + (long long)head * Dpad;
+        double* Yn = Y + (long long)head * Dpad;
+        double skyk = 0, yy = 0, gg = 0, ss = 0;
+        for (int i = lane; i < D; i += 32) {
+          const double s = xn[i] - xk[i], y = gn[i] - gk[i];
+          Sn[i] = s;
+          Yn[i] = y;
+          skyk = fma(s, y, skyk);
+          yy = fma(y, y, yy);
+          ss = fma(s, s, ss);
+          gg = fma(gn[i], gn[i], gg);
+        }
+        skyk = warp_sum(skyk); yy = warp_sum(yy); ss = warp_sum(ss); gg = warp_sum(gg);
+        const double gradNorm = sqrt(gg), stepNorm = sqrt(ss);
+        dfp_new = newDFp;
+        if (reset) {
+          const double B0 = yy / skyk;
+          nh = 0;
+          // keep the entry we just wrote as the only one
+          dfp_old /= B0;
+          dfp_new /= B0;
+          alpha *= B0;
+          if (head != 0) {
+            for (int i = lane; i < D; i += 32) { S[i] = Sn[i]; Y[i] = Yn[i]; }
+            head = 0;
+          }
+        }
+        gamma = skyk / yy;
+        rho[head] = 1.0 / skyk;
+        head = (head + 1) % H;
+        if (nh < H) ++nh;
+        fk_1 = fk;
+        fk = f1;
+        { double* t_ = xk; xk = xn; xn = t_; t_ = gk; gk = gn; gn = t_; }
+        __syncwarp();
+        __threadfence_block();
+        // ---------------- two-loop recursion -> pk
+        for (int i = lane; i < D; i += 32) pk[i] = -gk[i];
+        __syncwarp();
+        for (int j = 0; j < nh; ++j) {  // newest -> oldest
+          const int h = (head - 1 - j + 2 * H) % H;
+          const double* Sh = S + (long long)h * Dpad;
+          const double* Yh = Y + (long long)h * Dpad;
+          const double a = rho[h] * vdot(Sh, pk, D, lane);
+          al[h] = a;
+          for (int i = lane; i < D; i += 32) pk[i] = fma(-a, Yh[i], pk[i]);
+          __syncwarp();
+        }
+        for (int i = lane; i < D; i += 32) pk[i] *= gamma;
+        __syncwarp();
+        for (int j = nh - 1; j >= 0; --j) {  // oldest -> newest
+          const int h = (head - 1 - j + 2 * H) % H;
+          const double* Sh = S + (long long)h * Dpad;
+          const double* Yh = Y + (long long)h * Dpad;
+          const double beta = rho[h] * vdot(Yh, pk, D, lane);
+          const double c = al[h] - beta;
+          for (int i = lane; i < D; i += 32) pk[i] = fma(c, Sh[i], pk[i]);
+          __syncwarp();
+        }
+        // ---------------- convergence tests, Stan's order
+        const double df = fabs(fk_1 - fk);
+        const double gp = vdot(gk, pk, D, lane);
+        if (df < o.tol_obj)
+          code = BDRT_TERM_ABSF;
+        else if (df < o.tol_rel_obj * fmax(fabs(fk_1), fmax(fabs(fk), 1.0)) * EPS)
+          code = BDRT_TERM_RELF;
+        else if (gradNorm < o.tol_grad)
+          code = BDRT_TERM_ABSGRAD;
+        else if (-gp / fmax(fabs(fk), 1.0) < o.tol_rel_grad * EPS)
+          code = BDRT_TERM_RELGRAD;
+        else if (stepNorm < o.tol_param)
+          code = BDRT_TERM_ABSX;
+        else if (it >= o.max_iter)
+          code = BDRT_TERM_MAXIT;
+      }
+      for (int i = lane; i < D; i += 32) ub[i] = xk[i];
+    }
+    if (lane == 0) {
+      if (lp_out) lp_out[b] = -fk;
+      if (iters_out) iters_out[b] = it;
+      if (neval_out) neval_out[b] = neval;
+      if (status_out) status_out[b] = code;
+    }
+  }
+  // drain: keep serving the cooperative matrix products until every slot of the CTA is out of work
+  if (lane == 0) atomicSub((int*)n_active, 1);
+  while (true) {
+    engine_eval(m, sm, false, nullptr, nullptr, nullptr, 0, n_active, &snap);
+    if (snap == 0) break;
+  }
+}
+
+extern "C" void bdrt_lbfgs_default_opts(bdrt_lbfgs_opts* o) {
+  if (!o) return;
+  o->max_iter = 2000;  // Stan's own default; the reference passes iter=50000 (inversion.py:1076)
+  o->history = 5;
+  o->init_alpha = 1e-3;
+  o->tol_obj = 1e-12;
+  o->tol_rel_obj = 1e4;
+  o->tol_grad = 1e-8;
+  o->tol_rel_grad = 1e7;
+  o->tol_param = 1e-8;
+}
+
+extern "C" int bdrt_map_lbfgs(bdrt_ctx* ctx, const bdrt_series_data* data, const bdrt_lbfgs_opts* opts, double* u,
+                              double* lp, int* iters, int* n_eval, int* status) {
+  if (!ctx) return BDRT_E_NULL;
+  if (!u || !opts) BDRT_FAIL(ctx, BDRT_E_NULL, "bdrt_map_lbfgs: null pointer");
+  if (opts->history < 1 || opts->history > MAXHIST) BDRT_FAIL(ctx, BDRT_E_SIZE, "history must be in 1..%d", MAXHIST);
+  if (opts->max_iter < 1) BDRT_FAIL(ctx, BDRT_E_SIZE, "max_iter must be >= 1");
+  if (data && data->per_spectrum_grid)
+    BDRT_FAIL(ctx, BDRT_E_UNSUPPORTED, "bdrt_map_lbfgs: per-spectrum grids are not implemented in this build");
+  BdrtModel m;
+  {
+    // sizes first (model_prepare needs the scratch size)
+    if (!data) BDRT_FAIL(ctx, BDRT_E_NULL, "null data");
+  }
+  const int D = bdrt_num_params(data);
+  const int Dpad = (D + 1) & ~1;
+  const int grid = data->B == 0 ? 0 : ((data->B + NSLOT - 1) / NSLOT < ctx->sm_count ? (data->B + NSLOT - 1) / NSLOT
+                                                                                      : ctx->sm_count);
+  const size_t hist_bytes = (size_t)grid * NSLOT * 2 * MAXHIST * Dpad * sizeof(double);
+  const size_t gvec_bytes = (size_t)grid * NSLOT * 5 * Dpad * sizeof(double);
+  void* extra = nullptr;
+  int rc = bdrt_model_prepare(ctx, data, &m, 256 + hist_bytes + gvec_bytes, &extra);
+  if (rc) return rc;
+  if (data->B == 0) return BDRT_OK;
+  int* queue = (int*)extra;
+  double* hist = (double*)((char*)extra + 256);
+  double* gvec = (double*)((char*)extra + 256 + hist_bytes);
+  BDRT_CUDA(ctx, cudaMemsetAsync(queue, 0, 256, ctx->stream));
+  // how many of the 5 work vectors per slot fit in shared memory
+  const long long avail = (long long)ctx->smem_optin / 8 - m.oUser - 2;
+  int nvec = (int)(avail / ((long long)NSLOT * Dpad));
+  if (nvec > 5) nvec = 5;
+  if (nvec < 0) nvec = 0;
+  const size_t smem = ((size_t)m.oUser + 2 + (size_t)NSLOT * nvec * Dpad) * sizeof(double);
+  BDRT_CUDA(ctx, cudaFuncSetAttribute(lbfgs_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  lbfgs_kernel<<<grid, NTHREADS, smem, ctx->stream>>>(m, *opts, u, lp, iters, n_eval, status, queue, hist, gvec, nvec,
+                                                      Dpad);
+  ctx->launches++;
+  BDRT_CUDA(ctx, cudaGetLastError());
+  return BDRT_OK;
+}

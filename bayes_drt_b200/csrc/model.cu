@@ -1,0 +1,287 @@
+// Context management, model preparation, and the log_prob / constrain entry points.
+#include "engine.cuh"
+
+extern "C" int bdrt_version(void) { return BDRT_VERSION; }
+
+extern "C" int bdrt_ctx_create(int device, void* stream, bdrt_ctx** out) {
+  if (!out) return BDRT_E_NULL;
+  *out = nullptr;
+  cudaError_t e = cudaSetDevice(device);
+  if (e != cudaSuccess) return (int)e;
+  cudaDeviceProp prop;
+  e = cudaGetDeviceProperties(&prop, device);
+  if (e != cudaSuccess) return (int)e;
+  bdrt_ctx* c = new bdrt_ctx();
+  memset(c, 0, sizeof(*c));
+  c->device = device;
+  c->stream = (cudaStream_t)stream;
+  c->sm_count = prop.multiProcessorCount;
+  c->smem_optin = (int)prop.sharedMemPerBlockOptin;
+  *out = c;
+  return BDRT_OK;
+}
+
+extern "C" int bdrt_ctx_destroy(bdrt_ctx* ctx) {
+  if (!ctx) return BDRT_E_NULL;
+  cudaSetDevice(ctx->device);
+  if (ctx->ws) cudaFree(ctx->ws);
+  delete ctx;
+  return BDRT_OK;
+}
+
+extern "C" const char* bdrt_last_error(const bdrt_ctx* ctx) { return ctx ? ctx->err : "null context"; }
+extern "C" long long bdrt_launch_count(const bdrt_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+extern "C" int bdrt_num_params(const bdrt_series_data* d) {
+  if (!d) return BDRT_E_NULL;
+  return 2 * d->K + 9 + ((d->model & BDRT_MODEL_OUTLIERS) ? 2 * d->Nf : 0);
+}
+extern "C" int bdrt_num_outputs(const bdrt_series_data* d) {
+  if (!d) return BDRT_E_NULL;
+  return d->K + 6 + 2 * d->Nf + ((d->model & BDRT_MODEL_OUTLIERS) ? d->Nf : 0);
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Band extraction of the dense penalty matrices L0/L1/L2 (K x K each): at the reference's default epsilon the entries
+// decay like exp(-(n-m)^2), so only |n-m| <= bw are kept (everything dropped is < 1e-18 of the largest entry, i.e.
+// invisible in FP64 next to the reference's dense L @ x).  info[0] = bw, info[1] = 1 when every L_j is Toeplitz.
+// ---------------------------------------------------------------------------------------------------------------------
+__global__ void band_prep_kernel(const double* L, int K, double* Lb, int* info) {
+  const int j = blockIdx.x;
+  const double* Lj = L + (long long)j * K * K;
+  __shared__ double s_red[32];
+  __shared__ double s_max;
+  double mx = 0.0;
+  for (int i = threadIdx.x; i < K * K; i += blockDim.x) mx = fmax(mx, fabs(Lj[i]));
+  mx = warp_max(mx);
+  if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = mx;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double v = 0.0;
+    for (int w = 0; w < (blockDim.x + 31) / 32; ++w) v = fmax(v, s_red[w]);
+    s_max = v;
+  }
+  __syncthreads();
+  mx = s_max;
+  int bw = 0, toep = 1;
+  const int r = K / 2;
+  for (int i = threadIdx.x; i < K * K; i += blockDim.x) {
+    const int n = i / K, c = i - n * K;
+    const int d = c - n;
+    const double v = Lj[i];
+    if (fabs(v) > 1e-18 * mx) bw = max(bw, abs(d));
+    if (abs(d) <= MAXBW) {
+      Lb[((long long)j * K + n) * LBW + d + MAXBW] = v;
+      const int rc = r + d;
+      if (rc >= 0 && rc < K) {
+        if (fabs(v - Lj[r * K + rc]) > 1e-13 * mx) toep = 0;
+      } else if (fabs(v) > 1e-18 * mx) {
+        toep = 0;
+      }
+    }
+  }
+  // zero the out-of-range band slots
+  for (int i = threadIdx.x; i < K * LBW; i += blockDim.x) {
+    const int n = i / LBW, d = i - n * LBW - MAXBW;
+    if (n + d < 0 || n + d >= K) Lb[((long long)j * K + n) * LBW + d + MAXBW] = 0.0;
+  }
+  if (bw) atomicMax(&info[0], bw);
+  if (!toep) atomicAnd(&info[1], 0);
+}
+
+int bdrt_model_prepare(bdrt_ctx* ctx, const bdrt_series_data* d, BdrtModel* m, size_t extra_ws_bytes,
+                       void** extra_ws) {
+  if (!d) BDRT_FAIL(ctx, BDRT_E_NULL, "null data");
+  if (!d->A || !d->Z || !d->freq || !d->L) BDRT_FAIL(ctx, BDRT_E_NULL, "bdrt_series_data: null matrix pointer");
+  const int base = d->model & 15;
+  if (base != BDRT_MODEL_SERIES)
+    BDRT_FAIL(ctx, BDRT_E_UNSUPPORTED, "model id %d: only the Series family is implemented in this build", d->model);
+  if (d->model & ~(15 | BDRT_MODEL_POS | BDRT_MODEL_OUTLIERS)) BDRT_FAIL(ctx, BDRT_E_MODEL, "unknown model flags");
+  if (d->Nf < 2 || d->K < 3 || d->B < 0 || d->Nf > 4096 || d->K > 4096) BDRT_FAIL(ctx, BDRT_E_SIZE, "bad Nf/K/B");
+  if (!(d->sigma_min >= 0) || !(d->ups_alpha > 0) || !(d->ups_beta > 0) || !(d->induc_scale > 0))
+    BDRT_FAIL(ctx, BDRT_E_SIZE, "model constants must be positive");
+  memset(m, 0, sizeof(*m));
+  m->flags = ((d->model & BDRT_MODEL_POS) ? F_POS : 0) | ((d->model & BDRT_MODEL_OUTLIERS) ? F_OUT : 0);
+  m->Nf = d->Nf;
+  m->K = d->K;
+  m->B = d->B;
+  m->A = d->A;
+  m->A_stride = d->per_spectrum_grid ? (long long)2 * d->Nf * d->K : 0;
+  m->freq = d->freq;
+  m->f_stride = d->per_spectrum_grid ? d->Nf : 0;
+  m->Z = d->Z;
+  m->sigma_min2 = d->sigma_min * d->sigma_min;
+  m->ups_alpha = d->ups_alpha;
+  m->ups_beta = d->ups_beta;
+  m->induc_scale = d->induc_scale;
+  m->so_lambda = d->sigma_out_lambda;
+  m->so_alpha = d->sigma_out_alpha;
+  m->so_beta = d->sigma_out_beta;
+  const int eng = bdrt_model_layout(m);
+  if ((size_t)eng * 8 > (size_t)ctx->smem_optin)
+    BDRT_FAIL(ctx, BDRT_E_SMEM, "problem needs %zu B of shared memory per CTA, device offers %d", (size_t)eng * 8,
+              ctx->smem_optin);
+  // workspace: [info (16 B) | Lb | extra]
+  const size_t lb_bytes = (size_t)3 * d->K * LBW * sizeof(double);
+  const size_t head = 256 + ((lb_bytes + 255) & ~(size_t)255);
+  int rc = bdrt_ws_reserve(ctx, head + extra_ws_bytes);
+  if (rc) return rc;
+  int* info = (int*)ctx->ws;
+  double* Lb = (double*)((char*)ctx->ws + 256);
+  const int init[2] = {0, 1};
+  BDRT_CUDA(ctx, cudaMemcpyAsync(info, init, sizeof(init), cudaMemcpyHostToDevice, ctx->stream));
+  band_prep_kernel<<<3, 256, 0, ctx->stream>>>(d->L, d->K, Lb, info);
+  ctx->launches++;
+  BDRT_CUDA(ctx, cudaGetLastError());
+  int hinfo[2];
+  BDRT_CUDA(ctx, cudaMemcpyAsync(hinfo, info, sizeof(hinfo), cudaMemcpyDeviceToHost, ctx->stream));
+  BDRT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  if (hinfo[0] > MAXBW)
+    BDRT_FAIL(ctx, BDRT_E_UNSUPPORTED,
+              "penalty matrices L0/L1/L2 are not banded within %d off-diagonals (found %d): epsilon is too small "
+              "relative to the basis spacing for this build",
+              MAXBW, hinfo[0]);
+  m->bw = hinfo[0];
+  m->toeplitz = hinfo[1] && (d->K >= 2 * hinfo[0] + 1);
+  m->Lb = Lb;
+  if (extra_ws) *extra_ws = (char*)ctx->ws + head;
+  return BDRT_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// log_prob + gradient test hook
+// ---------------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(NTHREADS, 1)
+logpost_kernel(BdrtModel m, const double* u, const int* spec, int n_cols, int jacobian, double* lp, double* grad,
+               int cta_per_spec) {
+  extern __shared__ double sm[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (!cta_per_spec) {
+    engine_load(m, sm, 0);
+    const int ngroups = (n_cols + NSLOT - 1) / NSLOT;
+    for (int gidx = blockIdx.x; gidx < ngroups; gidx += gridDim.x) {
+      const int c = gidx * NSLOT + warp;
+      const bool active = c < n_cols;
+      const int b = active ? (spec ? spec[c] : c % m.B) : 0;
+      const double v = engine_eval(m, sm, active, u + (long long)c * m.D, grad + (long long)c * m.D,
+                                   m.Z + (long long)b * m.N2, jacobian);
+      if (active && lane == 0) lp[c] = v;
+    }
+  } else {
+    // per-spectrum grids: the 8 slots of a CTA must share A, so one CTA handles the columns of one spectrum
+    for (int b = blockIdx.x; b < m.B; b += gridDim.x) {
+      engine_load(m, sm, b);
+      // columns of spectrum b are those with spec[c] == b; spec == NULL means c % B == b
+      int c = (spec ? 0 : b) - (spec ? 1 : m.B);
+      bool more = true;
+      while (more) {
+        // every warp scans for the next (warp+1)-th matching column after c: simple sequential scan, uniform per CTA
+        int found[NSLOT];
+        int nf = 0;
+        int cc = c;
+        while (nf < NSLOT) {
+          cc += spec ? 1 : m.B;
+          if (cc >= n_cols) break;
+          if (!spec || spec[cc] == b) found[nf++] = cc;
+        }
+        more = (nf == NSLOT);
+        c = nf ? found[nf - 1] : c;
+        const bool active = warp < nf;
+        const int col = active ? found[warp] : 0;
+        const double v = engine_eval(m, sm, active, u + (long long)col * m.D, grad + (long long)col * m.D,
+                                     m.Z + (long long)b * m.N2, jacobian);
+        if (active && lane == 0) lp[col] = v;
+      }
+      cta_sync();
+    }
+  }
+}
+
+extern "C" int bdrt_logpost_grad(bdrt_ctx* ctx, const bdrt_series_data* data, const double* u, const int* spec,
+                                 int n_cols, int jacobian, double* lp, double* grad) {
+  if (!ctx) return BDRT_E_NULL;
+  if (!u || !lp || !grad) BDRT_FAIL(ctx, BDRT_E_NULL, "bdrt_logpost_grad: null pointer");
+  if (n_cols < 0) BDRT_FAIL(ctx, BDRT_E_SIZE, "n_cols < 0");
+  BdrtModel m;
+  int rc = bdrt_model_prepare(ctx, data, &m, 0, nullptr);
+  if (rc) return rc;
+  if (n_cols == 0 || data->B == 0) return BDRT_OK;
+  const size_t smem = (size_t)m.oUser * sizeof(double);
+  BDRT_CUDA(ctx, cudaFuncSetAttribute(logpost_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int grid;
+  if (data->per_spectrum_grid)
+    grid = data->B < ctx->sm_count ? data->B : ctx->sm_count;
+  else {
+    const int ngroups = (n_cols + NSLOT - 1) / NSLOT;
+    grid = ngroups < ctx->sm_count ? ngroups : ctx->sm_count;
+  }
+  logpost_kernel<<<grid, NTHREADS, smem, ctx->stream>>>(m, u, spec, n_cols, jacobian, lp, grad,
+                                                        data->per_spectrum_grid);
+  ctx->launches++;
+  BDRT_CUDA(ctx, cudaGetLastError());
+  return BDRT_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// constrain: unconstrained -> the constrained / transformed parameters the reference reads back
+// (Series_modelcode.txt:37-50; Inverter._extract_parameter, inversion.py:2494-2519)
+// one warp per point; plain FP64 FMA dot products (this is a read-out, not the hot loop)
+// ---------------------------------------------------------------------------------------------------------------------
+__global__ void constrain_kernel(BdrtModel m, const double* u, const int* spec, int n, double* out, int P) {
+  const int lane = threadIdx.x & 31;
+  const long long c = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (c >= n) return;
+  const int K = m.K, Nf = m.Nf;
+  const bool pos = m.flags & F_POS, outl = m.flags & F_OUT;
+  const double* uc = u + c * m.D;
+  double* o = out + c * P;
+  const int b = spec ? spec[c] : (int)(c % m.B);
+  const double* A = m.A + (long long)b * m.A_stride;
+  const double* f = m.freq + (long long)b * m.f_stride;
+  for (int k = lane; k < K; k += 32) o[k] = pos ? exp(uc[2 + k]) : uc[2 + k];
+  const double Rinf = 100.0 * exp(uc[0]), induc = exp(uc[1]) * m.induc_scale;
+  const double sr = 0.05 * exp(uc[2 + K]), ap = 0.05 * exp(uc[3 + K]), are = 0.05 * exp(uc[4 + K]),
+               aim = 0.05 * exp(uc[5 + K]);
+  if (lane == 0) {
+    o[K] = Rinf;
+    o[K + 1] = induc;
+    o[K + 2] = sr;
+    o[K + 3] = ap;
+    o[K + 4] = are;
+    o[K + 5] = aim;
+  }
+  __syncwarp();
+  for (int nn = lane; nn < Nf; nn += 32) {
+    double zre = 0, zim = 0;
+    for (int k = 0; k < K; ++k) {
+      const double xk = pos ? exp(uc[2 + k]) : uc[2 + k];
+      zre = fma(A[(long long)nn * K + k], xk, zre);
+      zim = fma(A[(long long)(Nf + nn) * K + k], xk, zim);
+    }
+    zre += Rinf;
+    zim += induc * 2.0 * M_PI * f[nn];
+    double common = (are * zre) * (are * zre) + (aim * zim) * (aim * zim);
+    if (outl) {
+      const double so = 0.05 * exp(uc[m.off_so + nn]) * exp(uc[m.off_so + Nf + nn]);
+      o[K + 6 + 2 * Nf + nn] = so;
+      common += so * so;
+    }
+    o[K + 6 + nn] = sqrt(m.sigma_min2 + sr * sr + (ap * zre) * (ap * zre) + common);
+    o[K + 6 + Nf + nn] = sqrt(m.sigma_min2 + sr * sr + (ap * zim) * (ap * zim) + common);
+  }
+}
+
+extern "C" int bdrt_constrain(bdrt_ctx* ctx, const bdrt_series_data* data, const double* u, const int* spec, int n,
+                              double* out) {
+  if (!ctx) return BDRT_E_NULL;
+  if (!u || !out) BDRT_FAIL(ctx, BDRT_E_NULL, "bdrt_constrain: null pointer");
+  BdrtModel m;
+  int rc = bdrt_model_prepare(ctx, data, &m, 0, nullptr);
+  if (rc) return rc;
+  if (n <= 0) return BDRT_OK;
+  const int P = bdrt_num_outputs(data);
+  constrain_kernel<<<(n + 3) / 4, 128, 0, ctx->stream>>>(m, u, spec, n, out, P);
+  ctx->launches++;
+  BDRT_CUDA(ctx, cudaGetLastError());
+  return BDRT_OK;
+}

@@ -1,0 +1,97 @@
+"""Line-by-line torch transcription of the Stan programs, differentiated by autograd.
+
+TEST INFRASTRUCTURE ONLY (see oracle/__init__.py).  Independent second statement of the density used to check the
+hand-derived gradient in oracle/model.py: every line below names the Stan line it transcribes
+(bayes_drt/stan_model_files/Series_modelcode.txt, Series_outliers_modelcode.txt).
+"""
+import math
+
+import torch
+
+
+def _inv_gamma_lpdf(y, a, b):
+    # Stan: inv_gamma_lpdf = a log b - lgamma(a) - (a+1) log y - b / y ; '~' drops the first two (data-only) terms
+    return torch.sum(-(a + 1) * torch.log(y) - b / y)
+
+
+def _normal_lpdf(y, mu, sigma):
+    # '~' drops -0.5 log(2 pi)
+    return torch.sum(-torch.log(sigma) - 0.5 * ((y - mu) / sigma) ** 2)
+
+
+def _std_normal_lpdf(y):
+    return torch.sum(-0.5 * y ** 2)
+
+
+def logpost_literal(u, d, jacobian=False):
+    """u: torch float64 tensor (requires_grad ok); d: dict from oracle.model.prep_series."""
+    K, Nf = d['K'], d['Nf']
+    t = lambda a: torch.as_tensor(a, dtype=torch.float64)
+    A, Z, freq = t(d['A']), t(d['Z']), t(d['freq'])
+    L0, L1, L2 = t(d['L0']), t(d['L1']), t(d['L2'])
+    N = 2 * Nf
+    # transformed data (Series_modelcode.txt:18-23)
+    Rinf_vec = torch.cat((torch.ones(Nf, dtype=torch.float64), torch.zeros(Nf, dtype=torch.float64)))
+    induc_vec = torch.cat((torch.zeros(Nf, dtype=torch.float64), 2 * math.pi * freq))
+    # parameters (Series_modelcode.txt:24-36): lower=0 -> exp transform, log-Jacobian = u
+    pos = 0
+    logjac = torch.zeros((), dtype=torch.float64)
+
+    def take(n, lower0):
+        nonlocal pos, logjac
+        raw = u[pos:pos + n]
+        pos += n
+        if lower0:
+            logjac = logjac + raw.sum()
+            return torch.exp(raw)
+        return raw
+
+    Rinf_raw = take(1, True)[0]
+    induc_raw = take(1, True)[0]
+    x = take(K, d['pos'])
+    sigma_res_raw = take(1, True)[0]
+    alpha_prop_raw = take(1, True)[0]
+    alpha_re_raw = take(1, True)[0]
+    alpha_im_raw = take(1, True)[0]
+    if d['outliers']:
+        sigma_out_raw = take(Nf, True)
+        sigma_out_scale = take(Nf, True)
+    ups_raw = take(K, True)
+    d0 = take(1, True)[0]
+    d1 = take(1, True)[0]
+    d2 = take(1, True)[0]
+    # transformed parameters (Series_modelcode.txt:37-54)
+    Rinf = Rinf_raw * 100
+    induc = induc_raw * d['induc_scale']
+    q = torch.sqrt(d0 * (L0 @ x) ** 2 + d1 * (L1 @ x) ** 2 + d2 * (L2 @ x) ** 2)
+    sigma_res = sigma_res_raw * 0.05
+    alpha_prop = alpha_prop_raw * 0.05
+    alpha_re = alpha_re_raw * 0.05
+    alpha_im = alpha_im_raw * 0.05
+    Z_hat = A @ x + Rinf * Rinf_vec + induc * induc_vec
+    Z_hat_re = torch.cat((Z_hat[:Nf], Z_hat[:Nf]))
+    Z_hat_im = torch.cat((Z_hat[Nf:], Z_hat[Nf:]))
+    var = d['sigma_min'] ** 2 + sigma_res ** 2 + (alpha_prop * Z_hat) ** 2 + (alpha_re * Z_hat_re) ** 2 \
+        + (alpha_im * Z_hat_im) ** 2
+    if d['outliers']:
+        sigma_out = sigma_out_raw * sigma_out_scale * 0.05  # Series_outliers_modelcode.txt:45
+        var = var + torch.cat((sigma_out, sigma_out)) ** 2  # :49-51
+    sigma_tot = torch.sqrt(var)
+    ups = ups_raw * 0.15
+    dups = 0.5 * (ups[1:-1] - 0.5 * (ups[:-2] + ups[2:])) / ups[1:-1]
+    # model (Series_modelcode.txt:55-69)
+    lp = _inv_gamma_lpdf(d0, 5.0, 5.0) + _inv_gamma_lpdf(d1, 5.0, 5.0) + _inv_gamma_lpdf(d2, 5.0, 5.0)
+    lp = lp + _inv_gamma_lpdf(ups_raw, d['ups_alpha'], d['ups_beta'])
+    lp = lp + _std_normal_lpdf(Rinf_raw) + _std_normal_lpdf(induc_raw)
+    lp = lp + _normal_lpdf(q, 0.0, ups)
+    lp = lp + _std_normal_lpdf(dups)
+    lp = lp + _normal_lpdf(Z, Z_hat, sigma_tot)
+    lp = lp + _std_normal_lpdf(sigma_res_raw) + _std_normal_lpdf(alpha_prop_raw) + _std_normal_lpdf(alpha_re_raw) \
+        + _std_normal_lpdf(alpha_im_raw)
+    if d['outliers']:
+        lp = lp + torch.sum(-d['sigma_out_lambda'] * sigma_out_raw)  # exponential(lambda), log(lambda) dropped
+        lp = lp + _inv_gamma_lpdf(sigma_out_scale, d['sigma_out_alpha'], d['sigma_out_beta'])
+    if jacobian:
+        lp = lp + logjac
+    assert pos == u.numel()
+    return lp
