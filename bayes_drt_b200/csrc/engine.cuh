@@ -44,6 +44,9 @@ struct BdrtModel {
   double sigma_min2, ups_alpha, ups_beta, induc_scale, so_lambda, so_alpha, so_beta;
   // shared-memory carve-up, in doubles
   int oA, oXV, oZG, oSt, oTap, oOm, oUser;
+  int xoff;  // offset of the data inside an X/V row (= bw: zero margin for the stencils)
+  int ws;    // stride of one stencil scratch vector (K + 2 bw, zero margins)
+  int st;    // per-slot scratch size
 };
 
 static inline int bdrt_pad_stride(int n) {  // smallest s >= n with s % 16 in {4, 12}
@@ -60,8 +63,13 @@ static inline int bdrt_model_layout(BdrtModel* m) {
   m->n2pad4 = (m->N2 + 3) / 4 * 4;
   m->n2pad8 = (m->N2 + 7) / 8 * 8;
   m->lda = bdrt_pad_stride(m->K);
-  int mx = m->kpad4 > m->n2pad4 ? m->kpad4 : m->n2pad4;
-  m->ldxv = bdrt_pad_stride(mx);
+  m->xoff = m->bw;
+  int kx = m->kpad4 > m->K + m->bw ? m->kpad4 : m->K + m->bw;
+  int mx = kx > m->n2pad4 ? kx : m->n2pad4;
+  m->ldxv = bdrt_pad_stride(m->xoff + mx);
+  m->ws = m->K + 2 * m->bw;
+  // per-slot scratch: W0 | W1 | W2 (ws each) | ups (K) | 1/ups (K) | scalars (16) | sigma_out raw, scale (2 Nf)
+  m->st = 3 * m->ws + 2 * m->K + 16 + ((m->flags & F_OUT) ? 2 * m->Nf : 0);
   int mz = m->kpad8 > m->n2pad8 ? m->kpad8 : m->n2pad8;
   m->ldzg = mz + 4;  // % 8 == 4
   m->off_so = 6 + m->K;
@@ -72,7 +80,7 @@ static inline int bdrt_model_layout(BdrtModel* m) {
   m->oA = o;   o += m->n2pad8 * m->lda + 8;
   m->oXV = o;  o += NSLOT * m->ldxv;
   m->oZG = o;  o += NSLOT * m->ldzg;
-  m->oSt = o;  o += NSLOT * 4 * m->K;
+  m->oSt = o;  o += NSLOT * m->st;
   m->oTap = o; o += 3 * LBW;
   m->oOm = o;  o += m->Nf;
   o = (o + 1) & ~1;
@@ -104,6 +112,7 @@ __device__ inline void engine_load(const BdrtModel& m, double* sm, long long spe
   }
   for (int i = tid; i < NSLOT * m.ldxv; i += NTHREADS) sm[m.oXV + i] = 0.0;
   for (int i = tid; i < NSLOT * m.ldzg; i += NTHREADS) sm[m.oZG + i] = 0.0;
+  for (int i = tid; i < NSLOT * m.st; i += NTHREADS) sm[m.oSt + i] = 0.0;
   // Toeplitz taps: row K/2 of the banded copies
   for (int i = tid; i < 3 * LBW; i += NTHREADS) {
     const int j = i / LBW, d = i - j * LBW;
@@ -114,133 +123,189 @@ __device__ inline void engine_load(const BdrtModel& m, double* sm, long long spe
   cta_sync();
 }
 
-__device__ __forceinline__ double tap_at(const BdrtModel& m, const double* sTap, int j, int row, int d) {
-  // L_j[row][row + d]
-  return m.toeplitz ? sTap[j * LBW + d + MAXBW] : __ldg(m.Lb + ((long long)j * m.K + row) * LBW + d + MAXBW);
-}
-
 // log p(u) and d/du for the slot of the calling warp; all NWARP warps of the CTA must call it together.
 //   active : this slot has a point to evaluate (inactive slots only help with the matrix products)
 //   u, grad: the slot's D-vectors (generic pointers: shared or global)
 //   Zs     : the slot's stacked scaled spectrum [N2] (global)
-// Returns lp (non-finite lp or gradient entries must be checked by the caller).
 //   nact/snap: optional CTA-wide "slots still working" counter; *snap receives its value at a point where no warp can
 //           be modifying it (between the first and last barrier), so every warp of the CTA reads the same value.
+// Returns lp (non-finite lp or gradient entries must be checked by the caller).
 __device__ inline double engine_eval(const BdrtModel& m, double* sm, bool active, const double* u, double* grad,
                                      const double* Zs, int jacobian, const volatile int* nact = nullptr,
                                      int* snap = nullptr) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int slot = warp;
-  const int K = m.K, Nf = m.Nf;
+  const int K = m.K, Nf = m.Nf, bw = m.bw;
   const bool pos = m.flags & F_POS, outl = m.flags & F_OUT;
   double* sA = sm + m.oA;
-  double* sX = sm + m.oXV + slot * m.ldxv;
+  double* sX = sm + m.oXV + slot * m.ldxv + m.xoff;  // x_k at sX[k], zero margins of width bw on both sides
   double* sZ = sm + m.oZG + slot * m.ldzg;
-  double* sW = sm + m.oSt + slot * 4 * K;  // w0 | w1 | w2 | ups
-  const double* sTap = sm + m.oTap;
+  double* sW = sm + m.oSt + slot * m.st + bw;         // W_j[k] at sW[j * ws + k], zero margins
+  double* sUps = sm + m.oSt + slot * m.st + 3 * m.ws;
+  double* sIu = sUps + K;
+  double* sTh = sIu + K;   // Rinf_raw, induc_raw, sigma_res_raw, alpha_prop/re/im_raw, d0, d1, d2
+  double* sSo = sTh + 16;  // sigma_out_raw [Nf], sigma_out_scale [Nf]
+  const double* sTap = sm + m.oTap + MAXBW;  // tap_j[d] at sTap[j * LBW + d]
   const double* sOm = sm + m.oOm;
   const double jac = jacobian ? 1.0 : 0.0;
 
   double lp = 0.0;
-  double rinf_raw = 0, ind_raw = 0, sr_raw = 0, ap_raw = 0, are_raw = 0, aim_raw = 0;
-  // ---------------------------------------------------------------- phase 1: x -> smem, priors, stencils (per slot)
+  // ---------------------------------------------------------------- phase 1: transforms, priors, stencils (per slot)
   if (active) {
-    rinf_raw = exp(u[0]);
-    ind_raw = exp(u[1]);
-    sr_raw = exp(u[2 + K]);
-    ap_raw = exp(u[3 + K]);
-    are_raw = exp(u[4 + K]);
-    aim_raw = exp(u[5 + K]);
-    const double d0 = exp(u[m.off_d]), d1 = exp(u[m.off_d + 1]), d2 = exp(u[m.off_d + 2]);
+    // 1a. theta = exp(u) for every lower=0 parameter, scattered to the slot's scratch (one coalesced pass over u)
     double ujac = 0.0;
-    for (int k = lane; k < m.kpad4; k += 32) {
-      double xv = 0.0;
-      if (k < K) {
-        const double uk = u[2 + k];
-        xv = pos ? exp(uk) : uk;
-        if (pos) ujac += uk;
-      }
-      sX[k] = xv;
+    for (int i = lane; i < m.D; i += 32) {
+      const double ui = u[i];
+      const bool isx = (i >= 2) && (i < 2 + K);
+      const double th = (isx && !pos) ? ui : exp(ui);
+      if (!isx || pos) ujac += ui;
+      if (isx)
+        sX[i - 2] = th;
+      else if (i < 2)
+        sTh[i] = th;
+      else if (i < 6 + K)
+        sTh[i - K] = th;  // 2+K..5+K -> 2..5
+      else if (i < m.off_ups)
+        sSo[i - m.off_so] = th;
+      else if (i < m.off_d) {
+        const double ups = 0.15 * th;
+        sUps[i - m.off_ups] = ups;
+        sIu[i - m.off_ups] = 1.0 / ups;
+      } else
+        sTh[6 + i - m.off_d] = th;
+    }
+    {
+      const int kend = (m.kpad4 > K + bw) ? m.kpad4 : K + bw;
+      for (int k = K + lane; k < kend; k += 32) sX[k] = 0.0;  // right margin (phase 3 of the previous call wrote V here)
     }
     __syncwarp();
+    const double d0 = sTh[6], d1 = sTh[7], d2 = sTh[8];
     double sa0 = 0, sa1 = 0, sa2 = 0;
-    const int bw = m.bw;
-    for (int k = lane; k < K; k += 32) {
-      double a0 = 0, a1 = 0, a2 = 0;
-      const int dlo = (k - bw < 0) ? -k : -bw, dhi = (k + bw > K - 1) ? (K - 1 - k) : bw;
-      for (int d = dlo; d <= dhi; ++d) {
-        const double xv = sX[k + d];
-        a0 = fma(tap_at(m, sTap, 0, k, d), xv, a0);
-        a1 = fma(tap_at(m, sTap, 1, k, d), xv, a1);
-        a2 = fma(tap_at(m, sTap, 2, k, d), xv, a2);
+    // 1b. a_j = L_j x (banded), q^2, hyper-priors, d lp / d ups, W_j = d_j a_j / ups^2
+    for (int kb = 0; kb < K; kb += 128) {
+      double a0[4] = {0, 0, 0, 0}, a1[4] = {0, 0, 0, 0}, a2[4] = {0, 0, 0, 0};
+      if (m.toeplitz) {
+        for (int d = -bw; d <= bw; ++d) {
+          const double t0 = sTap[d], t1 = sTap[LBW + d], t2 = sTap[2 * LBW + d];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const int k = kb + lane + 32 * j;
+            const double xv = (k < K) ? sX[k + d] : 0.0;
+            a0[j] = fma(t0, xv, a0[j]);
+            a1[j] = fma(t1, xv, a1[j]);
+            a2[j] = fma(t2, xv, a2[j]);
+          }
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int k = kb + lane + 32 * j;
+          if (k < K) {
+            const double* l0 = m.Lb + (long long)k * LBW + MAXBW;
+            const double* l1 = l0 + (long long)K * LBW;
+            const double* l2 = l1 + (long long)K * LBW;
+            for (int d = -bw; d <= bw; ++d) {
+              const double xv = sX[k + d];
+              a0[j] = fma(__ldg(l0 + d), xv, a0[j]);
+              a1[j] = fma(__ldg(l1 + d), xv, a1[j]);
+              a2[j] = fma(__ldg(l2 + d), xv, a2[j]);
+            }
+          }
+        }
       }
-      const double uk = u[m.off_ups + k];
-      ujac += uk;
-      const double ups_raw = exp(uk), ups = 0.15 * ups_raw;
-      const double iu = 1.0 / ups, iu2 = iu * iu;
-      const double q2 = d0 * a0 * a0 + d1 * a1 * a1 + d2 * a2 * a2;
-      // q ~ normal(0, ups): -1/2 q^2/ups^2 - log ups ;  ups_raw ~ inv_gamma(alpha, beta)
-      lp += -0.5 * q2 * iu2 - (LOG_015 + uk) - (m.ups_alpha + 1.0) * uk - m.ups_beta / ups_raw;
-      sa0 = fma(a0 * a0, iu2, sa0);
-      sa1 = fma(a1 * a1, iu2, sa1);
-      sa2 = fma(a2 * a2, iu2, sa2);
-      sW[k] = d0 * a0 * iu2;
-      sW[K + k] = d1 * a1 * iu2;
-      sW[2 * K + k] = d2 * a2 * iu2;
-      sW[3 * K + k] = ups;
-      grad[m.off_ups + k] = q2 * iu2 * iu - iu;  // d lp / d ups_k without the dups terms (finished below)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int k = kb + lane + 32 * j;
+        if (k < K) {
+          const double ups = sUps[k], iu = sIu[k], iu2 = iu * iu;
+          const double uk = u[m.off_ups + k];
+          const double q2 = d0 * a0[j] * a0[j] + d1 * a1[j] * a1[j] + d2 * a2[j] * a2[j];
+          // q ~ normal(0, ups): -1/2 q^2/ups^2 - log ups ;  ups_raw ~ inv_gamma(alpha, beta): -(alpha+1) log - beta/ups_raw
+          lp += -0.5 * q2 * iu2 - (LOG_015 + uk) - (m.ups_alpha + 1.0) * uk - m.ups_beta * 0.15 * iu;
+          sa0 = fma(a0[j] * a0[j], iu2, sa0);
+          sa1 = fma(a1[j] * a1[j], iu2, sa1);
+          sa2 = fma(a2[j] * a2[j], iu2, sa2);
+          sW[k] = d0 * a0[j] * iu2;
+          sW[m.ws + k] = d1 * a1[j] * iu2;
+          sW[2 * m.ws + k] = d2 * a2[j] * iu2;
+          // dups_j = 0.5 - 0.25 (ups_j + ups_{j+2}) / ups_{j+1},  j = 0..K-3   (Series_modelcode.txt:51-53)
+          double gu = q2 * iu2 * iu - iu;
+          if (k + 2 < K) {  // k is the left point of dups_k
+            const double e = 0.5 - 0.25 * (ups + sUps[k + 2]) * sIu[k + 1];
+            gu += e * 0.25 * sIu[k + 1];
+            lp += -0.5 * e * e;
+          }
+          if (k >= 1 && k + 1 < K) {  // middle point of dups_{k-1}
+            const double sum = sUps[k - 1] + sUps[k + 1];
+            const double e = 0.5 - 0.25 * sum * iu;
+            gu -= e * 0.25 * sum * iu2;
+          }
+          if (k >= 2) {  // right point of dups_{k-2}
+            const double e = 0.5 - 0.25 * (sUps[k - 2] + ups) * sIu[k - 1];
+            gu += e * 0.25 * sIu[k - 1];
+          }
+          grad[m.off_ups + k] = gu * ups - (m.ups_alpha + 1.0) + m.ups_beta * 0.15 * iu + jac;
+        }
+      }
     }
     __syncwarp();
-    const double* su = sW + 3 * K;
-    for (int k = lane; k < K; k += 32) {
-      // dups_j = 0.5 - 0.25 (ups_j + ups_{j+2}) / ups_{j+1},  j = 0..K-3   (Series_modelcode.txt:51-53)
-      double gu = grad[m.off_ups + k];
-      const double uk = su[k];
-      if (k + 2 < K) {  // k is the left point of dups_k
-        const double e = 0.5 - 0.25 * (uk + su[k + 2]) / su[k + 1];
-        gu += e * 0.25 / su[k + 1];
-        lp += -0.5 * e * e;
+    // 1c. prior part of d lp / d x:  - sum_j L_j^T W_j
+    for (int kb = 0; kb < K; kb += 128) {
+      double acc[4] = {0, 0, 0, 0};
+      if (m.toeplitz) {
+        double b1[4] = {0, 0, 0, 0}, b2[4] = {0, 0, 0, 0};
+        const double* w0 = sW + kb + lane;  // lanes past K read the (zero / neighbouring) scratch: never stored
+        for (int d = -bw; d <= bw; ++d) {   // row n = k + d, column k -> tap_j[-d]
+          const double t0 = sTap[-d], t1 = sTap[LBW - d], t2 = sTap[2 * LBW - d];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const int kc = (kb + lane + 32 * j < K) ? 32 * j : 0;
+            acc[j] = fma(t0, w0[kc + d], acc[j]);
+            b1[j] = fma(t1, w0[m.ws + kc + d], b1[j]);
+            b2[j] = fma(t2, w0[2 * m.ws + kc + d], b2[j]);
+          }
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[j] += b1[j] + b2[j];
+      } else {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int k = kb + lane + 32 * j;
+          if (k < K) {
+            const int dlo = (k - bw < 0) ? -k : -bw, dhi = (k + bw > K - 1) ? (K - 1 - k) : bw;
+            for (int d = dlo; d <= dhi; ++d) {
+              const double* l0 = m.Lb + (long long)(k + d) * LBW + MAXBW - d;
+              acc[j] = fma(__ldg(l0), sW[k + d], acc[j]);
+              acc[j] = fma(__ldg(l0 + (long long)K * LBW), sW[m.ws + k + d], acc[j]);
+              acc[j] = fma(__ldg(l0 + 2LL * K * LBW), sW[2 * m.ws + k + d], acc[j]);
+            }
+          }
+        }
       }
-      if (k >= 1 && k + 1 < K) {  // middle point of dups_{k-1}
-        const double sum = su[k - 1] + su[k + 1];
-        const double e = 0.5 - 0.25 * sum / uk;
-        gu -= e * 0.25 * sum / (uk * uk);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int k = kb + lane + 32 * j;
+        if (k < K) grad[2 + k] = -acc[j];
       }
-      if (k >= 2) {  // right point of dups_{k-2}
-        const double e = 0.5 - 0.25 * (su[k - 2] + uk) / su[k - 1];
-        gu += e * 0.25 / su[k - 1];
-      }
-      const double ups_raw = uk * (1.0 / 0.15);
-      grad[m.off_ups + k] = gu * uk - (m.ups_alpha + 1.0) + m.ups_beta / ups_raw + jac;
-      // prior part of d lp / d x_k:  - sum_j (L_j^T w_j)_k
-      double acc = 0.0;
-      const int dlo = (k - bw < 0) ? -k : -bw, dhi = (k + bw > K - 1) ? (K - 1 - k) : bw;
-      for (int d = dlo; d <= dhi; ++d) {  // row n = k + d, column k  ->  offset -d in that row
-        const int n = k + d;
-        acc = fma(tap_at(m, sTap, 0, n, -d), sW[n], acc);
-        acc = fma(tap_at(m, sTap, 1, n, -d), sW[K + n], acc);
-        acc = fma(tap_at(m, sTap, 2, n, -d), sW[2 * K + n], acc);
-      }
-      grad[2 + k] = -acc;
     }
     sa0 = warp_sum(sa0);
     sa1 = warp_sum(sa1);
     sa2 = warp_sum(sa2);
     if (lane == 0) {
-      // d_j ~ inv_gamma(5, 5): -6 log d - 5/d
+      // d_j ~ inv_gamma(5, 5): -6 log d - 5/d ; half-normal priors on the six scalar raw parameters
       lp += -6.0 * (u[m.off_d] + u[m.off_d + 1] + u[m.off_d + 2]) - 5.0 / d0 - 5.0 / d1 - 5.0 / d2;
-      lp += -0.5 * (rinf_raw * rinf_raw + ind_raw * ind_raw + sr_raw * sr_raw + ap_raw * ap_raw + are_raw * are_raw +
-                    aim_raw * aim_raw);
+      double ss = 0.0;
+#pragma unroll
+      for (int i = 0; i < 6; ++i) ss = fma(sTh[i], sTh[i], ss);
+      lp += -0.5 * ss;
       grad[m.off_d] = -0.5 * sa0 * d0 - 6.0 + 5.0 / d0 + jac;
       grad[m.off_d + 1] = -0.5 * sa1 * d1 - 6.0 + 5.0 / d1 + jac;
       grad[m.off_d + 2] = -0.5 * sa2 * d2 - 6.0 + 5.0 / d2 + jac;
-      ujac += u[0] + u[1] + u[2 + K] + u[3 + K] + u[4 + K] + u[5 + K] + u[m.off_d] + u[m.off_d + 1] + u[m.off_d + 2];
     }
-    if (outl)
-      for (int n = lane; n < 2 * Nf; n += 32) ujac += u[m.off_so + n];
     if (jacobian) lp += ujac;
   } else {
-    for (int k = lane; k < m.kpad4; k += 32) sX[k] = 0.0;
+    const int kend = (m.kpad4 > K + bw) ? m.kpad4 : K + bw;
+    for (int k = lane; k < kend; k += 32) sX[k] = 0.0;
   }
   cta_sync();
   if (snap) *snap = *nact;
@@ -248,7 +313,7 @@ __device__ inline double engine_eval(const BdrtModel& m, double* sm, bool active
   // ---------------------------------------------------------------- phase 2: Zhat = A X on the FP64 tensor cores
   const int g = lane >> 2, t = lane & 3;
   {
-    const double* bp = sm + m.oXV + g * m.ldxv + t;
+    const double* bp = sm + m.oXV + g * m.ldxv + m.xoff + t;
     double* zg = sm + m.oZG;
     const int nmt = m.n2pad8 >> 3;
     for (int mt = warp; mt < nmt; mt += 2 * NWARP) {
@@ -276,6 +341,8 @@ __device__ inline double engine_eval(const BdrtModel& m, double* sm, bool active
   // ---------------------------------------------------------------- phase 3: error model, residual weights (per slot)
   double* sV = sX;
   if (active) {
+    const double rinf_raw = sTh[0], ind_raw = sTh[1], sr_raw = sTh[2], ap_raw = sTh[3], are_raw = sTh[4],
+                 aim_raw = sTh[5];
     const double Rinf = 100.0 * rinf_raw, induc = ind_raw * m.induc_scale;
     const double sr = 0.05 * sr_raw, ap = 0.05 * ap_raw, are = 0.05 * are_raw, aim = 0.05 * aim_raw;
     const double base = m.sigma_min2 + sr * sr;
@@ -285,20 +352,19 @@ __device__ inline double engine_eval(const BdrtModel& m, double* sm, bool active
       const double om = sOm[n];
       const double zre = sZ[n] + Rinf, zim = sZ[Nf + n] + induc * om;
       double common = are2 * zre * zre + aim2 * zim * zim;
-      double so_raw = 0, so_scale = 0, so = 0, usc = 0;
+      double so_raw = 0, so_scale = 0, so = 0;
       if (outl) {
-        so_raw = exp(u[m.off_so + n]);
-        usc = u[m.off_so + Nf + n];
-        so_scale = exp(usc);
+        so_raw = sSo[n];
+        so_scale = sSo[Nf + n];
         so = 0.05 * so_raw * so_scale;  // Series_outliers_modelcode.txt:45
         common += so * so;
         // sigma_out_raw ~ exponential(lambda); sigma_out_scale ~ inv_gamma(alpha, beta)
-        lp += -m.so_lambda * so_raw - (m.so_alpha + 1.0) * usc - m.so_beta / so_scale;
+        lp += -m.so_lambda * so_raw - (m.so_alpha + 1.0) * u[m.off_so + Nf + n] - m.so_beta / so_scale;
       }
       const double s_re = base + ap2 * zre * zre + common, s_im = base + ap2 * zim * zim + common;
       const double i_re = 1.0 / s_re, i_im = 1.0 / s_im;
       const double r_re = Zs[n] - zre, r_im = Zs[Nf + n] - zim;
-      lp += -0.5 * (r_re * r_re * i_re + r_im * r_im * i_im) - 0.5 * (log(s_re) + log(s_im));
+      lp += -0.5 * (r_re * r_re * i_re + r_im * r_im * i_im) - 0.5 * log(s_re * s_im);
       const double g_re = 0.5 * r_re * r_re * i_re * i_re - 0.5 * i_re;
       const double g_im = 0.5 * r_im * r_im * i_im * i_im - 0.5 * i_im;
       const double G = g_re + g_im;
@@ -340,7 +406,7 @@ __device__ inline double engine_eval(const BdrtModel& m, double* sm, bool active
 
   // ---------------------------------------------------------------- phase 4: GX = A^T V on the FP64 tensor cores
   {
-    const double* bp = sm + m.oXV + g * m.ldxv + t;
+    const double* bp = sm + m.oXV + g * m.ldxv + m.xoff + t;
     double* zg = sm + m.oZG;
     const int nmt = m.kpad8 >> 3;
     for (int mt = warp; mt < nmt; mt += 2 * NWARP) {

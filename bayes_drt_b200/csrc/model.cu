@@ -117,10 +117,6 @@ int bdrt_model_prepare(bdrt_ctx* ctx, const bdrt_series_data* d, BdrtModel* m, s
   m->so_lambda = d->sigma_out_lambda;
   m->so_alpha = d->sigma_out_alpha;
   m->so_beta = d->sigma_out_beta;
-  const int eng = bdrt_model_layout(m);
-  if ((size_t)eng * 8 > (size_t)ctx->smem_optin)
-    BDRT_FAIL(ctx, BDRT_E_SMEM, "problem needs %zu B of shared memory per CTA, device offers %d", (size_t)eng * 8,
-              ctx->smem_optin);
   // workspace: [info (16 B) | Lb | extra]
   const size_t lb_bytes = (size_t)3 * d->K * LBW * sizeof(double);
   const size_t head = 256 + ((lb_bytes + 255) & ~(size_t)255);
@@ -144,6 +140,10 @@ int bdrt_model_prepare(bdrt_ctx* ctx, const bdrt_series_data* d, BdrtModel* m, s
   m->bw = hinfo[0];
   m->toeplitz = hinfo[1] && (d->K >= 2 * hinfo[0] + 1);
   m->Lb = Lb;
+  const int eng = bdrt_model_layout(m);
+  if ((size_t)eng * 8 > (size_t)ctx->smem_optin)
+    BDRT_FAIL(ctx, BDRT_E_SMEM, "problem needs %zu B of shared memory per CTA, device offers %d", (size_t)eng * 8,
+              ctx->smem_optin);
   if (extra_ws) *extra_ws = (char*)ctx->ws + head;
   return BDRT_OK;
 }
