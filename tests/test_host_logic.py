@@ -1,0 +1,90 @@
+"""CPU: host-side logic of the package that needs no GPU -- shard arithmetic, the world_size-2 gather over gloo, the
+hash-based Stan-style random init, the ESS estimator against the oracle's, and the reference-interface error checks."""
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_shard_range_covers_everything():
+    from bayes_drt_b200.distributed import shard_range
+    for n in (0, 1, 7, 8, 100000):
+        for ws in (1, 2, 3, 8):
+            r = [shard_range(n, k, ws) for k in range(ws)]
+            assert r[0][0] == 0 and r[-1][1] == n
+            assert all(a[1] == b[0] for a, b in zip(r, r[1:]))
+            assert max(b - a for a, b in r) - min(b - a for a, b in r) <= 1
+
+
+def _worker(rank, ws, port, q):
+    sys.path.insert(0, ROOT)
+    import torch.distributed as dist
+    from bayes_drt_b200.distributed import gather_results, shard_range
+    dist.init_process_group('gloo', init_method=f'tcp://127.0.0.1:{port}', rank=rank, world_size=ws)
+    n_total = 11  # ragged
+    a, b = shard_range(n_total)
+    local = torch.arange(a, b, dtype=torch.float64)[:, None] * torch.ones(1, 3, dtype=torch.float64)
+    out = gather_results(local, n_total)
+    q.put((rank, out[:, 0].tolist()))
+    dist.destroy_process_group()
+
+
+def test_gather_results_world2_gloo():
+    ctx = mp.get_context('spawn')
+    q = ctx.Queue()
+    port = 29500 + os.getpid() % 2000
+    ps = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    [p.start() for p in ps]
+    res = [q.get(timeout=120) for _ in range(2)]
+    [p.join(60) for p in ps]
+    for rank, vals in res:
+        assert vals == [float(i) for i in range(11)]
+
+
+def test_hash_uniform_is_index_keyed():
+    from bayes_drt_b200.inverter import _hash_uniform
+    u = _hash_uniform(1234, 0, 1000, 209, 'cpu')
+    assert u.min() >= -2 and u.max() <= 2
+    assert abs(u.mean().item()) < 0.02 and abs(u.std().item() - 4 / 12 ** 0.5) < 0.02
+    # shard invariance: rows 300..400 generated on their own are identical
+    assert torch.equal(u[300:400], _hash_uniform(1234, 300, 100, 209, 'cpu'))
+    assert not torch.equal(u, _hash_uniform(1235, 0, 1000, 209, 'cpu'))
+    # no visible correlation between neighbouring coordinates
+    c = np.corrcoef(u[:, :-1].flatten().numpy(), u[:, 1:].flatten().numpy())[0, 1]
+    assert abs(c) < 0.01
+
+
+def test_ess_matches_oracle():
+    from bayes_drt_b200.diagnostics import ess_bulk
+    from oracle.nuts import ess_bulk as oess
+    rng = np.random.RandomState(0)
+    x = np.zeros((3, 4, 400))
+    for i, phi in enumerate((0.0, 0.6, 0.95)):
+        e = rng.standard_normal((4, 400))
+        for t in range(1, 400):
+            e[:, t] = phi * e[:, t - 1] + np.sqrt(1 - phi ** 2) * e[:, t]
+        x[i] = e
+    got = ess_bulk(torch.tensor(x)).numpy()
+    want = np.array([oess(x[i]) for i in range(3)])
+    assert np.allclose(got, want, rtol=0.02), (got, want)
+
+
+def test_reference_interface_errors_without_gpu():
+    from bayes_drt_b200 import matrices as m
+    with pytest.raises(ValueError):
+        m.construct_A(np.logspace(3, 0, 5), 'real', basis='Zic')
+    with pytest.raises(ValueError):
+        m.construct_A(np.logspace(3, 0, 5), 'real', kernel='DRT', dist_type='parallel')
+    with pytest.raises(ValueError):
+        m.construct_A(np.logspace(3, 0, 5), 'real', kernel='XYZ')
+    with pytest.raises(ValueError):
+        m.construct_M(np.logspace(3, 0, 5), order=3)
+    assert m.is_loguniform(np.logspace(3, 0, 5)) and m.is_loguniform([9.0, 5.0, 4.9, 1.0])  # the reference's quirk
+    r = m.rel_round(np.array([123456.789012345, 0.00123456789012345]), 10)
+    # utils.py:113-131: round(x, precision - floor(log10 x)) decimals
+    assert r[0] == 123456.78901 and r[1] == round(0.00123456789012345, 13)
