@@ -1,0 +1,183 @@
+"""Oracle restatement of the reference's hyper-parametric ridge fit (numpy, FP64).
+
+TEST INFRASTRUCTURE ONLY (see oracle/__init__.py).
+
+Follows Inverter.ridge_fit (inversion.py:142-900; default hyper-lambda path :489-753), _hyper_lambda_discrete
+(:947-954), _hyper_lambda_integral (:973-983), _convex_opt (:1043-1067), _format_weights (:2338-2395),
+_prep_matrices (:2127-2336) and the result rescaling (:875-898).  SURVEY appendix B has the same iteration in
+pseudo-code.
+
+The QP itself is cvxopt.solvers.qp in the reference (third-party, absent here: **parity unpinned**).  Each QP is
+strictly convex with simple bounds, so its solution is unique; the oracle solves it *exactly* by block principal
+pivoting (active-set with exact Cholesky solves, KKT residual ~1e-13), which is what cvxopt's interior-point iterates
+converge to within its own tolerances (abstol 1e-7, reltol 1e-6).
+
+Stop test of the hyper loop: the reference's ``mean(|(coef - prev)/prev|) < xtol`` evaluated with numpy semantics.
+With an exact solver, coefficients on the bound are exactly 0 in consecutive iterations, 0/0 = NaN, NaN < xtol is
+False, and the loop runs all ``max_iter`` iterations -- the reference only stops early through cvxopt's interior
+jitter (SURVEY section 7 hard part 1b).  The oracle and the CUDA kernel both implement exactly that numpy semantics.
+"""
+import numpy as np
+
+from . import matrices as om
+from .model import default_epsilon, default_tau, z_scale
+
+
+def qp_bound(P, q, lb, F0=None, max_iter=500):
+    """argmin 1/2 x'Px + q'x  s.t. x >= lb, by block principal pivoting (Judice & Pires 1994; Kim & Park 2011).
+    Returns (x, y, F, iters) with y = Px + q the multipliers (y >= 0 on the bound set, 0 on the free set F)."""
+    n = len(q)
+    F = np.zeros(n, dtype=bool) if F0 is None else F0.copy()
+    x = lb.copy()
+    tries, ninf = 3, n + 1
+    y = None
+    for it in range(1, max_iter + 1):
+        x = lb.copy()
+        if F.any():
+            rhs = -(q[F] + P[np.ix_(F, ~F)] @ lb[~F])
+            x[F] = np.linalg.solve(P[np.ix_(F, F)], rhs)
+        y = P @ x + q
+        y[F] = 0.0
+        tol_x = 1e-14 * max(np.max(np.abs(x)), 1e-300)
+        tol_y = 1e-12 * max(np.max(np.abs(q)), 1e-300)
+        V = (F & (x < lb - tol_x)) | (~F & (y < -tol_y))
+        nv = int(V.sum())
+        if nv == 0:
+            return x, y, F, it
+        if nv < ninf:
+            ninf, tries = nv, 3
+            F = F ^ V
+        elif tries >= 1:
+            tries -= 1
+            F = F ^ V
+        else:
+            i = np.max(np.nonzero(V)[0])  # backup rule: only the largest infeasible index
+            F[i] = ~F[i]
+    raise RuntimeError('block principal pivoting did not terminate')
+
+
+def format_weights(Z, weights):
+    """inversion.py:2350-2380, part='both': returns complex weight vector (real part weights Z', imag part Z'')."""
+    n = len(Z)
+    if weights is None or (isinstance(weights, str) and weights == 'unity'):
+        return np.ones(n) * (1 + 1j)
+    if weights == 'modulus':
+        return (1 + 1j) / np.sqrt(np.real(Z * Z.conjugate()))
+    if weights == 'Orazem':
+        return (1 + 1j) / (np.abs(Z.real) + np.abs(Z.imag))
+    if weights == 'proportional':
+        return 1 / np.abs(Z.real) + 1j / np.abs(Z.imag)
+    raise ValueError(f'Invalid weights argument {weights}')
+
+
+def hyper_lambda_discrete(L, coef, hl_beta, lambda_0):
+    Lx2 = (L @ coef) ** 2
+    lam = 1 / (Lx2 / (hl_beta - 1) + 1 / lambda_0)
+    return np.hstack(([1, 1], lam))
+
+
+def hyper_lambda_integral(M, coef, lam_sqrt, hl_beta, lambda_0):
+    xlm = (coef * lam_sqrt)[:, None] * M * coef[None, :]
+    xlm = xlm - np.diag(np.diagonal(xlm))
+    C = np.sum(xlm, axis=0)
+    a = hl_beta / 2
+    b = 0.5 * (2 * a - 2) / lambda_0
+    d = coef ** 2 * np.diagonal(M) + 2 * b
+    return (C ** 2 - np.sign(C) * C * np.sqrt(4 * d * (2 * a - 2) + C ** 2) + 2 * d * (2 * a - 2)) / (2 * d ** 2)
+
+
+def prep(freq, Z, basis_freq=None, epsilon=None, penalty='discrete', weights=None, scale_Z=True, fit_inductance=True):
+    """Scaled / weighted augmented system of ridge_fit (inversion.py:370-447)."""
+    freq = np.asarray(freq, dtype=np.float64)
+    Z = np.asarray(Z, dtype=np.complex128)
+    idx = np.argsort(freq)[::-1]
+    freq, Z = freq[idx], Z[idx]
+    zs = z_scale(Z) if scale_Z else 1.0
+    Zs = Z / zs
+    tau = default_tau(freq) if basis_freq is None else 1.0 / (2 * np.pi * np.asarray(basis_freq, dtype=np.float64))
+    eps = default_epsilon(tau) if epsilon is None else float(epsilon)
+    w = format_weights(Zs, weights)
+    K = len(tau)
+    A_re = np.zeros((len(freq), K + 2))
+    A_im = np.zeros((len(freq), K + 2))
+    A_re[:, 2:] = om.construct_A(freq, 'real', tau=tau, epsilon=eps)
+    A_im[:, 2:] = om.construct_A(freq, 'imag', tau=tau, epsilon=eps)
+    A_re[:, 0] = 1
+    if fit_inductance:
+        A_im[:, 1] = 2 * np.pi * freq * 1e-4
+    bf = 1 / (2 * np.pi * tau)
+    Pen = np.zeros((3, K + 2, K + 2))
+    Lmat = np.zeros((3, K, K + 2))
+    for o in range(3):
+        if penalty == 'integral':
+            Pen[o, 2:, 2:] = om.construct_M(bf, order=o, epsilon=eps)
+        else:
+            Lmat[o, :, 2:] = om.construct_L(bf, tau=tau, epsilon=eps, order=o)
+            Pen[o] = Lmat[o].T @ Lmat[o]
+    return dict(freq=freq, tau=tau, epsilon=eps, Z_scale=zs, WA_re=w.real[:, None] * A_re, WA_im=w.imag[:, None] * A_im,
+                WZ_re=w.real * Zs.real, WZ_im=w.imag * Zs.imag, Pen=Pen, Lmat=Lmat, K=K)
+
+
+def ridge_fit(freq, Z, basis_freq=None, epsilon=None, penalty='discrete', reg_ord=2, L1_penalty=0.0, scale_Z=True,
+              nonneg=True, weights=None, hl_beta=2.5, lambda_0=1e-2, xtol=1e-3, max_iter=20, fit_inductance=True,
+              preset=None, x0=None, return_history=False):
+    """Default hyper-lambda path of Inverter.ridge_fit.  Returns dict(coef [K], R_inf, inductance, scaled_coef [K+2],
+    lam [3, K+2], iters, converged)."""
+    if preset == 'Huang':  # inversion.py:278-282
+        penalty, hl_beta, lambda_0, weights = 'integral', 2.5, 1e-2, 'modulus'
+    elif preset is not None:
+        raise NotImplementedError(preset)
+    p = prep(freq, Z, basis_freq, epsilon, penalty, weights, scale_Z, fit_inductance)
+    n = p['K'] + 2
+    frac = np.zeros(3)
+    if isinstance(reg_ord, int):
+        frac[reg_ord] = 1
+    else:
+        frac[:] = reg_ord
+    G0 = p['WA_re'].T @ p['WA_re'] + p['WA_im'].T @ p['WA_im']
+    L1_vec = np.ones(n) * np.pi ** 0.5 / p['epsilon'] * L1_penalty
+    L1_vec[0:2] = 0
+    q = -p['WA_re'].T @ p['WZ_re'] - p['WA_im'].T @ p['WZ_im'] + L1_vec
+    lb = np.zeros(n) if nonneg else np.r_[0.0, 0.0, -10.0 * np.ones(n - 2)]
+    coef = np.zeros(n) + 1e-6 if x0 is None else np.asarray(x0, dtype=np.float64).copy()
+    lam = np.ones((3, n)) * lambda_0
+    F = None
+    hist = []
+    converged = False
+    it = 0
+    while it < max_iter:
+        prev = coef.copy()
+        for o in range(3):
+            if frac[o] > 0:
+                if penalty == 'discrete':
+                    lam[o] = hyper_lambda_discrete(p['Lmat'][o][:, 2:], prev[2:], hl_beta, lambda_0)
+                else:
+                    factor = (100.0, 10.0, 1.0)[o]
+                    lv = hyper_lambda_integral(p['Pen'][o], factor * prev, np.sqrt(lam[o]), hl_beta, lambda_0)
+                    lv[lv <= 0] = 1e-15
+                    lam[o] = lv
+        Pm = G0.copy()
+        for o in range(3):
+            if frac[o] > 0:
+                s = np.sqrt(lam[o])
+                Pm += frac[o] * (s[:, None] * p['Pen'][o] * s[None, :])
+        coef, y, F, nit = qp_bound(Pm, q, lb, F0=F)
+        hist.append(coef.copy())
+        with np.errstate(all='ignore'):
+            delta = (coef - prev) / prev
+            if not fit_inductance:
+                delta[1] = 0
+            if np.mean(np.abs(delta)) < xtol:
+                converged = True
+                break
+        it += 1
+    iters = len(hist)
+    out_coef = coef * p['Z_scale']
+    out_coef[1] *= 1e-4
+    if not fit_inductance:
+        out_coef[1] = 0
+    res = dict(coef=out_coef[2:], R_inf=out_coef[0], inductance=out_coef[1], scaled_coef=coef, lam=lam, iters=iters,
+               converged=converged, Z_scale=p['Z_scale'], prep=p)
+    if return_history:
+        res['history'] = hist
+    return res

@@ -1,0 +1,83 @@
+"""GPU: batched bound-constrained QP and the hyper-lambda ridge loop against the oracle (exact active-set restatement
+of the reference's cvxopt path).  North-star tolerance: ridge solutions within 1e-6 (relative to the largest
+coefficient); QP KKT residual <= 1e-9."""
+import numpy as np
+import pytest
+import torch
+
+from helpers import load_spectrum
+from oracle import ridge as oridge
+
+pytestmark = pytest.mark.gpu
+NAMES = ['ZARC_uniform_0.25', 'ZARC-RL_uniform_0.25', '2ZARC_uniform_0.25', 'Gerischer_uniform_0.25']
+
+
+def test_qp_bound_random_problems():
+    from bayes_drt_b200 import capi
+    rng = np.random.RandomState(0)
+    for n, B in ((7, 5), (40, 9), (103, 300)):
+        A = rng.standard_normal((B, 2 * n, n))
+        P = np.einsum('bij,bik->bjk', A, A) + 1e-3 * np.eye(n)
+        q = rng.standard_normal((B, n)) * 3
+        lb = np.where(rng.rand(n) < 0.5, 0.0, -0.7)
+        x, kkt, iters = capi.qp_bound(torch.tensor(P), torch.tensor(q), torch.tensor(lb))
+        x, kkt = x.cpu().numpy(), kkt.cpu().numpy()
+        for b in range(0, B, max(1, B // 7)):
+            xo, yo, F, it = oridge.qp_bound(P[b], q[b], lb)
+            assert np.max(np.abs(x[b] - xo)) <= 1e-9 * max(1.0, np.max(np.abs(xo)))
+        assert np.all(kkt <= 1e-9 * (1 + np.abs(q).max()))
+        assert np.all(x >= lb - 1e-12)
+
+
+@pytest.mark.parametrize('kw', [dict(), dict(preset='Huang'),
+                                dict(penalty='integral', lambda_0=1, hl_beta=5, weights='modulus'),
+                                dict(nonneg=False), dict(reg_ord=[0.2, 0.3, 0.5], L1_penalty=0.01)])
+def test_ridge_fit_matches_oracle(kw):
+    from bayes_drt_b200 import Inverter
+    freq = load_spectrum(NAMES[0])[0]
+    Z = np.stack([load_spectrum(n)[1] for n in NAMES])
+    inv = Inverter()
+    inv.ridge_fit(freq, Z, **kw)
+    coef = inv.distribution_fits['DRT']['coef'].cpu().numpy()
+    for b in range(len(NAMES)):
+        o = oridge.ridge_fit(freq, Z[b], **kw)
+        scale = np.max(np.abs(o['coef']))
+        assert inv._ridge_iters[b].item() == o['iters']
+        assert np.max(np.abs(coef[b] - o['coef'])) <= 1e-6 * scale, (b, np.max(np.abs(coef[b] - o['coef'])) / scale)
+        assert abs(inv.R_inf[b].item() - o['R_inf']) <= 1e-6 * max(abs(o['R_inf']), scale)
+        assert abs(inv.inductance[b].item() - o['inductance']) <= 1e-6 * max(abs(o['inductance']), 1e-6)
+        lam = inv.distribution_fits['DRT']['lambda_vectors'][b].cpu().numpy()
+        assert np.allclose(lam, o['lam'], rtol=1e-5, atol=1e-12)
+
+
+def test_ridge_single_spectrum_and_plain_ridge():
+    """single-spectrum call returns reference shapes (numpy); hyper_lambda=False is one QP at lambda_0."""
+    from bayes_drt_b200 import Inverter
+    freq, Z = load_spectrum('ZARC_uniform_0.25')
+    inv = Inverter()
+    with pytest.warns(UserWarning):  # 'did not converge within 20 iterations' (exact zeros -> NaN stop test)
+        inv.ridge_fit(freq, Z)
+    assert isinstance(inv.distribution_fits['DRT']['coef'], np.ndarray) and inv.distribution_fits['DRT']['coef'].shape == (101,)
+    assert inv.fit_type == 'ridge' and abs(inv.R_inf - 0.9914) < 2e-4  # SURVEY section 7 1b sanity value
+    rp = inv.predict_Rp()
+    assert abs(rp - 1.0204) < 2e-4
+    inv.ridge_fit(freq, Z, hyper_lambda=False, lambda_0=1e-2)
+    p = oridge.prep(freq, Z)
+    G0 = p['WA_re'].T @ p['WA_re'] + p['WA_im'].T @ p['WA_im']
+    q = -p['WA_re'].T @ p['WZ_re'] - p['WA_im'].T @ p['WZ_im']
+    xo, _, _, _ = oridge.qp_bound(G0 + 1e-2 * p['Pen'][2], q, np.zeros(len(q)))
+    assert np.max(np.abs(inv.distribution_fits['DRT']['scaled_coef'] - xo)) <= 1e-8 * np.max(np.abs(xo))
+
+
+def test_ridge_unsupported_options_are_loud():
+    from bayes_drt_b200 import Inverter
+    freq, Z = load_spectrum('ZARC_uniform_0.25')
+    inv = Inverter()
+    for kw in (dict(preset='Ciucci'), dict(hyper_weights=True, hyper_lambda=False), dict(hl_solution='lm'),
+               dict(dZ=True), dict(penalty='cholesky')):
+        with pytest.raises(NotImplementedError):
+            inv.ridge_fit(freq, Z, **kw)
+    with pytest.raises(ValueError):
+        inv.ridge_fit(freq, Z, hl_beta=0.5)
+    with pytest.raises(ValueError):
+        inv.ridge_fit(freq, Z, preset='nope')
