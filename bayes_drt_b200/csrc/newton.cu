@@ -1,0 +1,265 @@
+// Damped-Newton polish of MAP estimates (not in the reference).
+//
+// Stan's L-BFGS stops on a relative-objective / relative-gradient test well short of the optimum of this posterior
+// (condition number ~3e7; SURVEY.md section 7 hard part 1: x is still ~3e-3 away), so "MAP within 1e-5" is defined
+// against the exact optimum, which for the default model is unique.  This kernel takes the L-BFGS result there:
+// Levenberg-damped Newton on f = -log_prob(jacobian=false) with a forward-difference Hessian of the analytic gradient.
+//
+// Mapping: one CTA per spectrum.  The 8 column slots of the engine evaluate 8 Hessian columns (perturbed points) per
+// cooperative engine_eval(), so one Hessian is ceil(D/8) evaluations; the packed D(D+1)/2 factorisation overlays the
+// CTA's shared memory when it fits (the resident A is simply re-loaded afterwards), else it lives in L2-resident scratch.
+//
+// Parameters whose optimum is on the boundary of a lower=0 constraint (theta = exp(u) -> 0, e.g. inductance or
+// alpha_im for most spectra) have no finite optimum in u: Newton moves them by -1 per iteration.  Once the Newton step
+// of such a coordinate is < -0.5 and it is already below exp(-6), it is sent to u = -40 (theta ~ 4e-18, i.e. 0 to
+// double precision in every formula) and frozen; it is released again if its gradient ever asks for a larger theta.
+#include "engine.cuh"
+
+#define U_FLOOR (-40.0)
+
+namespace {
+
+__device__ __forceinline__ int pk(int i, int k) { return i * (i + 1) / 2 + k; }  // packed lower triangle, k <= i
+
+// Cholesky of the packed lower triangle Hp (n x n) by the whole CTA, then r <- Hp^-1 r by warp 0.
+__device__ void chol_solve_packed(double* Hp, int n, double* r, volatile int* flag) {
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  for (int j = 0; j < n; ++j) {
+    if (tid == 0) {
+      double d = Hp[pk(j, j)];
+      if (!(d > 0.0)) { d = 1e-300; *flag = 1; }
+      Hp[pk(j, j)] = sqrt(d);
+    }
+    __syncthreads();
+    const double dj = 1.0 / Hp[pk(j, j)];
+    for (int i = j + 1 + tid; i < n; i += NTHREADS) Hp[pk(i, j)] *= dj;
+    __syncthreads();
+    for (int i = j + 1 + warp; i < n; i += NWARP) {
+      const double lij = Hp[pk(i, j)];
+      double* row = Hp + pk(i, 0);
+      for (int k = j + 1 + lane; k <= i; k += 32) row[k] = fma(-lij, Hp[pk(k, j)], row[k]);
+    }
+    __syncthreads();
+  }
+  if (tid < 32) {
+    for (int j = 0; j < n; ++j) {
+      const double zj = r[j] / Hp[pk(j, j)];
+      __syncwarp();
+      if (lane == 0) r[j] = zj;
+      for (int i = j + 1 + lane; i < n; i += 32) r[i] = fma(-Hp[pk(i, j)], zj, r[i]);
+      __syncwarp();
+    }
+    for (int j = n - 1; j >= 0; --j) {
+      const double xj = r[j] / Hp[pk(j, j)];
+      __syncwarp();
+      if (lane == 0) r[j] = xj;
+      const double* row = Hp + pk(j, 0);
+      for (int i = lane; i < j; i += 32) r[i] = fma(-row[i], xj, r[i]);
+      __syncwarp();
+    }
+  }
+  __syncthreads();
+}
+
+}  // namespace
+
+__global__ void __launch_bounds__(NTHREADS, 1)
+newton_kernel(BdrtModel m, bdrt_newton_opts o, double* __restrict__ U, double* lp_out, double* gnorm_out, int* iters_out,
+              int* neval_out, double* scratch, long long scratch_per_cta, int chol_in_smem, int Dpad) {
+  extern __shared__ double sm[];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int D = m.D;
+  // per-CTA global scratch: H rows [D*Dpad] | packed factor [D(D+1)/2] | u g step utry gtry [5 Dpad] | slot vectors
+  // [8 * 2 * Dpad] | frozen [Dpad ints]
+  double* sc = scratch + (long long)blockIdx.x * scratch_per_cta;
+  double* H = sc;
+  double* Hp_g = H + (long long)D * Dpad;
+  double* u = Hp_g + (long long)D * (D + 1) / 2 + 1;
+  double* g = u + Dpad;
+  double* step = g + Dpad;
+  double* utry = step + Dpad;
+  double* gtry = utry + Dpad;
+  double* sv = gtry + Dpad;
+  double* my_u = sv + (long long)warp * 2 * Dpad;
+  double* my_g = my_u + Dpad;
+  int* frozen = (int*)(sv + (long long)NSLOT * 2 * Dpad);
+  double* Hp = chol_in_smem ? sm : Hp_g;
+  __shared__ double s_val[8];
+  __shared__ int s_flag[4];
+  const bool pos = m.flags & F_POS;
+
+  for (int b = blockIdx.x; b < m.B; b += gridDim.x) {
+    engine_load(m, sm, 0);
+    const double* Zs = m.Z + (long long)b * m.N2;
+    for (int i = tid; i < D; i += NTHREADS) { u[i] = U[(long long)b * D + i]; frozen[i] = 0; }
+    __syncthreads();
+    double mu = 1e-6, f = 0.0, gmax = 0.0;
+    int it = 0, neval = 0;
+    bool stop = false;
+    // f, g at u (slot 0 evaluates; the other slots idle through the barriers)
+    {
+      const double lp = engine_eval(m, sm, warp == 0, u, g, Zs, 0);
+      ++neval;
+      if (tid == 0) s_val[0] = -lp;
+      __syncthreads();
+      f = s_val[0];
+      for (int i = tid; i < D; i += NTHREADS) g[i] = -g[i];
+      __syncthreads();
+    }
+    if (!isfinite(f)) stop = true;
+    while (!stop) {
+      // ---- convergence test on the non-frozen coordinates; release frozen ones whose gradient points inward
+      double mymax = 0.0;
+      for (int i = tid; i < D; i += NTHREADS) {
+        if (frozen[i] && g[i] < -o.gtol) frozen[i] = 0;
+        if (!frozen[i]) mymax = fmax(mymax, fabs(g[i]));
+      }
+      mymax = warp_max(mymax);
+      __syncthreads();
+      if (lane == 0) s_val[warp] = mymax;
+      __syncthreads();
+      gmax = 0.0;
+      for (int w = 0; w < NWARP; ++w) gmax = fmax(gmax, s_val[w]);
+      __syncthreads();
+      if (gmax < o.gtol || it >= o.max_iter) break;
+      ++it;
+      // ---- forward-difference Hessian, 8 columns per cooperative evaluation: H[j][:] = (g(u + h e_j) - g(u)) / h
+      for (int j0 = 0; j0 < D; j0 += NSLOT) {
+        const int j = j0 + warp;
+        const bool act = (j < D) && !frozen[j];
+        double h = 0.0;
+        if (act) {
+          for (int i = lane; i < D; i += 32) my_u[i] = u[i];
+          __syncwarp();
+          h = o.fd_step * fmax(1.0, fabs(u[j]));
+          if (lane == 0) my_u[j] = u[j] + h;
+          __syncwarp();
+          h = (u[j] + h) - u[j];
+        }
+        engine_eval(m, sm, act, my_u, my_g, Zs, 0);
+        if (act) {
+          const double ih = 1.0 / h;
+          for (int i = lane; i < D; i += 32) H[(long long)j * Dpad + i] = (-my_g[i] - g[i]) * ih;
+        } else if (j < D) {
+          for (int i = lane; i < D; i += 32) H[(long long)j * Dpad + i] = 0.0;
+        }
+        neval += (D - j0 < NSLOT) ? (D - j0) : NSLOT;
+      }
+      __syncthreads();
+      // ---- damped solves until a step is accepted
+      bool accepted = false;
+      for (int tries = 0; tries < 12 && !accepted; ++tries) {
+        // packed factor <- sym(H) + mu |diag|, frozen rows/cols -> identity
+        for (int idx = tid; idx < D * (D + 1) / 2; idx += NTHREADS) {
+          // invert idx -> (i, k): i = floor((sqrt(8 idx + 1) - 1)/2)
+          int i = (int)((sqrt(8.0 * idx + 1.0) - 1.0) * 0.5);
+          while (i * (i + 1) / 2 > idx) --i;
+          while ((i + 1) * (i + 2) / 2 <= idx) ++i;
+          const int k = idx - i * (i + 1) / 2;
+          double v;
+          if (frozen[i] || frozen[k])
+            v = (i == k) ? 1.0 : 0.0;
+          else {
+            v = 0.5 * (H[(long long)i * Dpad + k] + H[(long long)k * Dpad + i]);
+            if (i == k) v += mu * fmax(fabs(v), 1e-12);
+          }
+          Hp[idx] = v;
+        }
+        for (int i = tid; i < D; i += NTHREADS) step[i] = frozen[i] ? 0.0 : -g[i];
+        if (tid == 0) s_flag[0] = 0;
+        __syncthreads();
+        chol_solve_packed(Hp, D, step, s_flag);
+        const bool notpd = s_flag[0] != 0;
+        if (chol_in_smem) engine_load(m, sm, 0);  // the factor overlaid the engine's resident operands
+        if (notpd) { mu *= 10.0; __syncthreads(); continue; }
+        // tail jump of boundary-bound lower=0 coordinates (see header)
+        for (int i = tid; i < D; i += NTHREADS) {
+          const bool expc = pos || !(i >= 2 && i < 2 + m.K);
+          double s = step[i];
+          int jump = 0;
+          if (expc && !frozen[i] && s < -0.5 && u[i] + s < -6.0) { s = U_FLOOR - u[i]; jump = 1; }
+          utry[i] = u[i] + s;
+          gtry[i] = (double)jump;  // temporarily: jump flags
+        }
+        __syncthreads();
+        double gd = 0.0;
+        for (int i = tid; i < D; i += NTHREADS) gd = fma(g[i], utry[i] - u[i], gd);
+        gd = warp_sum(gd);
+        if (lane == 0) s_val[warp] = gd;
+        __syncthreads();
+        gd = 0.0;
+        for (int w = 0; w < NWARP; ++w) gd += s_val[w];
+        __syncthreads();
+        // remember the jump flags (gtry is about to be overwritten by the gradient)
+        for (int i = tid; i < D; i += NTHREADS) step[i] = gtry[i];
+        __syncthreads();
+        const double lp = engine_eval(m, sm, warp == 0, utry, gtry, Zs, 0);
+        ++neval;
+        if (tid == 0) s_val[0] = -lp;
+        __syncthreads();
+        const double ftry = s_val[0];
+        __syncthreads();
+        if (isfinite(ftry) && ftry <= f + 1e-4 * gd + 1e-13 * fabs(f)) {
+          for (int i = tid; i < D; i += NTHREADS) {
+            u[i] = utry[i];
+            g[i] = -gtry[i];
+            if (step[i] != 0.0) frozen[i] = 1;
+          }
+          f = ftry;
+          mu = fmax(mu * 0.1, 1e-12);
+          accepted = true;
+        } else {
+          mu *= 10.0;
+          if (mu > 1e12) break;
+        }
+        __syncthreads();
+      }
+      if (!accepted) stop = true;
+    }
+    for (int i = tid; i < D; i += NTHREADS) U[(long long)b * D + i] = u[i];
+    if (tid == 0) {
+      if (lp_out) lp_out[b] = -f;
+      if (gnorm_out) gnorm_out[b] = gmax;
+      if (iters_out) iters_out[b] = it;
+      if (neval_out) neval_out[b] = neval;
+    }
+    __syncthreads();
+  }
+}
+
+extern "C" void bdrt_newton_default_opts(bdrt_newton_opts* o) {
+  if (!o) return;
+  o->max_iter = 40;
+  o->gtol = 1e-9;
+  o->fd_step = 1e-6;
+}
+
+extern "C" int bdrt_map_newton(bdrt_ctx* ctx, const bdrt_series_data* data, const bdrt_newton_opts* opts, double* u,
+                               double* lp, double* gnorm, int* iters, int* n_eval) {
+  if (!ctx) return BDRT_E_NULL;
+  if (!data || !opts || !u) BDRT_FAIL(ctx, BDRT_E_NULL, "bdrt_map_newton: null pointer");
+  if (data->per_spectrum_grid)
+    BDRT_FAIL(ctx, BDRT_E_UNSUPPORTED, "bdrt_map_newton: per-spectrum grids are not implemented in this build");
+  if (opts->max_iter < 0 || !(opts->fd_step > 0)) BDRT_FAIL(ctx, BDRT_E_SIZE, "bad newton options");
+  const int D = bdrt_num_params(data);
+  const int Dpad = (D + 1) & ~1;
+  const int grid = data->B < ctx->sm_count ? data->B : ctx->sm_count;
+  const long long per_cta = (long long)D * Dpad + (long long)D * (D + 1) / 2 + 2 + 5LL * Dpad + (long long)NSLOT * 2 * Dpad +
+                            Dpad;  // doubles (frozen ints fit in the last Dpad doubles)
+  BdrtModel m;
+  void* extra = nullptr;
+  int rc = bdrt_model_prepare(ctx, data, &m, (size_t)(grid > 0 ? grid : 1) * per_cta * sizeof(double), &extra);
+  if (rc) return rc;
+  if (data->B == 0) return BDRT_OK;
+  const long long packed = (long long)D * (D + 1) / 2;
+  const long long smem_doubles = (long long)ctx->smem_optin / 8 - 64;
+  const int in_smem = packed <= smem_doubles;
+  size_t smem = (size_t)m.oUser * sizeof(double);
+  if (in_smem && (size_t)packed * 8 > smem) smem = (size_t)packed * 8;
+  BDRT_CUDA(ctx, cudaFuncSetAttribute(newton_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  newton_kernel<<<grid, NTHREADS, smem, ctx->stream>>>(m, *opts, u, lp, gnorm, iters, n_eval, (double*)extra, per_cta,
+                                                       in_smem, Dpad);
+  ctx->launches++;
+  BDRT_CUDA(ctx, cudaGetLastError());
+  return BDRT_OK;
+}

@@ -73,3 +73,34 @@ def test_lbfgs_batch_independent_of_batching():
     assert torch.equal(r_all['u'][5:8], r_sub['u'])
     assert torch.equal(r_all['lp'][5:8], r_sub['lp'])
     assert torch.all(r_all['lp'] > prob.logpost_grad(u0)[0])
+
+
+def test_map_polish_reaches_the_oracle_optimum():
+    """North star: MAP DRT coefficients within 1e-5 (relative to the largest coefficient) -- evaluated, as SURVEY section 7
+    prescribes, against the oracle's tightly converged optimum (damped Newton to max|grad| < 1e-9), which is unique for
+    the default model; both sides start from the same L-BFGS result.  R_inf and the error-model scales likewise;
+    boundary parameters (inductance, alpha_*: theta -> 0) are compared absolutely."""
+    from oracle import newton as onew
+    names = ['ZARC_uniform_0.25', '2ZARC_uniform_0.25']
+    freq = load_spectrum(names[0])[0]
+    ds = oracle_batch(freq, [load_spectrum(n)[1] for n in names], mode='optimize')
+    prob = gpu_problem(ds)
+    rng = np.random.RandomState(0)
+    u0 = torch.tensor(rng.uniform(-2, 2, (2, prob.D)))
+    r = prob.map_lbfgs(u0, max_iter=50000)
+    p = prob.map_newton(r['u'])
+    assert (p['gnorm'] < 1e-7).all(), p['gnorm']
+    assert (p['lp'] >= r['lp'] - 1e-9).all()
+    out = prob.split_outputs(prob.constrain(p['u']))
+    for b in range(2):
+        with np.errstate(all='ignore'):
+            o = onew.polish(_func(ds[b]), r['u'][b].cpu().numpy(), max_iter=80)
+        assert o['gnorm'] < 1e-8
+        c = omod.constrain(o['x'], ds[b])
+        x = out['x'][b].cpu().numpy()
+        assert abs(p['lp'][b].item() + o['f']) <= 1e-10 * abs(o['f'])
+        assert np.max(np.abs(x - c['x'])) <= 1e-5 * np.max(np.abs(c['x'])), np.max(np.abs(x - c['x'])) / np.max(np.abs(c['x']))
+        assert abs(out['Rinf'][b].item() - c['Rinf']) <= 1e-5 * c['Rinf']
+        assert abs(out['sigma_res'][b].item() - c['sigma_res']) <= 1e-5 * c['sigma_res'] + 1e-9
+        for nm in ('induc', 'alpha_prop', 'alpha_re', 'alpha_im'):
+            assert abs(out[nm][b].item() - c[nm]) <= 1e-5 * abs(c[nm]) + 1e-7, nm
