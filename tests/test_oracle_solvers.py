@@ -1,0 +1,99 @@
+"""CPU: the oracle's solver restatements on problems with known answers -- Stan-semantics L-BFGS, the exact
+bound-constrained QP (vs scipy's NNLS / bounded least squares), the hyper-lambda ridge loop (vs the survey's measured
+values on the reference's simulated spectrum), and the NUTS restatement on a Gaussian with known moments."""
+import numpy as np
+from scipy.optimize import lsq_linear, nnls
+
+from helpers import load_spectrum
+from oracle import lbfgs as olb, nuts as onuts, ridge as oridge
+
+
+def test_lbfgs_quadratic_and_rosenbrock():
+    rng = np.random.RandomState(0)
+    Q = rng.standard_normal((12, 12))
+    H = Q @ Q.T + 0.1 * np.eye(12)
+    b = rng.standard_normal(12)
+    r = olb.minimize(lambda x: (0.5 * x @ H @ x - b @ x, H @ x - b), np.zeros(12), max_iter=500)
+    assert np.allclose(r['x'], np.linalg.solve(H, b), atol=1e-3)  # Stan stops on tol_rel_obj = 1e4 eps
+    assert r['code'] in (olb.TERM_ABSF, olb.TERM_RELF, olb.TERM_ABSGRAD, olb.TERM_RELGRAD, olb.TERM_ABSX)
+
+    def rosen(x):
+        f = np.sum(100 * (x[1:] - x[:-1] ** 2) ** 2 + (1 - x[:-1]) ** 2)
+        g = np.zeros_like(x)
+        g[:-1] = -400 * x[:-1] * (x[1:] - x[:-1] ** 2) - 2 * (1 - x[:-1])
+        g[1:] += 200 * (x[1:] - x[:-1] ** 2)
+        return f, g
+    r = olb.minimize(rosen, np.full(6, -1.2), max_iter=5000)
+    assert np.allclose(r['x'], 1.0, atol=1e-3) and r['iters'] < 5000
+    # an objective that is not finite at the trial step is retried with a shorter step (Stan: line-search restarts)
+    r = olb.minimize(lambda x: None if x[0] > 5 else (0.5 * x @ x, x.copy()), np.array([4.0, -3.0]), max_iter=200)
+    assert np.allclose(r['x'], 0.0, atol=1e-4)
+    # iteration cap
+    r = olb.minimize(rosen, np.full(6, -1.2), max_iter=3)
+    assert r['code'] == olb.TERM_MAXIT and r['iters'] == 3
+
+
+def test_qp_bound_is_exact():
+    rng = np.random.RandomState(1)
+    for n, m in ((8, 20), (40, 30), (103, 162)):
+        A = rng.standard_normal((m, n))
+        y = rng.standard_normal(m)
+        P = A.T @ A + 1e-3 * np.eye(n)
+        q = -A.T @ y
+        x, mult, F, it = oridge.qp_bound(P, q, np.zeros(n))
+        # KKT: x >= 0, mult = Px + q >= 0, complementarity
+        assert x.min() >= 0 and mult.min() >= -1e-10 * np.abs(q).max()
+        assert np.max(np.abs(x * mult)) <= 1e-10 * np.abs(q).max()
+        assert np.allclose(mult, P @ x + q, atol=1e-10)
+        # the same problem as an NNLS:  min |[A; sqrt(1e-3) I] x - [y; 0]|
+        xa, _ = nnls(np.vstack((A, np.sqrt(1e-3) * np.eye(n))), np.r_[y, np.zeros(n)], maxiter=10 * n)
+        assert np.max(np.abs(x - xa)) <= 1e-8 * max(1.0, np.abs(xa).max())
+        # general lower bounds (the reference's nonneg=False box: c[0:2] >= 0, c[2:] >= -10, inversion.py:1054-1064)
+        lb = np.r_[0.0, 0.0, np.full(n - 2, -0.05)]
+        x2, mult2, F2, _ = oridge.qp_bound(P, q, lb)
+        ref = lsq_linear(np.vstack((A, np.sqrt(1e-3) * np.eye(n))), np.r_[y, np.zeros(n)], bounds=(lb, np.inf),
+                         method='bvls' if n < 50 else 'trf', tol=1e-14).x
+        assert np.max(np.abs(x2 - ref)) <= 1e-5 * max(1.0, np.abs(ref).max())
+        assert (x2 >= lb - 1e-14).all()
+
+
+def test_ridge_loop_on_reference_spectrum():
+    """SURVEY section 7 (1b) [measured with the restated loop]: defaults give R_inf = 0.9914, R_p = 1.020 on
+    Z_ZARC_uniform_0.25 (truth 1, 1); init_from_ridge settings give R_inf = 0.9988, R_p = 1.004; with an exact QP
+    solver the numpy stop test never passes (0/0) and the loop runs max_iter iterations."""
+    freq, Z = load_spectrum('ZARC_uniform_0.25')
+    r = oridge.ridge_fit(freq, Z)
+    eps = r['prep']['epsilon']
+    Rp = r['coef'].sum() * np.sqrt(np.pi) / eps
+    assert abs(r['R_inf'] - 0.9914) < 2e-3 and abs(Rp - 1.020) < 3e-3
+    assert r['iters'] == 20 and not r['converged']
+    assert (r['coef'] >= 0).all() and (r['coef'] == 0).sum() > 5  # exact zeros on the active set
+    r2 = oridge.ridge_fit(freq, Z, penalty='integral', lambda_0=1.0, hl_beta=5.0, weights='modulus')
+    Rp2 = r2['coef'].sum() * np.sqrt(np.pi) / eps
+    assert abs(r2['R_inf'] - 0.9988) < 2e-3 and abs(Rp2 - 1.004) < 3e-3
+    # preset='Huang' == penalty integral, hl_beta 2.5, lambda_0 1e-2, modulus weights (inversion.py:278-282)
+    r3 = oridge.ridge_fit(freq, Z, preset='Huang')
+    r4 = oridge.ridge_fit(freq, Z, penalty='integral', weights='modulus')
+    assert np.array_equal(r3['coef'], r4['coef'])
+
+
+def test_nuts_restatement_on_gaussian():
+    sd = np.array([0.1, 1.0, 3.0, 10.0, 0.5])
+    mu = np.array([1.0, -2.0, 0.0, 5.0, 0.3])
+
+    def lg(u):
+        z = (u - mu) / sd
+        return -0.5 * z @ z, -z / sd
+    chains = [onuts.sample_chain(lg, np.random.RandomState(c).uniform(-2, 2, 5), warmup=200, samples=400, seed=c)
+              for c in range(4)]
+    x = np.stack([c['draws'] for c in chains])  # [4, 400, 5]
+    for c in chains:
+        assert c['n_divergent'] == 0 and 0.6 < c['accept'] <= 1.0
+        # the adapted diagonal metric approximates the variances (regularised towards 1e-3)
+        assert np.all(np.abs(np.log(c['inv_metric'] / sd ** 2)) < 1.2)
+    for i in range(5):
+        ess = onuts.ess_bulk(x[:, :, i])
+        assert ess > 200
+        m, s = x[:, :, i].mean(), x[:, :, i].std(ddof=1)
+        assert abs(m - mu[i]) < 5 * sd[i] / np.sqrt(ess)
+        assert abs(np.log(s / sd[i])) < 0.15
