@@ -17,6 +17,7 @@ struct bdrt_ctx {
   size_t ws_bytes;
   int sm_count;
   int smem_optin;  // max dynamic shared memory per block (opt-in), bytes
+  int smem_per_sm; // shared memory per SM, bytes
 };
 
 #define BDRT_FAIL(ctx, code, ...)                             \

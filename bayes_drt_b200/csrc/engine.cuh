@@ -32,7 +32,11 @@
 struct BdrtModel {
   int flags, Nf, K, N2, D, B;
   int lda, ldxv, ldzg;
-  int kpad4, kpad8, n2pad4, n2pad8;
+  int kpad4, kpad8;
+  int nfp;    // Nf rounded up to a multiple of 8: inside the engine the stacked vectors are [re: nfp | im: nfp]
+  int n2p;    // 2 * nfp
+  int toepA;  // A_re / A_im are Toeplitz (shared log-uniform grid): resident operand = two 1-D tables of length lt
+  int lt;     // nfp + kpad8
   int off_so, off_ups, off_d;
   int bw, toeplitz;
   const double* A;
@@ -60,24 +64,25 @@ static inline int bdrt_model_layout(BdrtModel* m) {
   m->N2 = 2 * m->Nf;
   m->kpad4 = (m->K + 3) / 4 * 4;
   m->kpad8 = (m->K + 7) / 8 * 8;
-  m->n2pad4 = (m->N2 + 3) / 4 * 4;
-  m->n2pad8 = (m->N2 + 7) / 8 * 8;
+  m->nfp = (m->Nf + 7) / 8 * 8;
+  m->n2p = 2 * m->nfp;
+  m->lt = m->nfp + m->kpad8;
   m->lda = bdrt_pad_stride(m->K);
   m->xoff = m->bw;
   int kx = m->kpad4 > m->K + m->bw ? m->kpad4 : m->K + m->bw;
-  int mx = kx > m->n2pad4 ? kx : m->n2pad4;
+  int mx = kx > m->n2p ? kx : m->n2p;
   m->ldxv = bdrt_pad_stride(m->xoff + mx);
   m->ws = m->K + 2 * m->bw;
   // per-slot scratch: W0 | W1 | W2 (ws each) | ups (K) | 1/ups (K) | scalars (16) | sigma_out raw, scale (2 Nf)
   m->st = 3 * m->ws + 2 * m->K + 16 + ((m->flags & F_OUT) ? 2 * m->Nf : 0);
-  int mz = m->kpad8 > m->n2pad8 ? m->kpad8 : m->n2pad8;
+  int mz = m->kpad8 > m->n2p ? m->kpad8 : m->n2p;
   m->ldzg = mz + 4;  // % 8 == 4
   m->off_so = 6 + m->K;
   m->off_ups = 6 + m->K + ((m->flags & F_OUT) ? 2 * m->Nf : 0);
   m->off_d = m->off_ups + m->K;
   m->D = m->off_d + 3;
   int o = 0;
-  m->oA = o;   o += m->n2pad8 * m->lda + 8;
+  m->oA = o;   o += m->toepA ? 2 * m->lt : m->n2p * m->lda + 8;
   m->oXV = o;  o += NSLOT * m->ldxv;
   m->oZG = o;  o += NSLOT * m->ldzg;
   m->oSt = o;  o += NSLOT * m->st;
@@ -105,10 +110,21 @@ __device__ inline void engine_load(const BdrtModel& m, double* sm, long long spe
   double* sA = sm + m.oA;
   const double* gA = m.A + spec * m.A_stride;
   const int tid = threadIdx.x;
-  const int rows = m.n2pad8;
-  for (int i = tid; i < rows * m.lda + 8; i += NTHREADS) {
-    const int r = i / m.lda, c = i - r * m.lda;
-    sA[i] = (r < m.N2 && c < m.K) ? gA[(long long)r * m.K + c] : 0.0;  // coalesced along c
+  if (m.toepA) {
+    // table of part p: T_p[(col - row) + nfp - 1] = A_p[row][col]; first row for col - row >= 0, first column below
+    for (int i = tid; i < 2 * m.lt; i += NTHREADS) {
+      const int p = i >= m.lt, d = i - p * m.lt - (m.nfp - 1);
+      double v = 0.0;
+      if (d >= 0 && d < m.K) v = gA[(long long)p * m.Nf * m.K + d];
+      else if (d < 0 && -d < m.Nf) v = gA[((long long)p * m.Nf - d) * m.K];
+      sA[i] = v;
+    }
+  } else {
+    for (int i = tid; i < m.n2p * m.lda + 8; i += NTHREADS) {
+      const int rp = i / m.lda, c = i - rp * m.lda;
+      const int p = rp >= m.nfp, r = rp - p * m.nfp;  // padded row -> (part, row)
+      sA[i] = (rp < m.n2p && r < m.Nf && c < m.K) ? gA[((long long)p * m.Nf + r) * m.K + c] : 0.0;  // coalesced along c
+    }
   }
   for (int i = tid; i < NSLOT * m.ldxv; i += NTHREADS) sm[m.oXV + i] = 0.0;
   for (int i = tid; i < NSLOT * m.ldzg; i += NTHREADS) sm[m.oZG + i] = 0.0;
@@ -130,6 +146,7 @@ __device__ inline void engine_load(const BdrtModel& m, double* sm, long long spe
 //   nact/snap: optional CTA-wide "slots still working" counter; *snap receives its value at a point where no warp can
 //           be modifying it (between the first and last barrier), so every warp of the CTA reads the same value.
 // Returns lp (non-finite lp or gradient entries must be checked by the caller).
+template <int TOEP>
 __device__ inline double engine_eval(const BdrtModel& m, double* sm, bool active, const double* u, double* grad,
                                      const double* Zs, int jacobian, const volatile int* nact = nullptr,
                                      int* snap = nullptr) {
@@ -315,12 +332,20 @@ __device__ inline double engine_eval(const BdrtModel& m, double* sm, bool active
   {
     const double* bp = sm + m.oXV + g * m.ldxv + m.xoff + t;
     double* zg = sm + m.oZG;
-    const int nmt = m.n2pad8 >> 3;
+    const int nmt = m.n2p >> 3;
     for (int mt = warp; mt < nmt; mt += 2 * NWARP) {
       const int mt2 = mt + NWARP;
       const bool two = mt2 < nmt;
-      const double* a0p = sA + (mt * 8 + g) * m.lda + t;
-      const double* a1p = sA + ((two ? mt2 : mt) * 8 + g) * m.lda + t;
+      const double *a0p, *a1p;
+      if (TOEP) {  // A_p[row][col] = T_p[col - row + nfp - 1]
+        const int r0 = mt * 8 + g, r1 = (two ? mt2 : mt) * 8 + g;
+        const int p0 = r0 >= m.nfp, p1 = r1 >= m.nfp;
+        a0p = sA + p0 * m.lt + (m.nfp - 1) - (r0 - p0 * m.nfp) + t;
+        a1p = sA + p1 * m.lt + (m.nfp - 1) - (r1 - p1 * m.nfp) + t;
+      } else {
+        a0p = sA + (mt * 8 + g) * m.lda + t;
+        a1p = sA + ((two ? mt2 : mt) * 8 + g) * m.lda + t;
+      }
       double c00 = 0, c01 = 0, c10 = 0, c11 = 0;
 #pragma unroll 5
       for (int kk = 0; kk < m.kpad4; kk += 4) {
@@ -350,7 +375,7 @@ __device__ inline double engine_eval(const BdrtModel& m, double* sm, bool active
     double Sv = 0, Swv = 0, Sg = 0, Sgz = 0, SGre = 0, SGim = 0;
     for (int n = lane; n < Nf; n += 32) {
       const double om = sOm[n];
-      const double zre = sZ[n] + Rinf, zim = sZ[Nf + n] + induc * om;
+      const double zre = sZ[n] + Rinf, zim = sZ[m.nfp + n] + induc * om;
       double common = are2 * zre * zre + aim2 * zim * zim;
       double so_raw = 0, so_scale = 0, so = 0;
       if (outl) {
@@ -371,7 +396,7 @@ __device__ inline double engine_eval(const BdrtModel& m, double* sm, bool active
       const double v_re = r_re * i_re + 2.0 * zre * (ap2 * g_re + are2 * G);
       const double v_im = r_im * i_im + 2.0 * zim * (ap2 * g_im + aim2 * G);
       sV[n] = v_re;
-      sV[Nf + n] = v_im;
+      sV[m.nfp + n] = v_im;
       Sv += v_re;
       Swv = fma(om, v_im, Swv);
       Sg += G;
@@ -384,7 +409,10 @@ __device__ inline double engine_eval(const BdrtModel& m, double* sm, bool active
         grad[m.off_so + Nf + n] = dso - (m.so_alpha + 1.0) + m.so_beta / so_scale + jac;
       }
     }
-    for (int n = m.N2 + lane; n < m.n2pad4; n += 32) sV[n] = 0.0;
+    for (int n = Nf + lane; n < m.nfp; n += 32) {  // padding rows of both parts
+      sV[n] = 0.0;
+      sV[m.nfp + n] = 0.0;
+    }
     Sv = warp_sum(Sv);
     Swv = warp_sum(Swv);
     Sg = warp_sum(Sg);
@@ -400,7 +428,7 @@ __device__ inline double engine_eval(const BdrtModel& m, double* sm, bool active
       grad[5 + K] = (0.1 * aim * SGim - aim_raw) * aim_raw + jac;
     }
   } else {
-    for (int n = lane; n < m.n2pad4; n += 32) sV[n] = 0.0;
+    for (int n = lane; n < m.n2p; n += 32) sV[n] = 0.0;
   }
   cta_sync();
 
@@ -412,15 +440,20 @@ __device__ inline double engine_eval(const BdrtModel& m, double* sm, bool active
     for (int mt = warp; mt < nmt; mt += 2 * NWARP) {
       const int mt2 = mt + NWARP;
       const bool two = mt2 < nmt;
-      const double* a0p = sA + t * m.lda + mt * 8 + g;             // A^T[kk0+g][i0+t] = A[i0+t][kk0+g]
-      const double* a1p = sA + t * m.lda + (two ? mt2 : mt) * 8 + g;
+      const int col0 = mt * 8 + g, col1 = (two ? mt2 : mt) * 8 + g;
       double c00 = 0, c01 = 0, c10 = 0, c11 = 0;
-      const int step = 4 * m.lda;
-#pragma unroll 5
-      for (int i0 = 0, ao = 0; i0 < m.n2pad4; i0 += 4, ao += step) {
-        const double b = bp[i0];
-        dmma(c00, c01, a0p[ao], b);
-        dmma(c10, c11, a1p[ao], b);
+      const int step = TOEP ? -4 : 4 * m.lda;
+#pragma unroll
+      for (int p = 0; p < 2; ++p) {  // A^T[col][row] = A_p[row][col], rows of part p
+        const double* ab = TOEP ? sA + p * m.lt + (m.nfp - 1) - t : sA + (p * m.nfp + t) * m.lda;
+        const double *a0p = ab + col0, *a1p = ab + col1;
+        const double* bq = bp + p * m.nfp;
+#pragma unroll 3
+        for (int i0 = 0, ao = 0; i0 < m.nfp; i0 += 4, ao += step) {
+          const double b = bq[i0];
+          dmma(c00, c01, a0p[ao], b);
+          dmma(c10, c11, a1p[ao], b);
+        }
       }
       zg[(2 * t) * m.ldzg + mt * 8 + g] = c00;
       zg[(2 * t + 1) * m.ldzg + mt * 8 + g] = c01;
@@ -449,3 +482,43 @@ __device__ inline double engine_eval(const BdrtModel& m, double* sm, bool active
 // host side (model.cu)
 int bdrt_model_prepare(bdrt_ctx* ctx, const bdrt_series_data* data, BdrtModel* m, size_t extra_ws_bytes,
                        void** extra_ws);
+
+// Shared-memory plan of a persistent solver kernel: the engine region plus as many of the solver's per-slot work
+// vectors (Dpad doubles each, NSLOT slots) as fit.  With Toeplitz-resident A two CTAs share an SM.
+struct BdrtPlan {
+  int ctas_per_sm, nvec;
+  size_t smem;
+};
+static inline BdrtPlan bdrt_plan(const bdrt_ctx* ctx, const BdrtModel& m, int Dpad, int nvec_max, int head_doubles) {
+  BdrtPlan pl;
+  pl.ctas_per_sm = m.toepA ? 2 : 1;
+  long long budget = ctx->smem_optin;
+  if (pl.ctas_per_sm == 2) {
+    const long long half = ctx->smem_per_sm / 2 - 1024;  // 1 KB per resident CTA is reserved by the system
+    if (half < budget) budget = half;
+    if ((long long)(m.oUser + head_doubles) * 8 > budget) {  // engine alone does not fit twice
+      pl.ctas_per_sm = 1;
+      budget = ctx->smem_optin;
+    }
+  }
+  long long nv = (budget / 8 - m.oUser - head_doubles) / ((long long)NSLOT * Dpad);
+  if (nv > nvec_max) nv = nvec_max;
+  if (nv < 0) nv = 0;
+  pl.nvec = (int)nv;
+  pl.smem = ((size_t)m.oUser + head_doubles + (size_t)NSLOT * pl.nvec * Dpad) * sizeof(double);
+  return pl;
+}
+
+// launch KERNEL<1> (Toeplitz-resident A) or KERNEL<0> (dense-resident A)
+#define BDRT_LAUNCH(ctx, m, KERNEL, grid, smem, ...)                                                         \
+  do {                                                                                                       \
+    if ((m).toepA) {                                                                                         \
+      BDRT_CUDA(ctx, cudaFuncSetAttribute(KERNEL<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(smem))); \
+      KERNEL<1><<<grid, NTHREADS, smem, (ctx)->stream>>>(__VA_ARGS__);                                       \
+    } else {                                                                                                 \
+      BDRT_CUDA(ctx, cudaFuncSetAttribute(KERNEL<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(smem))); \
+      KERNEL<0><<<grid, NTHREADS, smem, (ctx)->stream>>>(__VA_ARGS__);                                       \
+    }                                                                                                        \
+    (ctx)->launches++;                                                                                       \
+    BDRT_CUDA(ctx, cudaGetLastError());                                                                      \
+  } while (0)

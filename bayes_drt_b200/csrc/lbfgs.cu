@@ -47,9 +47,97 @@ __device__ double cubic_interp(double df0, double x1, double f1, double df1, dou
   return minX;
 }
 
+// L-BFGS two-loop recursion  pk = -H gk  over the history entries head-nh .. head-1 (mod H), newest first.
+// NC > 0: the search direction lives in registers (lane owns elements lane + 32 c, c < NC) and both history vectors
+// of an entry are fetched together, so each entry costs one L2 round trip instead of two and no shared-memory
+// traffic; the summation order is that of vdot(), so the result is bitwise that of the generic path (NC == 0).
+template <int NC>
+__device__ __forceinline__ void two_loop(const double* S, const double* Y, const double* rho, double* al,
+                                         const double* gk, double* pk, int D, int Dpad, int nh, int head, int H,
+                                         double gamma, int lane) {
+  if (NC == 0) {
+    for (int i = lane; i < D; i += 32) pk[i] = -gk[i];
+    __syncwarp();
+    for (int j = 0; j < nh; ++j) {  // newest -> oldest
+      const int h = (head - 1 - j + 2 * H) % H;
+      const double* Sh = S + (long long)h * Dpad;
+      const double* Yh = Y + (long long)h * Dpad;
+      const double a = rho[h] * vdot(Sh, pk, D, lane);
+      al[h] = a;
+      for (int i = lane; i < D; i += 32) pk[i] = fma(-a, Yh[i], pk[i]);
+      __syncwarp();
+    }
+    for (int i = lane; i < D; i += 32) pk[i] *= gamma;
+    __syncwarp();
+    for (int j = nh - 1; j >= 0; --j) {  // oldest -> newest
+      const int h = (head - 1 - j + 2 * H) % H;
+      const double* Sh = S + (long long)h * Dpad;
+      const double* Yh = Y + (long long)h * Dpad;
+      const double beta = rho[h] * vdot(Yh, pk, D, lane);
+      const double c = al[h] - beta;
+      for (int i = lane; i < D; i += 32) pk[i] = fma(c, Sh[i], pk[i]);
+      __syncwarp();
+    }
+    return;
+  }
+  constexpr int NCC = NC > 0 ? NC : 1;
+  double pr[NCC];
+#pragma unroll
+  for (int c = 0; c < NCC; ++c) {
+    const int i = lane + 32 * c;
+    pr[c] = (i < D) ? -gk[i] : 0.0;
+  }
+  for (int j = 0; j < nh; ++j) {  // newest -> oldest
+    const int h = (head - 1 - j + 2 * H) % H;
+    const double* Sh = S + (long long)h * Dpad;
+    const double* Yh = Y + (long long)h * Dpad;
+    double sv[NCC], yv[NCC];
+#pragma unroll
+    for (int c = 0; c < NCC; ++c) {
+      const int i = lane + 32 * c;
+      sv[c] = (i < D) ? Sh[i] : 0.0;
+      yv[c] = (i < D) ? Yh[i] : 0.0;
+    }
+    double d = 0.0;
+#pragma unroll
+    for (int c = 0; c < NCC; ++c) d = fma(sv[c], pr[c], d);
+    const double a = rho[h] * warp_sum(d);
+    al[h] = a;
+#pragma unroll
+    for (int c = 0; c < NCC; ++c) pr[c] = fma(-a, yv[c], pr[c]);
+  }
+#pragma unroll
+  for (int c = 0; c < NCC; ++c) pr[c] *= gamma;
+  for (int j = nh - 1; j >= 0; --j) {  // oldest -> newest
+    const int h = (head - 1 - j + 2 * H) % H;
+    const double* Sh = S + (long long)h * Dpad;
+    const double* Yh = Y + (long long)h * Dpad;
+    double sv[NCC], yv[NCC];
+#pragma unroll
+    for (int c = 0; c < NCC; ++c) {
+      const int i = lane + 32 * c;
+      sv[c] = (i < D) ? Sh[i] : 0.0;
+      yv[c] = (i < D) ? Yh[i] : 0.0;
+    }
+    double d = 0.0;
+#pragma unroll
+    for (int c = 0; c < NCC; ++c) d = fma(yv[c], pr[c], d);
+    const double cc = al[h] - rho[h] * warp_sum(d);
+#pragma unroll
+    for (int c = 0; c < NCC; ++c) pr[c] = fma(cc, sv[c], pr[c]);
+  }
+#pragma unroll
+  for (int c = 0; c < NCC; ++c) {
+    const int i = lane + 32 * c;
+    if (i < D) pk[i] = pr[c];
+  }
+  __syncwarp();
+}
+
 }  // namespace
 
-__global__ void __launch_bounds__(NTHREADS, 1)
+template <int TOEP>
+__global__ void __launch_bounds__(NTHREADS, TOEP ? 2 : 1)
 lbfgs_kernel(BdrtModel m, bdrt_lbfgs_opts o, double* __restrict__ U, double* lp_out, int* iters_out, int* neval_out,
              int* status_out, int* queue, double* hist, double* gvec, int nvec_smem, int Dpad) {
   extern __shared__ double sm[];
@@ -79,7 +167,7 @@ lbfgs_kernel(BdrtModel m, bdrt_lbfgs_opts o, double* __restrict__ U, double* lp_
 
   // f(xn) -> f, gn = grad f ; returns false when not finite
   auto feval = [&](double& f) -> bool {
-    const double lp = engine_eval(m, sm, true, xn, gn, Zs, 0);
+    const double lp = engine_eval<TOEP>(m, sm, true, xn, gn, Zs, 0);
     ++neval;
     int fin = isfinite(lp);
     for (int i = lane; i < D; i += 32) {
@@ -252,28 +340,12 @@ lbfgs_kernel(BdrtModel m, bdrt_lbfgs_opts o, double* __restrict__ U, double* lp_
         __syncwarp();
         __threadfence_block();
         // ---------------- two-loop recursion -> pk
-        for (int i = lane; i < D; i += 32) pk[i] = -gk[i];
-        __syncwarp();
-        for (int j = 0; j < nh; ++j) {  // newest -> oldest
-          const int h = (head - 1 - j + 2 * H) % H;
-          const double* Sh = S + (long long)h * Dpad;
-          const double* Yh = Y + (long long)h * Dpad;
-          const double a = rho[h] * vdot(Sh, pk, D, lane);
-          al[h] = a;
-          for (int i = lane; i < D; i += 32) pk[i] = fma(-a, Yh[i], pk[i]);
-          __syncwarp();
-        }
-        for (int i = lane; i < D; i += 32) pk[i] *= gamma;
-        __syncwarp();
-        for (int j = nh - 1; j >= 0; --j) {  // oldest -> newest
-          const int h = (head - 1 - j + 2 * H) % H;
-          const double* Sh = S + (long long)h * Dpad;
-          const double* Yh = Y + (long long)h * Dpad;
-          const double beta = rho[h] * vdot(Yh, pk, D, lane);
-          const double c = al[h] - beta;
-          for (int i = lane; i < D; i += 32) pk[i] = fma(c, Sh[i], pk[i]);
-          __syncwarp();
-        }
+        if (D <= 32 * 7)
+          two_loop<7>(S, Y, rho, al, gk, pk, D, Dpad, nh, head, H, gamma, lane);
+        else if (D <= 32 * 12)
+          two_loop<12>(S, Y, rho, al, gk, pk, D, Dpad, nh, head, H, gamma, lane);
+        else
+          two_loop<0>(S, Y, rho, al, gk, pk, D, Dpad, nh, head, H, gamma, lane);
         // ---------------- convergence tests, Stan's order
         const double df = fabs(fk_1 - fk);
         const double gp = vdot(gk, pk, D, lane);
@@ -302,7 +374,7 @@ lbfgs_kernel(BdrtModel m, bdrt_lbfgs_opts o, double* __restrict__ U, double* lp_
   // drain: keep serving the cooperative matrix products until every slot of the CTA is out of work
   if (lane == 0) atomicSub((int*)n_active, 1);
   while (true) {
-    engine_eval(m, sm, false, nullptr, nullptr, nullptr, 0, n_active, &snap);
+    engine_eval<TOEP>(m, sm, false, nullptr, nullptr, nullptr, 0, n_active, &snap);
     if (snap == 0) break;
   }
 }
@@ -334,10 +406,11 @@ extern "C" int bdrt_map_lbfgs(bdrt_ctx* ctx, const bdrt_series_data* data, const
   }
   const int D = bdrt_num_params(data);
   const int Dpad = (D + 1) & ~1;
-  const int grid = data->B == 0 ? 0 : ((data->B + NSLOT - 1) / NSLOT < ctx->sm_count ? (data->B + NSLOT - 1) / NSLOT
-                                                                                      : ctx->sm_count);
-  const size_t hist_bytes = (size_t)grid * NSLOT * 2 * MAXHIST * Dpad * sizeof(double);
-  const size_t gvec_bytes = (size_t)grid * NSLOT * 5 * Dpad * sizeof(double);
+  const int max_ctas = 2 * ctx->sm_count;  // scratch is sized for the two-CTAs-per-SM (Toeplitz) plan
+  const int grid_max = data->B == 0 ? 0 : ((data->B + NSLOT - 1) / NSLOT < max_ctas ? (data->B + NSLOT - 1) / NSLOT : max_ctas);
+  int grid = grid_max;
+  const size_t hist_bytes = (size_t)grid_max * NSLOT * 2 * MAXHIST * Dpad * sizeof(double);
+  const size_t gvec_bytes = (size_t)grid_max * NSLOT * 5 * Dpad * sizeof(double);
   void* extra = nullptr;
   int rc = bdrt_model_prepare(ctx, data, &m, 256 + hist_bytes + gvec_bytes, &extra);
   if (rc) return rc;
@@ -347,15 +420,9 @@ extern "C" int bdrt_map_lbfgs(bdrt_ctx* ctx, const bdrt_series_data* data, const
   double* gvec = (double*)((char*)extra + 256 + hist_bytes);
   BDRT_CUDA(ctx, cudaMemsetAsync(queue, 0, 256, ctx->stream));
   // how many of the 5 work vectors per slot fit in shared memory
-  const long long avail = (long long)ctx->smem_optin / 8 - m.oUser - 2;
-  int nvec = (int)(avail / ((long long)NSLOT * Dpad));
-  if (nvec > 5) nvec = 5;
-  if (nvec < 0) nvec = 0;
-  const size_t smem = ((size_t)m.oUser + 2 + (size_t)NSLOT * nvec * Dpad) * sizeof(double);
-  BDRT_CUDA(ctx, cudaFuncSetAttribute(lbfgs_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  lbfgs_kernel<<<grid, NTHREADS, smem, ctx->stream>>>(m, *opts, u, lp, iters, n_eval, status, queue, hist, gvec, nvec,
-                                                      Dpad);
-  ctx->launches++;
-  BDRT_CUDA(ctx, cudaGetLastError());
+  const BdrtPlan pl = bdrt_plan(ctx, m, Dpad, 5, 2);
+  if (grid > ctx->sm_count * pl.ctas_per_sm) grid = ctx->sm_count * pl.ctas_per_sm;
+  BDRT_LAUNCH(ctx, m, lbfgs_kernel, grid, pl.smem, m, *opts, u, lp, iters, n_eval, status, queue, hist, gvec, pl.nvec,
+              Dpad);
   return BDRT_OK;
 }

@@ -1,4 +1,6 @@
 // Context management, model preparation, and the log_prob / constrain entry points.
+#include <stdlib.h>
+
 #include "engine.cuh"
 
 extern "C" int bdrt_version(void) { return BDRT_VERSION; }
@@ -17,6 +19,7 @@ extern "C" int bdrt_ctx_create(int device, void* stream, bdrt_ctx** out) {
   c->stream = (cudaStream_t)stream;
   c->sm_count = prop.multiProcessorCount;
   c->smem_optin = (int)prop.sharedMemPerBlockOptin;
+  c->smem_per_sm = (int)prop.sharedMemPerMultiprocessor;
   *out = c;
   return BDRT_OK;
 }
@@ -89,6 +92,32 @@ __global__ void band_prep_kernel(const double* L, int K, double* Lb, int* info) 
   if (!toep) atomicAnd(&info[1], 0);
 }
 
+// Is the stacked kernel matrix [A_re; A_im] Toeplitz in each part (shared log-uniform grid with the measurement
+// frequencies on the basis grid -- the case the reference special-cases too, matrices.py:145-242)?  info[2] &= yes.
+__global__ void toep_check_kernel(const double* A, int Nf, int K, int* info) {
+  __shared__ double s_red[32];
+  __shared__ double s_max;
+  double mx = 0.0;
+  for (int i = threadIdx.x; i < 2 * Nf * K; i += blockDim.x) mx = fmax(mx, fabs(A[i]));
+  mx = warp_max(mx);
+  if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = mx;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double v = 0.0;
+    for (int w = 0; w < (blockDim.x + 31) / 32; ++w) v = fmax(v, s_red[w]);
+    s_max = v;
+  }
+  __syncthreads();
+  const double tol = 1e-14 * s_max;
+  int ok = 1;
+  for (int i = threadIdx.x; i < 2 * Nf * K; i += blockDim.x) {
+    const int r = i / K, c = i - r * K;
+    const int rl = r >= Nf ? r - Nf : r;
+    if (rl + 1 < Nf && c + 1 < K && !(fabs(A[i] - A[i + K + 1]) <= tol)) ok = 0;
+  }
+  if (!ok) atomicAnd(&info[2], 0);
+}
+
 int bdrt_model_prepare(bdrt_ctx* ctx, const bdrt_series_data* d, BdrtModel* m, size_t extra_ws_bytes,
                        void** extra_ws) {
   if (!d) BDRT_FAIL(ctx, BDRT_E_NULL, "null data");
@@ -124,12 +153,19 @@ int bdrt_model_prepare(bdrt_ctx* ctx, const bdrt_series_data* d, BdrtModel* m, s
   if (rc) return rc;
   int* info = (int*)ctx->ws;
   double* Lb = (double*)((char*)ctx->ws + 256);
-  const int init[2] = {0, 1};
+  // BDRT_FORCE_DENSE=1 keeps the dense-resident A path even for Toeplitz grids (used by the tests to cover both)
+  const char* fd = getenv("BDRT_FORCE_DENSE");
+  const int try_toep = !d->per_spectrum_grid && !(fd && fd[0] == '1');
+  const int init[3] = {0, 1, try_toep};
   BDRT_CUDA(ctx, cudaMemcpyAsync(info, init, sizeof(init), cudaMemcpyHostToDevice, ctx->stream));
   band_prep_kernel<<<3, 256, 0, ctx->stream>>>(d->L, d->K, Lb, info);
   ctx->launches++;
+  if (try_toep) {
+    toep_check_kernel<<<1, 512, 0, ctx->stream>>>(d->A, d->Nf, d->K, info);
+    ctx->launches++;
+  }
   BDRT_CUDA(ctx, cudaGetLastError());
-  int hinfo[2];
+  int hinfo[3];
   BDRT_CUDA(ctx, cudaMemcpyAsync(hinfo, info, sizeof(hinfo), cudaMemcpyDeviceToHost, ctx->stream));
   BDRT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   if (hinfo[0] > MAXBW)
@@ -139,6 +175,7 @@ int bdrt_model_prepare(bdrt_ctx* ctx, const bdrt_series_data* d, BdrtModel* m, s
               MAXBW, hinfo[0]);
   m->bw = hinfo[0];
   m->toeplitz = hinfo[1] && (d->K >= 2 * hinfo[0] + 1);
+  m->toepA = hinfo[2];
   m->Lb = Lb;
   const int eng = bdrt_model_layout(m);
   if ((size_t)eng * 8 > (size_t)ctx->smem_optin)
@@ -151,7 +188,8 @@ int bdrt_model_prepare(bdrt_ctx* ctx, const bdrt_series_data* d, BdrtModel* m, s
 // ---------------------------------------------------------------------------------------------------------------------
 // log_prob + gradient test hook
 // ---------------------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(NTHREADS, 1)
+template <int TOEP>
+__global__ void __launch_bounds__(NTHREADS, TOEP ? 2 : 1)
 logpost_kernel(BdrtModel m, const double* u, const int* spec, int n_cols, int jacobian, double* lp, double* grad,
                int cta_per_spec) {
   extern __shared__ double sm[];
@@ -163,7 +201,7 @@ logpost_kernel(BdrtModel m, const double* u, const int* spec, int n_cols, int ja
       const int c = gidx * NSLOT + warp;
       const bool active = c < n_cols;
       const int b = active ? (spec ? spec[c] : c % m.B) : 0;
-      const double v = engine_eval(m, sm, active, u + (long long)c * m.D, grad + (long long)c * m.D,
+      const double v = engine_eval<TOEP>(m, sm, active, u + (long long)c * m.D, grad + (long long)c * m.D,
                                    m.Z + (long long)b * m.N2, jacobian);
       if (active && lane == 0) lp[c] = v;
     }
@@ -188,7 +226,7 @@ logpost_kernel(BdrtModel m, const double* u, const int* spec, int n_cols, int ja
         c = nf ? found[nf - 1] : c;
         const bool active = warp < nf;
         const int col = active ? found[warp] : 0;
-        const double v = engine_eval(m, sm, active, u + (long long)col * m.D, grad + (long long)col * m.D,
+        const double v = engine_eval<TOEP>(m, sm, active, u + (long long)col * m.D, grad + (long long)col * m.D,
                                      m.Z + (long long)b * m.N2, jacobian);
         if (active && lane == 0) lp[col] = v;
       }
@@ -206,19 +244,16 @@ extern "C" int bdrt_logpost_grad(bdrt_ctx* ctx, const bdrt_series_data* data, co
   int rc = bdrt_model_prepare(ctx, data, &m, 0, nullptr);
   if (rc) return rc;
   if (n_cols == 0 || data->B == 0) return BDRT_OK;
-  const size_t smem = (size_t)m.oUser * sizeof(double);
-  BDRT_CUDA(ctx, cudaFuncSetAttribute(logpost_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const BdrtPlan pl = bdrt_plan(ctx, m, 2, 0, 0);
+  const int slots = ctx->sm_count * pl.ctas_per_sm;
   int grid;
   if (data->per_spectrum_grid)
-    grid = data->B < ctx->sm_count ? data->B : ctx->sm_count;
+    grid = data->B < slots ? data->B : slots;
   else {
     const int ngroups = (n_cols + NSLOT - 1) / NSLOT;
-    grid = ngroups < ctx->sm_count ? ngroups : ctx->sm_count;
+    grid = ngroups < slots ? ngroups : slots;
   }
-  logpost_kernel<<<grid, NTHREADS, smem, ctx->stream>>>(m, u, spec, n_cols, jacobian, lp, grad,
-                                                        data->per_spectrum_grid);
-  ctx->launches++;
-  BDRT_CUDA(ctx, cudaGetLastError());
+  BDRT_LAUNCH(ctx, m, logpost_kernel, grid, pl.smem, m, u, spec, n_cols, jacobian, lp, grad, data->per_spectrum_grid);
   return BDRT_OK;
 }
 

@@ -56,7 +56,8 @@ __device__ __forceinline__ double logaddexp(double a, double b) {
 
 }  // namespace
 
-__global__ void __launch_bounds__(NTHREADS, 1)
+template <int TOEP>
+__global__ void __launch_bounds__(NTHREADS, TOEP ? 2 : 1)
 nuts_kernel(BdrtModel m, bdrt_nuts_opts o, const double* __restrict__ U0, double* draws, double* stepsize_out,
             long long* nleap_out, int* ndiv_out, int* nmax_out, double* accept_out, int* queue, double* gvec,
             double* ckpt, int nvec_smem, int Dpad) {
@@ -91,7 +92,7 @@ nuts_kernel(BdrtModel m, bdrt_nuts_opts o, const double* __restrict__ U0, double
       q[i] = fma(eps * mi[i], pi, q[i]);
     }
     __syncwarp();
-    const double lp = engine_eval(m, sm, true, q, g, Zs, 1);
+    const double lp = engine_eval<TOEP>(m, sm, true, q, g, Zs, 1);
     ++n_grad;
     for (int i = lane; i < D; i += 32) p[i] = fma(0.5 * eps, g[i], p[i]);
     __syncwarp();
@@ -124,7 +125,7 @@ nuts_kernel(BdrtModel m, bdrt_nuts_opts o, const double* __restrict__ U0, double
     vcopy(v[V_SQ], U0 + wi * D);
     for (int i = lane; i < D; i += 32) v[V_MINV][i] = 1.0;
     __syncwarp();
-    double s_lp = engine_eval(m, sm, true, v[V_SQ], v[V_SG], Zs, 1);
+    double s_lp = engine_eval<TOEP>(m, sm, true, v[V_SQ], v[V_SG], Zs, 1);
     ++n_grad;
     bool bad = !isfinite(s_lp);
 
@@ -359,7 +360,7 @@ nuts_kernel(BdrtModel m, bdrt_nuts_opts o, const double* __restrict__ U0, double
   int snap;
   if (lane == 0) atomicSub((int*)n_active, 1);
   while (true) {
-    engine_eval(m, sm, false, nullptr, nullptr, nullptr, 0, n_active, &snap);
+    engine_eval<TOEP>(m, sm, false, nullptr, nullptr, nullptr, 0, n_active, &snap);
     if (snap == 0) break;
   }
 }
@@ -393,9 +394,11 @@ extern "C" int bdrt_nuts(bdrt_ctx* ctx, const bdrt_series_data* data, const bdrt
   const long long n_work = (long long)data->B * opts->chains;
   if (n_work > 2000000000LL) BDRT_FAIL(ctx, BDRT_E_SIZE, "too many chains in one call");
   const long long groups = (n_work + NSLOT - 1) / NSLOT;
-  const int grid = n_work == 0 ? 0 : (int)(groups < ctx->sm_count ? groups : ctx->sm_count);
-  const size_t gvec_bytes = (size_t)grid * NSLOT * NV * Dpad * sizeof(double);
-  const size_t ck_bytes = (size_t)grid * NSLOT * 2 * MAXDEPTH * Dpad * sizeof(double);
+  const int max_ctas = 2 * ctx->sm_count;  // scratch is sized for the two-CTAs-per-SM (Toeplitz) plan
+  const int grid_max = n_work == 0 ? 0 : (int)(groups < max_ctas ? groups : max_ctas);
+  int grid = grid_max;
+  const size_t gvec_bytes = (size_t)grid_max * NSLOT * NV * Dpad * sizeof(double);
+  const size_t ck_bytes = (size_t)grid_max * NSLOT * 2 * MAXDEPTH * Dpad * sizeof(double);
   BdrtModel m;
   void* extra = nullptr;
   int rc = bdrt_model_prepare(ctx, data, &m, 256 + gvec_bytes + ck_bytes, &extra);
@@ -405,15 +408,9 @@ extern "C" int bdrt_nuts(bdrt_ctx* ctx, const bdrt_series_data* data, const bdrt
   double* gvec = (double*)((char*)extra + 256);
   double* ckpt = (double*)((char*)extra + 256 + gvec_bytes);
   BDRT_CUDA(ctx, cudaMemsetAsync(queue, 0, 256, ctx->stream));
-  const long long avail = (long long)ctx->smem_optin / 8 - m.oUser - 2;
-  int nvec = (int)(avail / ((long long)NSLOT * Dpad));
-  if (nvec > NV) nvec = NV;
-  if (nvec < 0) nvec = 0;
-  const size_t smem = ((size_t)m.oUser + 2 + (size_t)NSLOT * nvec * Dpad) * sizeof(double);
-  BDRT_CUDA(ctx, cudaFuncSetAttribute(nuts_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  nuts_kernel<<<grid, NTHREADS, smem, ctx->stream>>>(m, *opts, u0, draws, stepsize, n_leapfrog, n_divergent,
-                                                     n_maxdepth, accept, queue, gvec, ckpt, nvec, Dpad);
-  ctx->launches++;
-  BDRT_CUDA(ctx, cudaGetLastError());
+  const BdrtPlan pl = bdrt_plan(ctx, m, Dpad, NV, 2);
+  if (grid > ctx->sm_count * pl.ctas_per_sm) grid = ctx->sm_count * pl.ctas_per_sm;
+  BDRT_LAUNCH(ctx, m, nuts_kernel, grid, pl.smem, m, *opts, u0, draws, stepsize, n_leapfrog, n_divergent, n_maxdepth,
+              accept, queue, gvec, ckpt, pl.nvec, Dpad);
   return BDRT_OK;
 }

@@ -1,0 +1,207 @@
+"""Oracle restatement of the reference's two-distribution Stan program ``Series-Parallel[_pos]`` (numpy, FP64).
+
+TEST INFRASTRUCTURE ONLY (see oracle/__init__.py).
+
+Follows
+  * Stan program                bayes_drt/stan_model_files/Series-Parallel_modelcode.txt:1-111 and
+                                Series-Parallel_pos_modelcode.txt:35 (``vector<lower=0>[Ks] xs``)
+  * Inverter._prep_stan_data    inversion.py:1886-1959 (constants per mode; note the parallel L0 multiplier
+                                1.5*0.36 in 'optimize', x_sum_invscale 1 ('sample') / 0 ('optimize'), xp_scale from
+                                distributions[...]['x_scale'])
+  * Inverter._prep_matrices     inversion.py:2127-2336 per distribution; _scale_Z :2437-2441 (mixed model branch)
+  * result rescaling            inversion.py:2445-2450 (series coef * Z_scale, parallel coef / Z_scale)
+
+Unconstrained vector, Stan declaration order (Series-Parallel_modelcode.txt:32-49):
+  Rinf_raw, induc_raw, xs[Ks], xp_raw[Kp], sigma_res_raw, alpha_prop_raw, alpha_re_raw, alpha_im_raw,
+  ups_s_raw[Ks], ups_p_raw[Kp], d0s, d1s, d2s, d0p, d1p, d2p          ->  D = 2 (Ks + Kp) + 12
+Every parameter is ``lower=0`` (theta = exp(u)) except ``xs`` in the non-_pos variant.  The transformed parameter
+``real<lower=0> x_sum_raw = sum(xs) + sum(xp_raw)`` (:56) is validity-checked by Stan: a negative value rejects the
+point (log density -inf); that can only happen in the non-_pos variant.
+
+**Parity unpinned** (pystan absent, no reference golden vector): checked against the literal autograd transcription
+``oracle.stan_literal.logpost_literal_sp``.
+"""
+import numpy as np
+
+from . import matrices as om
+from .model import default_epsilon, default_tau, z_scale
+
+# inversion.py:1913-1930
+MODE_CONSTANTS_SP = {
+    'sample': dict(ups_alpha=1.0, ups_beta=0.1, ls=(1.0, 1.0, 0.75), lp=(1.0, 1.0, 0.75), x_sum_invscale=1.0),
+    'optimize': dict(ups_alpha=0.05, ups_beta=0.1, ls=(1.5 * 0.24, 1.5 * 0.16, 1.5 * 0.08),
+                     lp=(1.5 * 0.36, 1.5 * 0.16, 1.5 * 0.08), x_sum_invscale=0.0),
+}
+
+
+def _dist_matrices(freq, info):
+    """A_re, A_im, L0, L1, L2, tau, epsilon of one distribution (inversion.py:2191-2209, :2250-2271, :2301-2307)."""
+    bf = info.get('basis_freq')
+    tau = default_tau(freq) if bf is None else 1.0 / (2 * np.pi * np.asarray(bf, dtype=np.float64))
+    eps = info.get('epsilon') or default_epsilon(tau)
+    kw = dict(tau=tau, epsilon=eps, kernel=info['kernel'], dist_type=info['dist_type'],
+              symmetry=info.get('symmetry', 'planar'), bc=info.get('bc'), ct=info.get('ct', False),
+              k_ct=info.get('k_ct'))
+    A_re = om.construct_A(freq, 'real', **kw)
+    A_im = om.construct_A(freq, 'imag', **kw)
+    bfr = 1.0 / (2 * np.pi * tau)
+    L = [om.construct_L(bfr, tau=tau, epsilon=eps, order=o) for o in (0, 1, 2)]
+    return A_re, A_im, L, tau, eps
+
+
+def prep_series_parallel(freq, Z, ser, par, mode='optimize', nonneg=True, sigma_min=0.002, inductance_scale=1.0,
+                         scale_Z=True):
+    """Stan data of the Series-Parallel model for one spectrum.  ``ser`` / ``par``: the reference's distribution
+    info dicts ({'kernel': 'DRT', ...} / {'kernel': 'DDT', 'dist_type': 'parallel', 'symmetry': 'planar',
+    'bc': 'transmissive', 'x_scale': 0.8, ...})."""
+    freq = np.asarray(freq, dtype=np.float64)
+    Z = np.asarray(Z, dtype=np.complex128)
+    idx = np.argsort(freq)[::-1]
+    freq, Z = freq[idx], Z[idx]
+    zs = z_scale(Z) if scale_Z else 1.0
+    Zs = Z / zs
+    ser = dict(ser, dist_type='series')
+    par = dict(par, dist_type='parallel')
+    As_re, As_im, Ls, tau_s, eps_s = _dist_matrices(freq, ser)
+    Ap_re, Ap_im, Lp, tau_p, eps_p = _dist_matrices(freq, par)
+    c = MODE_CONSTANTS_SP[mode]
+    return dict(
+        Nf=len(freq), Ks=len(tau_s), Kp=len(tau_p), freq=freq, tau_s=tau_s, tau_p=tau_p, eps_s=eps_s, eps_p=eps_p,
+        Z_scale=zs, As=np.concatenate((As_re, As_im)), Ap=np.concatenate((Ap_re, Ap_im)),
+        Z=np.concatenate((Zs.real, Zs.imag)),
+        Ls=[c['ls'][o] * Ls[o] for o in range(3)], Lp=[c['lp'][o] * Lp[o] for o in range(3)],
+        sigma_min=float(sigma_min), ups_alpha=c['ups_alpha'], ups_beta=c['ups_beta'],
+        induc_scale=float(inductance_scale), x_sum_invscale=c['x_sum_invscale'],
+        xp_scale=float(par.get('x_scale', 1)), pos=bool(nonneg))
+
+
+def n_params(d):
+    return 2 * (d['Ks'] + d['Kp']) + 12
+
+
+def param_slices(d):
+    Ks, Kp = d['Ks'], d['Kp']
+    o = 2
+    s = {'Rinf_raw': slice(0, 1), 'induc_raw': slice(1, 2), 'xs': slice(o, o + Ks), 'xp_raw': slice(o + Ks, o + Ks + Kp)}
+    o += Ks + Kp
+    s['err'] = slice(o, o + 4)
+    o += 4
+    s['ups_s_raw'] = slice(o, o + Ks)
+    s['ups_p_raw'] = slice(o + Ks, o + Ks + Kp)
+    o += Ks + Kp
+    s['ds'] = slice(o, o + 3)
+    s['dp'] = slice(o + 3, o + 6)
+    return s
+
+
+def _prior_block(x, L, dstr, ups):
+    """sum_k [-1/2 q_k^2/ups_k^2 - log ups_k] - 1/2 sum dups^2 and its derivatives w.r.t. x, d, ups."""
+    a = [L[j] @ x for j in range(3)]
+    q2 = sum(dstr[j] * a[j] ** 2 for j in range(3))
+    iu2 = 1.0 / ups ** 2
+    e = 0.5 - 0.25 * (ups[:-2] + ups[2:]) / ups[1:-1]
+    lp = np.sum(-0.5 * q2 * iu2 - np.log(ups)) - 0.5 * np.sum(e ** 2)
+    gx = -sum(L[j].T @ (dstr[j] * a[j] * iu2) for j in range(3))
+    gd = np.array([-0.5 * np.sum(a[j] ** 2 * iu2) for j in range(3)])
+    gu = q2 / ups ** 3 - 1.0 / ups
+    um = ups[1:-1]
+    gu[:-2] += e * 0.25 / um
+    gu[2:] += e * 0.25 / um
+    gu[1:-1] -= e * 0.25 * (ups[:-2] + ups[2:]) / um ** 2
+    return lp, gx, gd, gu
+
+
+def logpost(u, d, jacobian=False, want_grad=True):
+    """log p(u | data) up to Stan's dropped constants and its gradient (Series-Parallel_modelcode.txt:50-110)."""
+    Ks, Kp, Nf = d['Ks'], d['Kp'], d['Nf']
+    sl = param_slices(d)
+    w = 2 * np.pi * d['freq']
+    th = np.exp(u)
+    Rinf_raw, induc_raw = th[0], th[1]
+    xs = th[sl['xs']] if d['pos'] else u[sl['xs']]
+    xp_raw = th[sl['xp_raw']]
+    sr_raw, ap_raw, are_raw, aim_raw = th[sl['err']]
+    ups_s_raw, ups_p_raw = th[sl['ups_s_raw']], th[sl['ups_p_raw']]
+    ds, dp = th[sl['ds']], th[sl['dp']]
+    sr, ap, are, aim = 0.05 * sr_raw, 0.05 * ap_raw, 0.05 * are_raw, 0.05 * aim_raw
+    xsc, inv = d['xp_scale'], d['x_sum_invscale']
+
+    x_sum_raw = np.sum(xs) + np.sum(xp_raw)
+    if x_sum_raw < 0:  # real<lower=0> x_sum_raw (:56): Stan rejects the point
+        return (-np.inf, np.full_like(u, np.nan)) if want_grad else -np.inf
+    x_sum = x_sum_raw * inv
+    Y = d['Ap'] @ (xp_raw * xsc)
+    Yr, Yi = Y[:Nf], Y[Nf:]
+    M = Yr ** 2 + Yi ** 2
+    zhat = d['As'] @ xs
+    zhat[:Nf] += Yr / M + 100.0 * Rinf_raw
+    zhat[Nf:] += -Yi / M + induc_raw * d['induc_scale'] * w
+    zre, zim = zhat[:Nf], zhat[Nf:]
+    common = (are * zre) ** 2 + (aim * zim) ** 2
+    s = d['sigma_min'] ** 2 + sr ** 2 + (ap * zhat) ** 2 + np.tile(common, 2)
+    r = d['Z'] - zhat
+    ups_s, ups_p = 0.15 * ups_s_raw, 0.15 * ups_p_raw
+    lps, gxs, gds, gus = _prior_block(xs, d['Ls'], ds, ups_s)
+    lpp, gxp, gdp, gup = _prior_block(xp_raw, d['Lp'], dp, ups_p)
+
+    lp = np.sum(-6.0 * np.log(ds) - 5.0 / ds) + np.sum(-6.0 * np.log(dp) - 5.0 / dp)
+    lp += -0.5 * x_sum ** 2
+    for ur in (ups_s_raw, ups_p_raw):
+        lp += np.sum(-(d['ups_alpha'] + 1) * np.log(ur) - d['ups_beta'] / ur)
+    lp += -0.5 * (Rinf_raw ** 2 + induc_raw ** 2 + sr_raw ** 2 + ap_raw ** 2 + are_raw ** 2 + aim_raw ** 2)
+    lp += lps + lpp
+    lp += np.sum(-0.5 * r ** 2 / s - 0.5 * np.log(s))
+    lower0 = np.ones(len(u), dtype=bool)
+    if not d['pos']:
+        lower0[sl['xs']] = False
+    if jacobian:
+        lp += np.sum(u[lower0])
+    if not want_grad:
+        return lp
+
+    g = 0.5 * r ** 2 / s ** 2 - 0.5 / s
+    G = g[:Nf] + g[Nf:]
+    v = r / s + 2 * ap ** 2 * zhat * g
+    v[:Nf] += 2 * are ** 2 * zre * G
+    v[Nf:] += 2 * aim ** 2 * zim * G
+    # Z_p = 1 / (Y' + i Y''):  d lp / d Y from v = d lp / d Z_hat
+    vr, vi = v[:Nf], v[Nf:]
+    c1, c2 = (Yi ** 2 - Yr ** 2) / M ** 2, 2 * Yr * Yi / M ** 2
+    gY = np.concatenate((vr * c1 + vi * c2, -vr * c2 + vi * c1))
+
+    grad = np.empty_like(u)
+    grad[0] = 100.0 * np.sum(vr) - Rinf_raw
+    grad[1] = d['induc_scale'] * np.sum(w * vi) - induc_raw
+    grad[sl['xs']] = d['As'].T @ v + gxs - x_sum * inv
+    grad[sl['xp_raw']] = xsc * (d['Ap'].T @ gY) + gxp - x_sum * inv
+    o = sl['err'].start
+    grad[o] = 0.05 * 2 * sr * np.sum(g) - sr_raw
+    grad[o + 1] = 0.05 * 2 * ap * np.sum(g * zhat ** 2) - ap_raw
+    grad[o + 2] = 0.05 * 2 * are * np.sum(G * zre ** 2) - are_raw
+    grad[o + 3] = 0.05 * 2 * aim * np.sum(G * zim ** 2) - aim_raw
+    for nm, gu, ur in (('ups_s_raw', gus, ups_s_raw), ('ups_p_raw', gup, ups_p_raw)):
+        grad[sl[nm]] = 0.15 * gu - (d['ups_alpha'] + 1) / ur + d['ups_beta'] / ur ** 2
+    grad[sl['ds']] = gds - 6.0 / ds + 5.0 / ds ** 2
+    grad[sl['dp']] = gdp - 6.0 / dp + 5.0 / dp ** 2
+    grad[lower0] = grad[lower0] * th[lower0] + (1.0 if jacobian else 0.0)
+    return lp, grad
+
+
+def constrain(u, d):
+    """The names the reference reads back (inversion.py:1236-1276): xs, xp, Rinf, induc, sigma_*, alpha_*."""
+    Ks, Kp, Nf = d['Ks'], d['Kp'], d['Nf']
+    sl = param_slices(d)
+    th = np.exp(u)
+    out = {'xs': th[sl['xs']] if d['pos'] else u[sl['xs']].copy(), 'xp': th[sl['xp_raw']] * d['xp_scale'],
+           'Rinf': 100.0 * th[0], 'induc': th[1] * d['induc_scale']}
+    for i, nm in enumerate(('sigma_res', 'alpha_prop', 'alpha_re', 'alpha_im')):
+        out[nm] = 0.05 * th[sl['err']][i]
+    Y = d['Ap'] @ out['xp']
+    M = Y[:Nf] ** 2 + Y[Nf:] ** 2
+    zhat = d['As'] @ out['xs']
+    zhat[:Nf] += Y[:Nf] / M + out['Rinf']
+    zhat[Nf:] += -Y[Nf:] / M + out['induc'] * 2 * np.pi * d['freq']
+    out['Z_hat'] = zhat
+    out['sigma_tot'] = np.sqrt(d['sigma_min'] ** 2 + out['sigma_res'] ** 2 + (out['alpha_prop'] * zhat) ** 2
+                               + np.tile((out['alpha_re'] * zhat[:Nf]) ** 2 + (out['alpha_im'] * zhat[Nf:]) ** 2, 2))
+    return out

@@ -304,3 +304,35 @@ def _ess(z):
         t += 2
     tau = max(tau, 1.0 / np.log10(m * n))
     return m * n / tau
+
+
+def ess_indicator(x, thr):
+    """Split-chain ESS of the indicator I(x <= thr) (the ESS behind a quantile estimate, Vehtari et al. 2021 sec. 4.3)."""
+    c, n = x.shape
+    half = n // 2
+    z = np.concatenate((x[:, :half], x[:, half:2 * half]), axis=0)
+    ind = (z <= thr).astype(np.float64)
+    if ind.min() == ind.max():
+        return float(z.size)
+    return _ess(ind)
+
+
+def mcse_quantile(x, p):
+    """Monte-Carlo standard error of the p-quantile of draws x [chains, n] (posterior::mcse_quantile): the ESS of the
+    indicator gives a Beta interval for the probability, mapped back through the empirical quantile function."""
+    from scipy.stats import beta
+    flat = np.sort(x.ravel())
+    S = flat.size
+    ess = ess_indicator(x, np.quantile(flat, p))
+    a, b = beta.ppf([0.1586553, 0.8413447], ess * p + 1, ess * (1 - p) + 1)
+    lo = flat[max(int(np.floor(a * S)), 1) - 1]
+    hi = flat[min(int(np.ceil(b * S)), S) - 1]
+    return 0.5 * (hi - lo)
+
+
+def mcse_mean(x):
+    """sd / sqrt(bulk ESS) with the un-normalised split-chain ESS of the draws themselves."""
+    c, n = x.shape
+    half = n // 2
+    z = np.concatenate((x[:, :half], x[:, half:2 * half]), axis=0)
+    return x.std(ddof=1) / np.sqrt(_ess(z))

@@ -95,3 +95,82 @@ def logpost_literal(u, d, jacobian=False):
         lp = lp + logjac
     assert pos == u.numel()
     return lp
+
+
+def logpost_literal_sp(u, d, jacobian=False):
+    """Series-Parallel[_pos]_modelcode.txt, line by line.  u: torch float64 tensor; d: dict from
+    oracle.model_sp.prep_series_parallel.  Returns -inf when the validity check ``real<lower=0> x_sum_raw`` fails."""
+    Ks, Kp, Nf = d['Ks'], d['Kp'], d['Nf']
+    t = lambda a: torch.as_tensor(a, dtype=torch.float64)
+    As, Ap, Z, freq = t(d['As']), t(d['Ap']), t(d['Z']), t(d['freq'])
+    L0s, L1s, L2s = (t(x) for x in d['Ls'])
+    L0p, L1p, L2p = (t(x) for x in d['Lp'])
+    # transformed data (:26-31)
+    Rinf_vec = torch.cat((torch.ones(Nf, dtype=torch.float64), torch.zeros(Nf, dtype=torch.float64)))
+    induc_vec = torch.cat((torch.zeros(Nf, dtype=torch.float64), 2 * math.pi * freq))
+    pos = 0
+    logjac = torch.zeros((), dtype=torch.float64)
+
+    def take(n, lower0):
+        nonlocal pos, logjac
+        raw = u[pos:pos + n]
+        pos += n
+        if lower0:
+            logjac = logjac + raw.sum()
+            return torch.exp(raw)
+        return raw
+
+    # parameters (:32-49)
+    Rinf_raw = take(1, True)[0]
+    induc_raw = take(1, True)[0]
+    xs = take(Ks, d['pos'])
+    xp_raw = take(Kp, True)
+    sigma_res_raw = take(1, True)[0]
+    alpha_prop_raw = take(1, True)[0]
+    alpha_re_raw = take(1, True)[0]
+    alpha_im_raw = take(1, True)[0]
+    ups_s_raw = take(Ks, True)
+    ups_p_raw = take(Kp, True)
+    d0s, d1s, d2s = take(1, True)[0], take(1, True)[0], take(1, True)[0]
+    d0p, d1p, d2p = take(1, True)[0], take(1, True)[0], take(1, True)[0]
+    assert pos == u.numel()
+    # transformed parameters (:50-85)
+    Rinf = Rinf_raw * 100
+    induc = induc_raw * d['induc_scale']
+    xp = xp_raw * d['xp_scale']
+    qs = torch.sqrt(d0s * (L0s @ xs) ** 2 + d1s * (L1s @ xs) ** 2 + d2s * (L2s @ xs) ** 2)
+    qp = torch.sqrt(d0p * (L0p @ xp_raw) ** 2 + d1p * (L1p @ xp_raw) ** 2 + d2p * (L2p @ xp_raw) ** 2)
+    x_sum_raw = xs.sum() + xp_raw.sum()
+    if x_sum_raw.item() < 0:
+        return torch.tensor(-float('inf'), dtype=torch.float64)
+    x_sum = x_sum_raw * d['x_sum_invscale']
+    sigma_res = sigma_res_raw * 0.05
+    alpha_prop = alpha_prop_raw * 0.05
+    alpha_re = alpha_re_raw * 0.05
+    alpha_im = alpha_im_raw * 0.05
+    Y_hat = Ap @ xp
+    Y_hat_re, Y_hat_im = Y_hat[:Nf], Y_hat[Nf:]
+    Z_hat_p = torch.cat((Y_hat_re / (Y_hat_re ** 2 + Y_hat_im ** 2), -Y_hat_im / (Y_hat_re ** 2 + Y_hat_im ** 2)))
+    Z_hat = Z_hat_p + As @ xs + Rinf * Rinf_vec + induc * induc_vec
+    Z_hat_re = torch.cat((Z_hat[:Nf], Z_hat[:Nf]))
+    Z_hat_im = torch.cat((Z_hat[Nf:], Z_hat[Nf:]))
+    sigma_tot = torch.sqrt(d['sigma_min'] ** 2 + sigma_res ** 2 + (alpha_prop * Z_hat) ** 2
+                           + (alpha_re * Z_hat_re) ** 2 + (alpha_im * Z_hat_im) ** 2)
+    ups_s = ups_s_raw * 0.15
+    ups_p = ups_p_raw * 0.15
+    dups_s = 0.5 * (ups_s[1:-1] - 0.5 * (ups_s[:-2] + ups_s[2:])) / ups_s[1:-1]
+    dups_p = 0.5 * (ups_p[1:-1] - 0.5 * (ups_p[:-2] + ups_p[2:])) / ups_p[1:-1]
+    # model (:86-107)
+    lp = sum(_inv_gamma_lpdf(x, 5.0, 5.0) for x in (d0s, d1s, d2s, d0p, d1p, d2p))
+    lp = lp + _std_normal_lpdf(x_sum)
+    lp = lp + _inv_gamma_lpdf(ups_s_raw, d['ups_alpha'], d['ups_beta']) \
+        + _inv_gamma_lpdf(ups_p_raw, d['ups_alpha'], d['ups_beta'])
+    lp = lp + _std_normal_lpdf(Rinf_raw) + _std_normal_lpdf(induc_raw)
+    lp = lp + _normal_lpdf(qs, 0.0, ups_s) + _normal_lpdf(qp, 0.0, ups_p)
+    lp = lp + _std_normal_lpdf(dups_s) + _std_normal_lpdf(dups_p)
+    lp = lp + _normal_lpdf(Z, Z_hat, sigma_tot)
+    lp = lp + _std_normal_lpdf(sigma_res_raw) + _std_normal_lpdf(alpha_prop_raw) + _std_normal_lpdf(alpha_re_raw) \
+        + _std_normal_lpdf(alpha_im_raw)
+    if jacobian:
+        lp = lp + logjac
+    return lp

@@ -48,7 +48,10 @@ if __name__ == '__main__':
                stepsize=np.array([r['stepsize'] for r in res]), n_leapfrog=np.array([r['n_leapfrog'] for r in res]),
                n_divergent=np.array([r['n_divergent'] for r in res]), n_maxdepth=np.array([r['n_maxdepth'] for r in res]),
                chains=chains, warmup=warmup, samples=samples, Z_scale=d['Z_scale'], wall_s=time.time() - t,
-               chain_means=cons.mean(1))
+               chain_means=cons.mean(1),
+               mcse_mean=np.array([nuts.mcse_mean(cons[:, :, i]) for i in range(K + 6)]),
+               mcse_q025=np.array([nuts.mcse_quantile(cons[:, :, i], 0.025) for i in range(K + 6)]),
+               mcse_q975=np.array([nuts.mcse_quantile(cons[:, :, i], 0.975) for i in range(K + 6)]))
     dst = os.path.join(os.path.dirname(__file__), '..', 'tests', 'golden', f'nuts_{name}.npz')
     np.savez_compressed(dst, **out)
     print('wrote', dst, 'wall %.0f s' % (time.time() - t), 'min ESS', ess.min(), 'stepsizes', out['stepsize'],

@@ -15,3 +15,14 @@ def pytest_configure(config):
 @pytest.fixture(scope='session')
 def golden_dir():
     return os.path.join(ROOT, 'tests', 'golden')
+
+
+@pytest.fixture(params=['toeplitz', 'dense'])
+def resident_A(request, monkeypatch):
+    """Run a GPU test on both resident-operand layouts of the engine: the Toeplitz tables (picked automatically for
+    shared log-uniform grids, two CTAs per SM) and the dense A (forced with BDRT_FORCE_DENSE=1)."""
+    if request.param == 'dense':
+        monkeypatch.setenv('BDRT_FORCE_DENSE', '1')
+    else:
+        monkeypatch.delenv('BDRT_FORCE_DENSE', raising=False)
+    return request.param

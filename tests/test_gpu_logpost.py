@@ -24,7 +24,7 @@ def _check(ds, prob, u, spec, jac):
 @pytest.mark.parametrize('nonneg', [False, True])
 @pytest.mark.parametrize('outliers', [False, True])
 @pytest.mark.parametrize('mode', ['optimize', 'sample'])
-def test_logpost_S_shape(nonneg, outliers, mode):
+def test_logpost_S_shape(nonneg, outliers, mode, resident_A):
     """data/simulated shape: Nf = 81, default basis K = 101 (D = 211 / 373)."""
     names = ['ZARC_uniform_0.25', 'ZARC-RL_uniform_0.25', '2ZARC_uniform_0.25']
     freq = load_spectrum(names[0])[0]
@@ -38,7 +38,7 @@ def test_logpost_S_shape(nonneg, outliers, mode):
         _check(ds, prob, u, spec, jac)
 
 
-def test_logpost_B_shape_many_columns():
+def test_logpost_B_shape_many_columns(resident_A):
     """benchmark shape: Nf = 70, K = 100, shared grid; more columns than one wave of CTAs."""
     from bayes_drt_b200 import synth
     freq, Z, _ = synth.make_spectra(40, seed=11)
@@ -56,7 +56,7 @@ def test_logpost_B_shape_many_columns():
         assert np.max(np.abs(grad[c] - go)) <= 1e-9 * np.max(np.abs(go))
 
 
-def test_logpost_near_optimum_and_nonfinite():
+def test_logpost_near_optimum_and_nonfinite(resident_A):
     """points near a MAP optimum (boundary parameters at exp(-20)), and a point that overflows -> non-finite lp, not a
     crash (Stan rejects such points)."""
     freq, Z = load_spectrum('ZARC_uniform_0.25')
@@ -71,3 +71,15 @@ def test_logpost_near_optimum_and_nonfinite():
     u[2, -1] = 800.0  # d2_strength = exp(800) = inf
     lp, grad = prob.logpost_grad(torch.tensor(u))
     assert not np.isfinite(lp[2].item()) or not np.all(np.isfinite(grad[2].cpu().numpy()))
+
+
+def test_logpost_non_toeplitz_grid():
+    """measurement frequencies off the basis grid (jittered): A is not Toeplitz, the engine must keep the dense A."""
+    rng = np.random.RandomState(8)
+    freq, Z = load_spectrum('ZARC_uniform_0.25')
+    fj = freq * np.exp(rng.uniform(-0.05, 0.05, len(freq)))
+    ds = oracle_batch(fj, [Z, Z[::-1].copy()], basis_freq=np.logspace(6.5, -2.5, 91), mode='sample', nonneg=True)
+    prob = gpu_problem(ds)
+    u = rng.uniform(-1.5, 1.5, (9, prob.D))
+    for jac in (False, True):
+        _check(ds, prob, u, None, jac)

@@ -18,7 +18,7 @@ def _func(d):
     return f
 
 
-def test_lbfgs_first_iterations_match_oracle():
+def test_lbfgs_first_iterations_match_oracle(resident_A):
     """Same algorithm, same init: after a fixed small number of iterations (before round-off differences between the
     DMMA products and numpy's BLAS have been amplified by the ill-conditioning) the iterates agree closely."""
     freq, Z = load_spectrum('ZARC_uniform_0.25')
@@ -58,7 +58,7 @@ def test_lbfgs_converges_like_oracle():
     assert abs(lo - r['lp'][0].item()) <= 1e-10 * abs(lo)
 
 
-def test_lbfgs_batch_independent_of_batching():
+def test_lbfgs_batch_independent_of_batching(resident_A):
     """Results per spectrum are bitwise independent of which other spectra share the CTA / the batch."""
     from bayes_drt_b200 import synth
     freq, Z, _ = synth.make_spectra(24, seed=2)

@@ -59,7 +59,7 @@ def test_nuts_posterior_matches_oracle():
     assert 0.3 < np.median(r['stepsize'].cpu().numpy()) / np.median(gold['stepsize']) < 3.0
 
 
-def test_nuts_deterministic_and_shard_independent():
+def test_nuts_deterministic_and_shard_independent(resident_A):
     from bayes_drt_b200 import synth
     freq, Z, _ = synth.make_spectra(6, seed=4)
     _, bf = synth.bench_grid()

@@ -89,3 +89,61 @@ def test_oracle_map_lands_on_paper_drt(name, tol):
     gold = g[name + '/map_gamma']
     assert np.max(np.abs(gamma - gold)) <= tol * np.max(gold), np.max(np.abs(gamma - gold)) / np.max(gold)
     assert abs(c['Rinf'] * d['Z_scale'] - 1.0) < 0.02
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# Series-Parallel (DRT + transmissive planar DDT), the paper's two-distribution shape (Run fits.ipynb cell 20)
+# ---------------------------------------------------------------------------------------------------------------------
+def _sp_data(mode, nonneg, Nf=41, K=33):
+    from oracle import model_sp as osp
+    rng = np.random.RandomState(3)
+    freq = np.logspace(5, -1, Nf)
+    bf = np.logspace(5.5, -1.5, K)
+    # a DRT arc in series with a transmissive diffusion element
+    tau0, R1, n, Rd, td = 1e-3, 1.0, 0.8, 0.7, 0.3
+    w = 2 * np.pi * freq
+    Zd = Rd * np.tanh(np.sqrt(1j * w * td)) / np.sqrt(1j * w * td)
+    Z = 0.5 + R1 / (1 + (1j * w * tau0) ** n) + Zd
+    Z = Z + 0.002 * (rng.standard_normal(Nf) + 1j * rng.standard_normal(Nf))
+    ser = {'kernel': 'DRT', 'basis_freq': bf}
+    par = {'kernel': 'DDT', 'symmetry': 'planar', 'bc': 'transmissive', 'dist_type': 'parallel', 'basis_freq': bf,
+           'x_scale': 0.8}
+    return osp.prep_series_parallel(freq, Z, ser, par, mode=mode, nonneg=nonneg)
+
+
+@pytest.mark.parametrize('nonneg', [True, False])
+@pytest.mark.parametrize('mode', ['optimize', 'sample'])
+def test_series_parallel_logpost_matches_literal_autograd(nonneg, mode):
+    from oracle import model_sp as osp
+    from oracle.stan_literal import logpost_literal_sp
+    d = _sp_data(mode, nonneg)
+    D = osp.n_params(d)
+    assert D == 2 * (d['Ks'] + d['Kp']) + 12
+    rng = np.random.RandomState(9)
+    for jac in (False, True):
+        for scale in (0.3, 1.0):
+            u = rng.uniform(-scale, scale, D)
+            if not nonneg:
+                u[2:2 + d['Ks']] = np.abs(u[2:2 + d['Ks']])  # keep x_sum_raw >= 0 (Stan rejects otherwise)
+            lp, g = osp.logpost(u, d, jacobian=jac)
+            ut = torch.tensor(u, requires_grad=True)
+            lt = logpost_literal_sp(ut, d, jacobian=jac)
+            lt.backward()
+            assert abs(lp - lt.item()) <= 1e-12 * abs(lt.item())
+            gt = ut.grad.numpy()
+            assert np.max(np.abs(g - gt)) <= 1e-10 * np.max(np.abs(gt))
+    if not nonneg:  # validity check of the transformed parameter x_sum_raw
+        u = rng.uniform(-0.3, 0.3, D)
+        u[2:2 + d['Ks']] = -5.0
+        assert osp.logpost(u, d)[0] == -np.inf
+        assert logpost_literal_sp(torch.tensor(u), d).item() == -np.inf
+
+
+def test_series_parallel_constants_follow_reference():
+    d = _sp_data('optimize', True)
+    assert d['x_sum_invscale'] == 0.0 and d['xp_scale'] == 0.8 and (d['ups_alpha'], d['ups_beta']) == (0.05, 0.1)
+    k = d['Ks'] // 2
+    # inversion.py:1921-1926: L0s x 0.36, L0p x 0.54
+    assert np.isclose(d['Ls'][0][k, k], 0.36) and np.isclose(d['Lp'][0][k, k], 0.54)
+    s = _sp_data('sample', True)
+    assert s['x_sum_invscale'] == 1.0 and np.isclose(s['Lp'][0][k, k], 1.0)
