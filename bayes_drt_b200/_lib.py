@@ -24,7 +24,7 @@ KERNEL = {'DRT': 0, 'DDT': 1}
 DIST = {'series': 0, 'parallel': 1}
 SYM = {'planar': 0, 'spherical': 1}
 BC = {'transmissive': 0, 'blocking': 1}
-MODEL_SERIES, MODEL_POS, MODEL_OUTLIERS = 0, 16, 32
+MODEL_SERIES, MODEL_SERIES_PARALLEL, MODEL_POS, MODEL_OUTLIERS = 0, 1, 16, 32
 
 TERM_NAMES = {0: 'running', 10: 'absx', 20: 'absf', 21: 'relf', 30: 'absgrad', 31: 'relgrad', 40: 'maxit',
               -1: 'lsfail', -2: 'badinit'}
@@ -35,7 +35,9 @@ class SeriesData(C.Structure):
                 ('A', C.c_void_p), ('Z', C.c_void_p), ('freq', C.c_void_p), ('L', C.c_void_p),
                 ('sigma_min', C.c_double), ('ups_alpha', C.c_double), ('ups_beta', C.c_double),
                 ('induc_scale', C.c_double), ('sigma_out_lambda', C.c_double), ('sigma_out_alpha', C.c_double),
-                ('sigma_out_beta', C.c_double)]
+                ('sigma_out_beta', C.c_double),
+                ('Kp', C.c_int), ('Ap', C.c_void_p), ('Lp', C.c_void_p), ('x_sum_invscale', C.c_double),
+                ('xp_scale', C.c_double)]
 
 
 class LbfgsOpts(C.Structure):

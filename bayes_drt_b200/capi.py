@@ -68,7 +68,10 @@ class SeriesProblem:
     """Owns the device tensors behind one bdrt_series_data (keeps them alive for the duration of the calls)."""
 
     def __init__(self, A, Z, freq, L, nonneg=False, outliers=False, sigma_min=0.002, ups_alpha=0.05, ups_beta=0.1,
-                 induc_scale=1.0, sigma_out_lambda=10.0, sigma_out_alpha=2.0, sigma_out_beta=1.0, device=None):
+                 induc_scale=1.0, sigma_out_lambda=10.0, sigma_out_alpha=2.0, sigma_out_beta=1.0, device=None,
+                 Ap=None, Lp=None, x_sum_invscale=0.0, xp_scale=1.0):
+        """Series family: A, L describe the single DRT.  Series-Parallel (pass Ap, Lp): A, L describe the series
+        distribution, Ap [2Nf, Kp] / Lp [3, Kp, Kp] the parallel one (Stan data of inversion.py:1886-1959)."""
         self.ctx = context(device)
         dev = self.ctx.device
         self.A = f64(A, dev)
@@ -83,13 +86,24 @@ class SeriesProblem:
         self.per_spectrum_grid = self.A.dim() == 3
         if self.A.shape[-2] != n2 or self.freq.shape[-1] != self.Nf or tuple(self.L.shape) != (3, self.K, self.K):
             raise ValueError('inconsistent shapes in SeriesProblem')
+        self.series_parallel = Ap is not None
         d = SeriesData()
-        d.model = _lib.MODEL_SERIES | (_lib.MODEL_POS if nonneg else 0) | (_lib.MODEL_OUTLIERS if outliers else 0)
+        d.model = (_lib.MODEL_SERIES_PARALLEL if self.series_parallel else _lib.MODEL_SERIES) \
+            | (_lib.MODEL_POS if nonneg else 0) | (_lib.MODEL_OUTLIERS if outliers else 0)
         d.Nf, d.K, d.B = self.Nf, self.K, self.B
         d.per_spectrum_grid = int(self.per_spectrum_grid)
         d.A, d.Z, d.freq, d.L = self.A.data_ptr(), self.Z.data_ptr(), self.freq.data_ptr(), self.L.data_ptr()
         d.sigma_min, d.ups_alpha, d.ups_beta, d.induc_scale = sigma_min, ups_alpha, ups_beta, induc_scale
         d.sigma_out_lambda, d.sigma_out_alpha, d.sigma_out_beta = sigma_out_lambda, sigma_out_alpha, sigma_out_beta
+        self.Kp = 0
+        if self.series_parallel:
+            self.Ap, self.Lp = f64(Ap, dev), f64(Lp, dev)
+            self.Kp = self.Ap.shape[-1]
+            if self.Ap.shape[-2] != n2 or (self.Ap.dim() == 3) != self.per_spectrum_grid \
+                    or tuple(self.Lp.shape) != (3, self.Kp, self.Kp):
+                raise ValueError('inconsistent shapes of the parallel distribution in SeriesProblem')
+            d.Kp, d.Ap, d.Lp = self.Kp, self.Ap.data_ptr(), self.Lp.data_ptr()
+            d.x_sum_invscale, d.xp_scale = float(x_sum_invscale), float(xp_scale)
         self.c = d
         self.nonneg, self.outliers = bool(nonneg), bool(outliers)
         self.D = int(self.ctx.lib.bdrt_num_params(C.byref(d)))
@@ -169,12 +183,14 @@ class SeriesProblem:
 
     def split_outputs(self, out):
         """Named views of bdrt_constrain's packed output."""
-        K, Nf = self.K, self.Nf
+        K, Nf = self.K + self.Kp, self.Nf
         d = {'x': out[..., :K], 'Rinf': out[..., K], 'induc': out[..., K + 1], 'sigma_res': out[..., K + 2],
              'alpha_prop': out[..., K + 3], 'alpha_re': out[..., K + 4], 'alpha_im': out[..., K + 5],
              'sigma_tot': out[..., K + 6:K + 6 + 2 * Nf]}
         if self.outliers:
             d['sigma_out'] = out[..., K + 6 + 2 * Nf:]
+        if self.series_parallel:
+            d['xs'], d['xp'] = out[..., :self.K], out[..., self.K:K]
         return d
 
 

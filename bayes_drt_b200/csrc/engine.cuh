@@ -1,21 +1,27 @@
-// Fused log-posterior + analytic-gradient engine for the 'Series' family of Stan programs
-// (bayes_drt/stan_model_files/Series_modelcode.txt:24-69, Series_pos_modelcode.txt:27,
-//  Series_outliers_modelcode.txt:22-72, Series_pos_outliers_modelcode.txt:25).
+// Fused log-posterior + analytic-gradient engine for the reference's Stan programs
+//   'Series' family  (bayes_drt/stan_model_files/Series_modelcode.txt:24-69, Series_pos_modelcode.txt:27,
+//                     Series_outliers_modelcode.txt:22-72, Series_pos_outliers_modelcode.txt:25)            ND = 1
+//   'Series-Parallel' (Series-Parallel_modelcode.txt:32-107, Series-Parallel_pos_modelcode.txt:35)         ND = 2
 //
-// Execution model (B200): one persistent CTA of 8 warps per SM.  The CTA owns NSLOT = 8 "column slots"; slot s is
-// driven by warp s, which runs its own copy of the calling algorithm (L-BFGS, NUTS, ...) with ordinary warp-uniform
-// control flow.  Whenever the algorithms need log p and its gradient they all call engine_eval(): the stacked kernel
-// matrix A (2Nf x K, FP64) stays resident in shared memory for the lifetime of the CTA and the two dense products
-//     Zhat = A   X   (2Nf x K) (K x 8)     and     GX = A^T V   (K x 2Nf) (2Nf x 8)
+// Execution model (B200): persistent CTAs of 8 warps.  A CTA owns NSLOT = 8 "column slots"; slot s is driven by warp s,
+// which runs its own copy of the calling algorithm (L-BFGS, NUTS, ...) with ordinary warp-uniform control flow.
+// Whenever the algorithms need log p and its gradient they all call engine_eval(): the stacked kernel matrix of every
+// distribution stays resident in shared memory for the lifetime of the CTA and the dense products
+//     Zhat_d = A_d X_d   (2Nf x K_d) (K_d x 8)     and     G_d = A_d^T V_d   (K_d x 2Nf) (2Nf x 8)
 // are done cooperatively by all 8 warps for all 8 slots at once on the FP64 tensor cores
 // (mma.sync.m8n8k4.f64: the 8 slots are exactly the N=8 columns of the DMMA tile), while everything that is
 // per-slot and O(Nf + K) -- error model, residual weights, banded derivative stencils, hyper-priors, chain rule to
-// the unconstrained space -- is done by the slot's own warp with shuffle reductions.  Four CTA barriers per
+// the unconstrained space -- is done by the slot's own warp with shuffle reductions.  Five CTA barriers per
 // evaluation; no global-memory traffic besides the slot's own u / grad vectors and its spectrum Z.
 //
-// Shared-memory strides are chosen so that every DMMA fragment load is bank-conflict free without any swizzle:
-//   A [row][lda], lda % 16 in {4, 12}: the A-operand fragment of A (8 rows x 4 cols) and of A^T (4 rows x 8 cols) both
-//   hit 16 distinct 8-byte banks per half-warp;  X / V [slot][ldxv] with the same rule for the B-operand fragment.
+// Resident operand, two layouts (template parameter TOEP):
+//   dense    A_d [row][lda], lda % 16 in {4, 12}: the A-operand fragment of A (8 rows x 4 cols) and of A^T (4 rows x 8
+//            cols) both hit 16 distinct 8-byte banks per half-warp, no swizzle; one CTA per SM (A alone is ~115 kB);
+//   Toeplitz when both grids are log-uniform with the same spacing (the reference's own special case,
+//            matrices.py:145-242) A_re / A_im only depend on (col - row): two 1-D tables per distribution replace the
+//            dense matrix, fragment loads become broadcast table look-ups, and two CTAs fit on an SM.
+// Inside the engine the stacked vectors are laid out [re: nfp | im: nfp] with nfp = Nf rounded up to 8, so that neither
+// an 8-row tile nor a 4-row k-step straddles the two parts.
 #pragma once
 #include "common.cuh"
 
@@ -25,32 +31,42 @@
 #define MAXBW 24
 #define LBW (2 * MAXBW + 1)
 #define LOG_015 (-1.8971199848858813)  // log(0.15)
+#define MAXD 2                          // distributions per model
 
-#define F_POS 1
-#define F_OUT 2
+#define F_POS 1  // lower=0 coefficients of the series distribution (x = exp(u))
+#define F_OUT 2  // outlier error model (Series family only)
+
+struct BdrtDist {
+  int K, kpad4, kpad8, lda, lt;
+  int off_x, off_ups, off_d;  // offsets of x, ups_raw, d_strength inside the unconstrained vector
+  int oA, oTap;               // shared-memory offsets (doubles) of the resident operand and of the stencil taps
+  int pos;                    // coefficients are lower=0
+  int toepL;                  // L0/L1/L2 are Toeplitz: use the tap table
+  const double* A;            // [2Nf, K] or [B, 2Nf, K]
+  long long A_stride;         // per-spectrum stride (0: shared)
+  const double* Lb;           // [3][K][LBW] banded copies of the scaled L0, L1, L2
+  double ascale;              // the resident operand is A * ascale (xp = xp_raw * xp_scale, Series-Parallel :52)
+};
 
 struct BdrtModel {
-  int flags, Nf, K, N2, D, B;
-  int lda, ldxv, ldzg;
-  int kpad4, kpad8;
-  int nfp;    // Nf rounded up to a multiple of 8: inside the engine the stacked vectors are [re: nfp | im: nfp]
+  int flags, ND, Nf, N2, D, B;
+  BdrtDist d[MAXD];
+  int Kmax, ldxv, ldzg;
+  int nfp;    // Nf rounded up to a multiple of 8
   int n2p;    // 2 * nfp
-  int toepA;  // A_re / A_im are Toeplitz (shared log-uniform grid): resident operand = two 1-D tables of length lt
-  int lt;     // nfp + kpad8
-  int off_so, off_ups, off_d;
-  int bw, toeplitz;
-  const double* A;
-  long long A_stride;  // per-spectrum stride (0: shared)
+  int toepA;  // Toeplitz-resident operands
+  int off_err, off_so;
+  int bw;
   const double* freq;
   long long f_stride;
-  const double* Z;   // [B, N2]
-  const double* Lb;  // [3][K][LBW] banded copies of the scaled L0, L1, L2
-  double sigma_min2, ups_alpha, ups_beta, induc_scale, so_lambda, so_alpha, so_beta;
+  const double* Z;  // [B, N2]
+  double sigma_min2, ups_alpha, ups_beta, induc_scale, so_lambda, so_alpha, so_beta, x_sum_invscale;
   // shared-memory carve-up, in doubles
-  int oA, oXV, oZG, oSt, oTap, oOm, oUser;
+  int oXV, oZG, oSt, oOm, oUser;
   int xoff;  // offset of the data inside an X/V row (= bw: zero margin for the stencils)
-  int ws;    // stride of one stencil scratch vector (K + 2 bw, zero margins)
-  int st;    // per-slot scratch size
+  int ws;    // stride of one stencil scratch vector (Kmax + 2 bw, zero margins)
+  int sd;    // per-slot, per-distribution scratch: W0 | W1 | W2 (ws each) | ups (Kmax) | 1/ups (Kmax)
+  int st;    // per-slot scratch size: ND * sd | scalars (16) | sigma_out raw, scale (2 Nf)
 };
 
 static inline int bdrt_pad_stride(int n) {  // smallest s >= n with s % 16 in {4, 12}
@@ -59,34 +75,53 @@ static inline int bdrt_pad_stride(int n) {  // smallest s >= n with s % 16 in {4
   return s;
 }
 
-// Fills the derived fields of m (everything but the pointers / scalars).  Returns doubles of engine smem.
+// Fills the derived fields of m (everything but the pointers / scalars; needs ND, Nf, d[].K, d[].pos, flags, bw, toepA).
+// Returns the doubles of engine shared memory.
 static inline int bdrt_model_layout(BdrtModel* m) {
   m->N2 = 2 * m->Nf;
-  m->kpad4 = (m->K + 3) / 4 * 4;
-  m->kpad8 = (m->K + 7) / 8 * 8;
   m->nfp = (m->Nf + 7) / 8 * 8;
   m->n2p = 2 * m->nfp;
-  m->lt = m->nfp + m->kpad8;
-  m->lda = bdrt_pad_stride(m->K);
   m->xoff = m->bw;
-  int kx = m->kpad4 > m->K + m->bw ? m->kpad4 : m->K + m->bw;
-  int mx = kx > m->n2p ? kx : m->n2p;
+  m->Kmax = 0;
+  int kx = 0, k8 = 0;
+  for (int i = 0; i < m->ND; ++i) {
+    BdrtDist& d = m->d[i];
+    d.kpad4 = (d.K + 3) / 4 * 4;
+    d.kpad8 = (d.K + 7) / 8 * 8;
+    d.lt = m->nfp + d.kpad8;
+    d.lda = bdrt_pad_stride(d.K);
+    if (d.K > m->Kmax) m->Kmax = d.K;
+    const int k = d.kpad4 > d.K + m->bw ? d.kpad4 : d.K + m->bw;
+    if (k > kx) kx = k;
+    if (d.kpad8 > k8) k8 = d.kpad8;
+  }
+  const int mx = kx > m->n2p ? kx : m->n2p;
   m->ldxv = bdrt_pad_stride(m->xoff + mx);
-  m->ws = m->K + 2 * m->bw;
-  // per-slot scratch: W0 | W1 | W2 (ws each) | ups (K) | 1/ups (K) | scalars (16) | sigma_out raw, scale (2 Nf)
-  m->st = 3 * m->ws + 2 * m->K + 16 + ((m->flags & F_OUT) ? 2 * m->Nf : 0);
-  int mz = m->kpad8 > m->n2p ? m->kpad8 : m->n2p;
+  m->ws = m->Kmax + 2 * m->bw;
+  m->sd = 3 * m->ws + 2 * m->Kmax;
+  m->st = m->ND * m->sd + 16 + ((m->flags & F_OUT) ? 2 * m->Nf : 0);
+  const int mz = k8 > m->n2p ? k8 : m->n2p;
   m->ldzg = mz + 4;  // % 8 == 4
-  m->off_so = 6 + m->K;
-  m->off_ups = 6 + m->K + ((m->flags & F_OUT) ? 2 * m->Nf : 0);
-  m->off_d = m->off_ups + m->K;
-  m->D = m->off_d + 3;
-  int o = 0;
-  m->oA = o;   o += m->toepA ? 2 * m->lt : m->n2p * m->lda + 8;
-  m->oXV = o;  o += NSLOT * m->ldxv;
-  m->oZG = o;  o += NSLOT * m->ldzg;
+  // unconstrained vector, Stan declaration order:
+  //   Rinf_raw induc_raw | x_0 .. x_{ND-1} | sigma_res alpha_prop alpha_re alpha_im | [sigma_out_raw sigma_out_scale] |
+  //   ups_0 .. ups_{ND-1} | d_0(3) .. d_{ND-1}(3)
+  int o = 2;
+  for (int i = 0; i < m->ND; ++i) { m->d[i].off_x = o; o += m->d[i].K; }
+  m->off_err = o; o += 4;
+  m->off_so = o;
+  if (m->flags & F_OUT) o += 2 * m->Nf;
+  for (int i = 0; i < m->ND; ++i) { m->d[i].off_ups = o; o += m->d[i].K; }
+  for (int i = 0; i < m->ND; ++i) { m->d[i].off_d = o; o += 3; }
+  m->D = o;
+  o = 0;
+  for (int i = 0; i < m->ND; ++i) {
+    m->d[i].oA = o;
+    o += m->toepA ? 2 * m->d[i].lt : m->n2p * m->d[i].lda + 8;
+  }
+  m->oXV = o;  o += m->ND * NSLOT * m->ldxv;
+  m->oZG = o;  o += m->ND * NSLOT * m->ldzg;
   m->oSt = o;  o += NSLOT * m->st;
-  m->oTap = o; o += 3 * LBW;
+  for (int i = 0; i < m->ND; ++i) { m->d[i].oTap = o; o += 3 * LBW; }
   m->oOm = o;  o += m->Nf;
   o = (o + 1) & ~1;
   m->oUser = o;
@@ -104,36 +139,46 @@ __device__ __forceinline__ void cta_sync() {
   asm volatile("bar.sync 0;" ::: "memory");
 }
 
+// Is coordinate i of the unconstrained vector a lower=0 parameter (theta = exp(u))?
+__device__ __forceinline__ bool bdrt_is_exp(const BdrtModel& m, int i) {
+  for (int dd = 0; dd < m.ND; ++dd)
+    if (!m.d[dd].pos && i >= m.d[dd].off_x && i < m.d[dd].off_x + m.d[dd].K) return false;
+  return true;
+}
+
 // Cooperative load of the resident operands.  Called by all threads once (or once per spectrum when the grid is
 // per-spectrum); ends with a CTA barrier.
 __device__ inline void engine_load(const BdrtModel& m, double* sm, long long spec) {
-  double* sA = sm + m.oA;
-  const double* gA = m.A + spec * m.A_stride;
   const int tid = threadIdx.x;
-  if (m.toepA) {
-    // table of part p: T_p[(col - row) + nfp - 1] = A_p[row][col]; first row for col - row >= 0, first column below
-    for (int i = tid; i < 2 * m.lt; i += NTHREADS) {
-      const int p = i >= m.lt, d = i - p * m.lt - (m.nfp - 1);
-      double v = 0.0;
-      if (d >= 0 && d < m.K) v = gA[(long long)p * m.Nf * m.K + d];
-      else if (d < 0 && -d < m.Nf) v = gA[((long long)p * m.Nf - d) * m.K];
-      sA[i] = v;
+  for (int dd = 0; dd < m.ND; ++dd) {
+    const BdrtDist& D = m.d[dd];
+    double* sA = sm + D.oA;
+    const double* gA = D.A + spec * D.A_stride;
+    if (m.toepA) {
+      // table of part p: T_p[(col - row) + nfp - 1] = A_p[row][col]; first row for col - row >= 0, first column below
+      for (int i = tid; i < 2 * D.lt; i += NTHREADS) {
+        const int p = i >= D.lt, d = i - p * D.lt - (m.nfp - 1);
+        double v = 0.0;
+        if (d >= 0 && d < D.K) v = gA[(long long)p * m.Nf * D.K + d];
+        else if (d < 0 && -d < m.Nf) v = gA[((long long)p * m.Nf - d) * D.K];
+        sA[i] = v * D.ascale;
+      }
+    } else {
+      for (int i = tid; i < m.n2p * D.lda + 8; i += NTHREADS) {
+        const int rp = i / D.lda, c = i - rp * D.lda;
+        const int p = rp >= m.nfp, r = rp - p * m.nfp;  // padded row -> (part, row)
+        sA[i] = (rp < m.n2p && r < m.Nf && c < D.K) ? gA[((long long)p * m.Nf + r) * D.K + c] * D.ascale : 0.0;
+      }
     }
-  } else {
-    for (int i = tid; i < m.n2p * m.lda + 8; i += NTHREADS) {
-      const int rp = i / m.lda, c = i - rp * m.lda;
-      const int p = rp >= m.nfp, r = rp - p * m.nfp;  // padded row -> (part, row)
-      sA[i] = (rp < m.n2p && r < m.Nf && c < m.K) ? gA[((long long)p * m.Nf + r) * m.K + c] : 0.0;  // coalesced along c
+    // Toeplitz taps: row K/2 of the banded copies
+    for (int i = tid; i < 3 * LBW; i += NTHREADS) {
+      const int j = i / LBW, d = i - j * LBW;
+      sm[D.oTap + i] = D.Lb[((long long)j * D.K + D.K / 2) * LBW + d];
     }
   }
-  for (int i = tid; i < NSLOT * m.ldxv; i += NTHREADS) sm[m.oXV + i] = 0.0;
-  for (int i = tid; i < NSLOT * m.ldzg; i += NTHREADS) sm[m.oZG + i] = 0.0;
+  for (int i = tid; i < m.ND * NSLOT * m.ldxv; i += NTHREADS) sm[m.oXV + i] = 0.0;
+  for (int i = tid; i < m.ND * NSLOT * m.ldzg; i += NTHREADS) sm[m.oZG + i] = 0.0;
   for (int i = tid; i < NSLOT * m.st; i += NTHREADS) sm[m.oSt + i] = 0.0;
-  // Toeplitz taps: row K/2 of the banded copies
-  for (int i = tid; i < 3 * LBW; i += NTHREADS) {
-    const int j = i / LBW, d = i - j * LBW;
-    sm[m.oTap + i] = m.Lb[((long long)j * m.K + m.K / 2) * LBW + d];
-  }
   const double* f = m.freq + spec * m.f_stride;
   for (int i = tid; i < m.Nf; i += NTHREADS) sm[m.oOm + i] = 2.0 * M_PI * f[i];
   cta_sync();
@@ -146,226 +191,268 @@ __device__ inline void engine_load(const BdrtModel& m, double* sm, long long spe
 //   nact/snap: optional CTA-wide "slots still working" counter; *snap receives its value at a point where no warp can
 //           be modifying it (between the first and last barrier), so every warp of the CTA reads the same value.
 // Returns lp (non-finite lp or gradient entries must be checked by the caller).
-template <int TOEP>
+template <int TOEP, int ND>
 __device__ inline double engine_eval(const BdrtModel& m, double* sm, bool active, const double* u, double* grad,
                                      const double* Zs, int jacobian, const volatile int* nact = nullptr,
                                      int* snap = nullptr) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int slot = warp;
-  const int K = m.K, Nf = m.Nf, bw = m.bw;
-  const bool pos = m.flags & F_POS, outl = m.flags & F_OUT;
-  double* sA = sm + m.oA;
-  double* sX = sm + m.oXV + slot * m.ldxv + m.xoff;  // x_k at sX[k], zero margins of width bw on both sides
-  double* sZ = sm + m.oZG + slot * m.ldzg;
-  double* sW = sm + m.oSt + slot * m.st + bw;         // W_j[k] at sW[j * ws + k], zero margins
-  double* sUps = sm + m.oSt + slot * m.st + 3 * m.ws;
-  double* sIu = sUps + K;
-  double* sTh = sIu + K;   // Rinf_raw, induc_raw, sigma_res_raw, alpha_prop/re/im_raw, d0, d1, d2
-  double* sSo = sTh + 16;  // sigma_out_raw [Nf], sigma_out_scale [Nf]
-  const double* sTap = sm + m.oTap + MAXBW;  // tap_j[d] at sTap[j * LBW + d]
+  const int Nf = m.Nf, bw = m.bw, nfp = m.nfp;
+  const bool outl = (ND == 1) && (m.flags & F_OUT);
+  double* sSt = sm + m.oSt + slot * m.st;
+  double* sTh = sSt + ND * m.sd;  // Rinf_raw, induc_raw, sigma_res_raw, alpha_prop/re/im_raw, d_0(3) [, d_1(3)]
+  double* sSo = sTh + 16;         // sigma_out_raw [Nf], sigma_out_scale [Nf]
   const double* sOm = sm + m.oOm;
   const double jac = jacobian ? 1.0 : 0.0;
+  // per-distribution views of the slot's rows
+  auto rowX = [&](int dd) { return sm + m.oXV + (dd * NSLOT + slot) * m.ldxv + m.xoff; };  // x_k at [k], zero margins
+  auto rowZ = [&](int dd) { return sm + m.oZG + (dd * NSLOT + slot) * m.ldzg; };
 
   double lp = 0.0;
+  double xsum = 0.0;  // sum(xs) + sum(xp_raw)  (Series-Parallel :56)
   // ---------------------------------------------------------------- phase 1: transforms, priors, stencils (per slot)
   if (active) {
-    // 1a. theta = exp(u) for every lower=0 parameter, scattered to the slot's scratch (one coalesced pass over u)
     double ujac = 0.0;
-    for (int i = lane; i < m.D; i += 32) {
+    // 1a. scalars: theta = exp(u)
+    if (lane < 6 + 3 * ND) {
+      const int i = lane < 2 ? lane : (lane < 6 ? m.off_err + lane - 2 : m.d[0].off_d + lane - 6);
       const double ui = u[i];
-      const bool isx = (i >= 2) && (i < 2 + K);
-      const double th = (isx && !pos) ? ui : exp(ui);
-      if (!isx || pos) ujac += ui;
-      if (isx)
-        sX[i - 2] = th;
-      else if (i < 2)
-        sTh[i] = th;
-      else if (i < 6 + K)
-        sTh[i - K] = th;  // 2+K..5+K -> 2..5
-      else if (i < m.off_ups)
-        sSo[i - m.off_so] = th;
-      else if (i < m.off_d) {
-        const double ups = 0.15 * th;
-        sUps[i - m.off_ups] = ups;
-        sIu[i - m.off_ups] = 1.0 / ups;
-      } else
-        sTh[6 + i - m.off_d] = th;
+      ujac += ui;
+      sTh[lane] = exp(ui);
     }
-    {
-      const int kend = (m.kpad4 > K + bw) ? m.kpad4 : K + bw;
+    if (outl) {
+      for (int i = lane; i < 2 * Nf; i += 32) {
+        const double ui = u[m.off_so + i];
+        ujac += ui;
+        sSo[i] = exp(ui);
+      }
+    }
+#pragma unroll
+    for (int dd = 0; dd < ND; ++dd) {
+      const BdrtDist& Dd = m.d[dd];
+      const int K = Dd.K;
+      double* sX = rowX(dd);
+      double* sUps = sSt + dd * m.sd + 3 * m.ws;
+      double* sIu = sUps + m.Kmax;
+      for (int k = lane; k < K; k += 32) {
+        const double ux = u[Dd.off_x + k], uu = u[Dd.off_ups + k];
+        const double xv = Dd.pos ? exp(ux) : ux;
+        const double ups = 0.15 * exp(uu);
+        sX[k] = xv;
+        sUps[k] = ups;
+        sIu[k] = 1.0 / ups;
+        ujac += uu + (Dd.pos ? ux : 0.0);
+        if (ND > 1) xsum += xv;
+      }
+      const int kend = (Dd.kpad4 > K + bw) ? Dd.kpad4 : K + bw;
       for (int k = K + lane; k < kend; k += 32) sX[k] = 0.0;  // right margin (phase 3 of the previous call wrote V here)
     }
     __syncwarp();
-    const double d0 = sTh[6], d1 = sTh[7], d2 = sTh[8];
-    double sa0 = 0, sa1 = 0, sa2 = 0;
     // 1b. a_j = L_j x (banded), q^2, hyper-priors, d lp / d ups, W_j = d_j a_j / ups^2
-    for (int kb = 0; kb < K; kb += 128) {
-      double a0[4] = {0, 0, 0, 0}, a1[4] = {0, 0, 0, 0}, a2[4] = {0, 0, 0, 0};
-      if (m.toeplitz) {
-        for (int d = -bw; d <= bw; ++d) {
-          const double t0 = sTap[d], t1 = sTap[LBW + d], t2 = sTap[2 * LBW + d];
+#pragma unroll
+    for (int dd = 0; dd < ND; ++dd) {
+      const BdrtDist& Dd = m.d[dd];
+      const int K = Dd.K;
+      const double* sX = rowX(dd);
+      double* sW = sSt + dd * m.sd + bw;  // W_j[k] at sW[j * ws + k], zero margins
+      const double* sUps = sSt + dd * m.sd + 3 * m.ws;
+      const double* sIu = sUps + m.Kmax;
+      const double* sTap = sm + Dd.oTap + MAXBW;  // tap_j[d] at sTap[j * LBW + d]
+      const double d0 = sTh[6 + 3 * dd], d1 = sTh[7 + 3 * dd], d2 = sTh[8 + 3 * dd];
+      double sa0 = 0, sa1 = 0, sa2 = 0;
+      for (int kb = 0; kb < K; kb += 128) {
+        double a0[4] = {0, 0, 0, 0}, a1[4] = {0, 0, 0, 0}, a2[4] = {0, 0, 0, 0};
+        if (Dd.toepL) {
+          for (int d = -bw; d <= bw; ++d) {
+            const double t0 = sTap[d], t1 = sTap[LBW + d], t2 = sTap[2 * LBW + d];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const int k = kb + lane + 32 * j;
+              const double xv = (k < K) ? sX[k + d] : 0.0;
+              a0[j] = fma(t0, xv, a0[j]);
+              a1[j] = fma(t1, xv, a1[j]);
+              a2[j] = fma(t2, xv, a2[j]);
+            }
+          }
+        } else {
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
             const int k = kb + lane + 32 * j;
-            const double xv = (k < K) ? sX[k + d] : 0.0;
-            a0[j] = fma(t0, xv, a0[j]);
-            a1[j] = fma(t1, xv, a1[j]);
-            a2[j] = fma(t2, xv, a2[j]);
+            if (k < K) {
+              const double* l0 = Dd.Lb + (long long)k * LBW + MAXBW;
+              const double* l1 = l0 + (long long)K * LBW;
+              const double* l2 = l1 + (long long)K * LBW;
+              for (int d = -bw; d <= bw; ++d) {
+                const double xv = sX[k + d];
+                a0[j] = fma(__ldg(l0 + d), xv, a0[j]);
+                a1[j] = fma(__ldg(l1 + d), xv, a1[j]);
+                a2[j] = fma(__ldg(l2 + d), xv, a2[j]);
+              }
+            }
           }
         }
-      } else {
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
           const int k = kb + lane + 32 * j;
           if (k < K) {
-            const double* l0 = m.Lb + (long long)k * LBW + MAXBW;
-            const double* l1 = l0 + (long long)K * LBW;
-            const double* l2 = l1 + (long long)K * LBW;
-            for (int d = -bw; d <= bw; ++d) {
-              const double xv = sX[k + d];
-              a0[j] = fma(__ldg(l0 + d), xv, a0[j]);
-              a1[j] = fma(__ldg(l1 + d), xv, a1[j]);
-              a2[j] = fma(__ldg(l2 + d), xv, a2[j]);
+            const double ups = sUps[k], iu = sIu[k], iu2 = iu * iu;
+            const double uk = u[Dd.off_ups + k];
+            const double q2 = d0 * a0[j] * a0[j] + d1 * a1[j] * a1[j] + d2 * a2[j] * a2[j];
+            // q ~ normal(0, ups): -1/2 q^2/ups^2 - log ups ;  ups_raw ~ inv_gamma(alpha, beta)
+            lp += -0.5 * q2 * iu2 - (LOG_015 + uk) - (m.ups_alpha + 1.0) * uk - m.ups_beta * 0.15 * iu;
+            sa0 = fma(a0[j] * a0[j], iu2, sa0);
+            sa1 = fma(a1[j] * a1[j], iu2, sa1);
+            sa2 = fma(a2[j] * a2[j], iu2, sa2);
+            sW[k] = d0 * a0[j] * iu2;
+            sW[m.ws + k] = d1 * a1[j] * iu2;
+            sW[2 * m.ws + k] = d2 * a2[j] * iu2;
+            // dups_j = 0.5 - 0.25 (ups_j + ups_{j+2}) / ups_{j+1},  j = 0..K-3   (Series_modelcode.txt:51-53)
+            double gu = q2 * iu2 * iu - iu;
+            if (k + 2 < K) {  // k is the left point of dups_k
+              const double e = 0.5 - 0.25 * (ups + sUps[k + 2]) * sIu[k + 1];
+              gu += e * 0.25 * sIu[k + 1];
+              lp += -0.5 * e * e;
+            }
+            if (k >= 1 && k + 1 < K) {  // middle point of dups_{k-1}
+              const double sum = sUps[k - 1] + sUps[k + 1];
+              const double e = 0.5 - 0.25 * sum * iu;
+              gu -= e * 0.25 * sum * iu2;
+            }
+            if (k >= 2) {  // right point of dups_{k-2}
+              const double e = 0.5 - 0.25 * (sUps[k - 2] + ups) * sIu[k - 1];
+              gu += e * 0.25 * sIu[k - 1];
+            }
+            grad[Dd.off_ups + k] = gu * ups - (m.ups_alpha + 1.0) + m.ups_beta * 0.15 * iu + jac;
+          }
+        }
+      }
+      __syncwarp();
+      // 1c. prior part of d lp / d x:  - sum_j L_j^T W_j
+      for (int kb = 0; kb < K; kb += 128) {
+        double acc[4] = {0, 0, 0, 0};
+        if (Dd.toepL) {
+          double b1[4] = {0, 0, 0, 0}, b2[4] = {0, 0, 0, 0};
+          const double* w0 = sW + kb + lane;  // lanes past K read the (zero / neighbouring) scratch: never stored
+          for (int d = -bw; d <= bw; ++d) {   // row n = k + d, column k -> tap_j[-d]
+            const double t0 = sTap[-d], t1 = sTap[LBW - d], t2 = sTap[2 * LBW - d];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const int kc = (kb + lane + 32 * j < K) ? 32 * j : 0;
+              acc[j] = fma(t0, w0[kc + d], acc[j]);
+              b1[j] = fma(t1, w0[m.ws + kc + d], b1[j]);
+              b2[j] = fma(t2, w0[2 * m.ws + kc + d], b2[j]);
             }
           }
-        }
-      }
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const int k = kb + lane + 32 * j;
-        if (k < K) {
-          const double ups = sUps[k], iu = sIu[k], iu2 = iu * iu;
-          const double uk = u[m.off_ups + k];
-          const double q2 = d0 * a0[j] * a0[j] + d1 * a1[j] * a1[j] + d2 * a2[j] * a2[j];
-          // q ~ normal(0, ups): -1/2 q^2/ups^2 - log ups ;  ups_raw ~ inv_gamma(alpha, beta): -(alpha+1) log - beta/ups_raw
-          lp += -0.5 * q2 * iu2 - (LOG_015 + uk) - (m.ups_alpha + 1.0) * uk - m.ups_beta * 0.15 * iu;
-          sa0 = fma(a0[j] * a0[j], iu2, sa0);
-          sa1 = fma(a1[j] * a1[j], iu2, sa1);
-          sa2 = fma(a2[j] * a2[j], iu2, sa2);
-          sW[k] = d0 * a0[j] * iu2;
-          sW[m.ws + k] = d1 * a1[j] * iu2;
-          sW[2 * m.ws + k] = d2 * a2[j] * iu2;
-          // dups_j = 0.5 - 0.25 (ups_j + ups_{j+2}) / ups_{j+1},  j = 0..K-3   (Series_modelcode.txt:51-53)
-          double gu = q2 * iu2 * iu - iu;
-          if (k + 2 < K) {  // k is the left point of dups_k
-            const double e = 0.5 - 0.25 * (ups + sUps[k + 2]) * sIu[k + 1];
-            gu += e * 0.25 * sIu[k + 1];
-            lp += -0.5 * e * e;
-          }
-          if (k >= 1 && k + 1 < K) {  // middle point of dups_{k-1}
-            const double sum = sUps[k - 1] + sUps[k + 1];
-            const double e = 0.5 - 0.25 * sum * iu;
-            gu -= e * 0.25 * sum * iu2;
-          }
-          if (k >= 2) {  // right point of dups_{k-2}
-            const double e = 0.5 - 0.25 * (sUps[k - 2] + ups) * sIu[k - 1];
-            gu += e * 0.25 * sIu[k - 1];
-          }
-          grad[m.off_ups + k] = gu * ups - (m.ups_alpha + 1.0) + m.ups_beta * 0.15 * iu + jac;
-        }
-      }
-    }
-    __syncwarp();
-    // 1c. prior part of d lp / d x:  - sum_j L_j^T W_j
-    for (int kb = 0; kb < K; kb += 128) {
-      double acc[4] = {0, 0, 0, 0};
-      if (m.toeplitz) {
-        double b1[4] = {0, 0, 0, 0}, b2[4] = {0, 0, 0, 0};
-        const double* w0 = sW + kb + lane;  // lanes past K read the (zero / neighbouring) scratch: never stored
-        for (int d = -bw; d <= bw; ++d) {   // row n = k + d, column k -> tap_j[-d]
-          const double t0 = sTap[-d], t1 = sTap[LBW - d], t2 = sTap[2 * LBW - d];
+          for (int j = 0; j < 4; ++j) acc[j] += b1[j] + b2[j];
+        } else {
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
-            const int kc = (kb + lane + 32 * j < K) ? 32 * j : 0;
-            acc[j] = fma(t0, w0[kc + d], acc[j]);
-            b1[j] = fma(t1, w0[m.ws + kc + d], b1[j]);
-            b2[j] = fma(t2, w0[2 * m.ws + kc + d], b2[j]);
-          }
-        }
-#pragma unroll
-        for (int j = 0; j < 4; ++j) acc[j] += b1[j] + b2[j];
-      } else {
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const int k = kb + lane + 32 * j;
-          if (k < K) {
-            const int dlo = (k - bw < 0) ? -k : -bw, dhi = (k + bw > K - 1) ? (K - 1 - k) : bw;
-            for (int d = dlo; d <= dhi; ++d) {
-              const double* l0 = m.Lb + (long long)(k + d) * LBW + MAXBW - d;
-              acc[j] = fma(__ldg(l0), sW[k + d], acc[j]);
-              acc[j] = fma(__ldg(l0 + (long long)K * LBW), sW[m.ws + k + d], acc[j]);
-              acc[j] = fma(__ldg(l0 + 2LL * K * LBW), sW[2 * m.ws + k + d], acc[j]);
+            const int k = kb + lane + 32 * j;
+            if (k < K) {
+              const int dlo = (k - bw < 0) ? -k : -bw, dhi = (k + bw > K - 1) ? (K - 1 - k) : bw;
+              for (int d = dlo; d <= dhi; ++d) {
+                const double* l0 = Dd.Lb + (long long)(k + d) * LBW + MAXBW - d;
+                acc[j] = fma(__ldg(l0), sW[k + d], acc[j]);
+                acc[j] = fma(__ldg(l0 + (long long)K * LBW), sW[m.ws + k + d], acc[j]);
+                acc[j] = fma(__ldg(l0 + 2LL * K * LBW), sW[2 * m.ws + k + d], acc[j]);
+              }
             }
           }
         }
-      }
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const int k = kb + lane + 32 * j;
-        if (k < K) grad[2 + k] = -acc[j];
+        for (int j = 0; j < 4; ++j) {
+          const int k = kb + lane + 32 * j;
+          if (k < K) grad[Dd.off_x + k] = -acc[j];
+        }
+      }
+      sa0 = warp_sum(sa0);
+      sa1 = warp_sum(sa1);
+      sa2 = warp_sum(sa2);
+      if (lane == 0) {
+        // d_j ~ inv_gamma(5, 5): -6 log d - 5/d
+        lp += -6.0 * (u[Dd.off_d] + u[Dd.off_d + 1] + u[Dd.off_d + 2]) - 5.0 / d0 - 5.0 / d1 - 5.0 / d2;
+        grad[Dd.off_d] = -0.5 * sa0 * d0 - 6.0 + 5.0 / d0 + jac;
+        grad[Dd.off_d + 1] = -0.5 * sa1 * d1 - 6.0 + 5.0 / d1 + jac;
+        grad[Dd.off_d + 2] = -0.5 * sa2 * d2 - 6.0 + 5.0 / d2 + jac;
       }
     }
-    sa0 = warp_sum(sa0);
-    sa1 = warp_sum(sa1);
-    sa2 = warp_sum(sa2);
-    if (lane == 0) {
-      // d_j ~ inv_gamma(5, 5): -6 log d - 5/d ; half-normal priors on the six scalar raw parameters
-      lp += -6.0 * (u[m.off_d] + u[m.off_d + 1] + u[m.off_d + 2]) - 5.0 / d0 - 5.0 / d1 - 5.0 / d2;
+    if (lane == 0) {  // half-normal priors on the six scalar raw parameters
       double ss = 0.0;
 #pragma unroll
       for (int i = 0; i < 6; ++i) ss = fma(sTh[i], sTh[i], ss);
       lp += -0.5 * ss;
-      grad[m.off_d] = -0.5 * sa0 * d0 - 6.0 + 5.0 / d0 + jac;
-      grad[m.off_d + 1] = -0.5 * sa1 * d1 - 6.0 + 5.0 / d1 + jac;
-      grad[m.off_d + 2] = -0.5 * sa2 * d2 - 6.0 + 5.0 / d2 + jac;
+    }
+    if (ND > 1) {
+      xsum = warp_sum(xsum);
+      // x_sum = x_sum_raw * x_sum_invscale ~ std_normal(); real<lower=0> x_sum_raw is validity-checked by Stan (:56-57)
+      if (lane == 0) lp += (xsum < 0.0) ? -INFINITY : -0.5 * (xsum * m.x_sum_invscale) * (xsum * m.x_sum_invscale);
     }
     if (jacobian) lp += ujac;
   } else {
-    const int kend = (m.kpad4 > K + bw) ? m.kpad4 : K + bw;
-    for (int k = lane; k < kend; k += 32) sX[k] = 0.0;
+#pragma unroll
+    for (int dd = 0; dd < ND; ++dd) {
+      double* sX = rowX(dd);
+      const int kend = (m.d[dd].kpad4 > m.d[dd].K + bw) ? m.d[dd].kpad4 : m.d[dd].K + bw;
+      for (int k = lane; k < kend; k += 32) sX[k] = 0.0;
+    }
   }
   cta_sync();
   if (snap) *snap = *nact;
 
-  // ---------------------------------------------------------------- phase 2: Zhat = A X on the FP64 tensor cores
+  // ---------------------------------------------------------------- phase 2: Zhat_d = A_d X_d on the FP64 tensor cores
   const int g = lane >> 2, t = lane & 3;
   {
-    const double* bp = sm + m.oXV + g * m.ldxv + m.xoff + t;
-    double* zg = sm + m.oZG;
     const int nmt = m.n2p >> 3;
-    for (int mt = warp; mt < nmt; mt += 2 * NWARP) {
-      const int mt2 = mt + NWARP;
-      const bool two = mt2 < nmt;
+    for (int ti = warp; ti < ND * nmt; ti += 2 * NWARP) {
+      const int ti2 = ti + NWARP;
+      const bool two = ti2 < ND * nmt;
+      const int tj = two ? ti2 : ti;
+      const int da = (ND > 1 && ti >= nmt) ? 1 : 0, db = (ND > 1 && tj >= nmt) ? 1 : 0;
+      const int mt = ti - da * nmt, mt2 = tj - db * nmt;
+      const BdrtDist &Da = m.d[da], &Db = m.d[db];
       const double *a0p, *a1p;
       if (TOEP) {  // A_p[row][col] = T_p[col - row + nfp - 1]
-        const int r0 = mt * 8 + g, r1 = (two ? mt2 : mt) * 8 + g;
-        const int p0 = r0 >= m.nfp, p1 = r1 >= m.nfp;
-        a0p = sA + p0 * m.lt + (m.nfp - 1) - (r0 - p0 * m.nfp) + t;
-        a1p = sA + p1 * m.lt + (m.nfp - 1) - (r1 - p1 * m.nfp) + t;
+        const int r0 = mt * 8 + g, r1 = mt2 * 8 + g;
+        const int p0 = r0 >= nfp, p1 = r1 >= nfp;
+        a0p = sm + Da.oA + p0 * Da.lt + (nfp - 1) - (r0 - p0 * nfp) + t;
+        a1p = sm + Db.oA + p1 * Db.lt + (nfp - 1) - (r1 - p1 * nfp) + t;
       } else {
-        a0p = sA + (mt * 8 + g) * m.lda + t;
-        a1p = sA + ((two ? mt2 : mt) * 8 + g) * m.lda + t;
+        a0p = sm + Da.oA + (mt * 8 + g) * Da.lda + t;
+        a1p = sm + Db.oA + (mt2 * 8 + g) * Db.lda + t;
       }
+      const double* b0p = sm + m.oXV + (da * NSLOT + g) * m.ldxv + m.xoff + t;
+      const double* b1p = sm + m.oXV + (db * NSLOT + g) * m.ldxv + m.xoff + t;
       double c00 = 0, c01 = 0, c10 = 0, c11 = 0;
+      if (ND == 1 || (da == db && Da.kpad4 == Db.kpad4)) {
 #pragma unroll 5
-      for (int kk = 0; kk < m.kpad4; kk += 4) {
-        const double b = bp[kk];
-        dmma(c00, c01, a0p[kk], b);
-        dmma(c10, c11, a1p[kk], b);
+        for (int kk = 0; kk < Da.kpad4; kk += 4) {
+          const double b = b0p[kk];
+          dmma(c00, c01, a0p[kk], b);
+          dmma(c10, c11, a1p[kk], b);
+        }
+      } else {
+#pragma unroll 5
+        for (int kk = 0; kk < Da.kpad4; kk += 4) dmma(c00, c01, a0p[kk], b0p[kk]);
+#pragma unroll 5
+        for (int kk = 0; kk < Db.kpad4; kk += 4) dmma(c10, c11, a1p[kk], b1p[kk]);
       }
-      zg[(2 * t) * m.ldzg + mt * 8 + g] = c00;
-      zg[(2 * t + 1) * m.ldzg + mt * 8 + g] = c01;
+      double* z0 = sm + m.oZG + da * NSLOT * m.ldzg;
+      z0[(2 * t) * m.ldzg + mt * 8 + g] = c00;
+      z0[(2 * t + 1) * m.ldzg + mt * 8 + g] = c01;
       if (two) {
-        zg[(2 * t) * m.ldzg + mt2 * 8 + g] = c10;
-        zg[(2 * t + 1) * m.ldzg + mt2 * 8 + g] = c11;
+        double* z1 = sm + m.oZG + db * NSLOT * m.ldzg;
+        z1[(2 * t) * m.ldzg + mt2 * 8 + g] = c10;
+        z1[(2 * t + 1) * m.ldzg + mt2 * 8 + g] = c11;
       }
     }
   }
   cta_sync();
 
   // ---------------------------------------------------------------- phase 3: error model, residual weights (per slot)
-  double* sV = sX;
   if (active) {
+    const double* sZ = rowZ(0);
+    double* sV = rowX(0);
     const double rinf_raw = sTh[0], ind_raw = sTh[1], sr_raw = sTh[2], ap_raw = sTh[3], are_raw = sTh[4],
                  aim_raw = sTh[5];
     const double Rinf = 100.0 * rinf_raw, induc = ind_raw * m.induc_scale;
@@ -375,7 +462,17 @@ __device__ inline double engine_eval(const BdrtModel& m, double* sm, bool active
     double Sv = 0, Swv = 0, Sg = 0, Sgz = 0, SGre = 0, SGim = 0;
     for (int n = lane; n < Nf; n += 32) {
       const double om = sOm[n];
-      const double zre = sZ[n] + Rinf, zim = sZ[m.nfp + n] + induc * om;
+      double zre = sZ[n] + Rinf, zim = sZ[nfp + n] + induc * om;
+      double Yr = 0, Yi = 0, iM = 0;
+      if (ND > 1) {
+        // Z_p = 1 / (Y' + i Y'')  (Series-Parallel :63-66)
+        const double* sY = rowZ(ND - 1);
+        Yr = sY[n];
+        Yi = sY[nfp + n];
+        iM = 1.0 / (Yr * Yr + Yi * Yi);
+        zre += Yr * iM;
+        zim -= Yi * iM;
+      }
       double common = are2 * zre * zre + aim2 * zim * zim;
       double so_raw = 0, so_scale = 0, so = 0;
       if (outl) {
@@ -396,7 +493,13 @@ __device__ inline double engine_eval(const BdrtModel& m, double* sm, bool active
       const double v_re = r_re * i_re + 2.0 * zre * (ap2 * g_re + are2 * G);
       const double v_im = r_im * i_im + 2.0 * zim * (ap2 * g_im + aim2 * G);
       sV[n] = v_re;
-      sV[m.nfp + n] = v_im;
+      sV[nfp + n] = v_im;
+      if (ND > 1) {
+        double* sGY = rowX(ND - 1);
+        const double c1 = (Yi * Yi - Yr * Yr) * iM * iM, c2 = 2.0 * Yr * Yi * iM * iM;
+        sGY[n] = v_re * c1 + v_im * c2;
+        sGY[nfp + n] = -v_re * c2 + v_im * c1;
+      }
       Sv += v_re;
       Swv = fma(om, v_im, Swv);
       Sg += G;
@@ -409,9 +512,13 @@ __device__ inline double engine_eval(const BdrtModel& m, double* sm, bool active
         grad[m.off_so + Nf + n] = dso - (m.so_alpha + 1.0) + m.so_beta / so_scale + jac;
       }
     }
-    for (int n = Nf + lane; n < m.nfp; n += 32) {  // padding rows of both parts
-      sV[n] = 0.0;
-      sV[m.nfp + n] = 0.0;
+#pragma unroll
+    for (int dd = 0; dd < ND; ++dd) {
+      double* sVd = rowX(dd);
+      for (int n = Nf + lane; n < nfp; n += 32) {  // padding rows of both parts
+        sVd[n] = 0.0;
+        sVd[nfp + n] = 0.0;
+      }
     }
     Sv = warp_sum(Sv);
     Swv = warp_sum(Swv);
@@ -422,44 +529,68 @@ __device__ inline double engine_eval(const BdrtModel& m, double* sm, bool active
     if (lane == 0) {
       grad[0] = (100.0 * Sv - rinf_raw) * rinf_raw + jac;
       grad[1] = (m.induc_scale * Swv - ind_raw) * ind_raw + jac;
-      grad[2 + K] = (0.1 * sr * Sg - sr_raw) * sr_raw + jac;
-      grad[3 + K] = (0.1 * ap * Sgz - ap_raw) * ap_raw + jac;
-      grad[4 + K] = (0.1 * are * SGre - are_raw) * are_raw + jac;
-      grad[5 + K] = (0.1 * aim * SGim - aim_raw) * aim_raw + jac;
+      grad[m.off_err] = (0.1 * sr * Sg - sr_raw) * sr_raw + jac;
+      grad[m.off_err + 1] = (0.1 * ap * Sgz - ap_raw) * ap_raw + jac;
+      grad[m.off_err + 2] = (0.1 * are * SGre - are_raw) * are_raw + jac;
+      grad[m.off_err + 3] = (0.1 * aim * SGim - aim_raw) * aim_raw + jac;
     }
   } else {
-    for (int n = lane; n < m.n2p; n += 32) sV[n] = 0.0;
+#pragma unroll
+    for (int dd = 0; dd < ND; ++dd) {
+      double* sVd = rowX(dd);
+      for (int n = lane; n < m.n2p; n += 32) sVd[n] = 0.0;
+    }
   }
   cta_sync();
 
-  // ---------------------------------------------------------------- phase 4: GX = A^T V on the FP64 tensor cores
+  // ---------------------------------------------------------------- phase 4: G_d = A_d^T V_d on the FP64 tensor cores
   {
-    const double* bp = sm + m.oXV + g * m.ldxv + m.xoff + t;
-    double* zg = sm + m.oZG;
-    const int nmt = m.kpad8 >> 3;
-    for (int mt = warp; mt < nmt; mt += 2 * NWARP) {
-      const int mt2 = mt + NWARP;
-      const bool two = mt2 < nmt;
-      const int col0 = mt * 8 + g, col1 = (two ? mt2 : mt) * 8 + g;
+    int nmt_d[MAXD], nmt_tot = 0;
+#pragma unroll
+    for (int dd = 0; dd < ND; ++dd) {
+      nmt_d[dd] = m.d[dd].kpad8 >> 3;
+      nmt_tot += nmt_d[dd];
+    }
+    for (int ti = warp; ti < nmt_tot; ti += 2 * NWARP) {
+      const int ti2 = ti + NWARP;
+      const bool two = ti2 < nmt_tot;
+      const int tj = two ? ti2 : ti;
+      const int da = (ND > 1 && ti >= nmt_d[0]) ? 1 : 0, db = (ND > 1 && tj >= nmt_d[0]) ? 1 : 0;
+      const int mt = ti - (da ? nmt_d[0] : 0), mt2 = tj - (db ? nmt_d[0] : 0);
+      const BdrtDist &Da = m.d[da], &Db = m.d[db];
+      const int col0 = mt * 8 + g, col1 = mt2 * 8 + g;
+      const double* b0p = sm + m.oXV + (da * NSLOT + g) * m.ldxv + m.xoff + t;
+      const double* b1p = sm + m.oXV + (db * NSLOT + g) * m.ldxv + m.xoff + t;
       double c00 = 0, c01 = 0, c10 = 0, c11 = 0;
-      const int step = TOEP ? -4 : 4 * m.lda;
+      const int step0 = TOEP ? -4 : 4 * Da.lda, step1 = TOEP ? -4 : 4 * Db.lda;
 #pragma unroll
       for (int p = 0; p < 2; ++p) {  // A^T[col][row] = A_p[row][col], rows of part p
-        const double* ab = TOEP ? sA + p * m.lt + (m.nfp - 1) - t : sA + (p * m.nfp + t) * m.lda;
-        const double *a0p = ab + col0, *a1p = ab + col1;
-        const double* bq = bp + p * m.nfp;
+        const double* a0p = (TOEP ? sm + Da.oA + p * Da.lt + (nfp - 1) - t : sm + Da.oA + (p * nfp + t) * Da.lda) + col0;
+        const double* a1p = (TOEP ? sm + Db.oA + p * Db.lt + (nfp - 1) - t : sm + Db.oA + (p * nfp + t) * Db.lda) + col1;
+        const double* bq0 = b0p + p * nfp;
+        const double* bq1 = b1p + p * nfp;
+        if (ND == 1) {
 #pragma unroll 3
-        for (int i0 = 0, ao = 0; i0 < m.nfp; i0 += 4, ao += step) {
-          const double b = bq[i0];
-          dmma(c00, c01, a0p[ao], b);
-          dmma(c10, c11, a1p[ao], b);
+          for (int i0 = 0, ao = 0; i0 < nfp; i0 += 4, ao += step0) {
+            const double b = bq0[i0];
+            dmma(c00, c01, a0p[ao], b);
+            dmma(c10, c11, a1p[ao], b);
+          }
+        } else {
+#pragma unroll 3
+          for (int i0 = 0, ao0 = 0, ao1 = 0; i0 < nfp; i0 += 4, ao0 += step0, ao1 += step1) {
+            dmma(c00, c01, a0p[ao0], bq0[i0]);
+            dmma(c10, c11, a1p[ao1], bq1[i0]);
+          }
         }
       }
-      zg[(2 * t) * m.ldzg + mt * 8 + g] = c00;
-      zg[(2 * t + 1) * m.ldzg + mt * 8 + g] = c01;
+      double* z0 = sm + m.oZG + da * NSLOT * m.ldzg;
+      z0[(2 * t) * m.ldzg + mt * 8 + g] = c00;
+      z0[(2 * t + 1) * m.ldzg + mt * 8 + g] = c01;
       if (two) {
-        zg[(2 * t) * m.ldzg + mt2 * 8 + g] = c10;
-        zg[(2 * t + 1) * m.ldzg + mt2 * 8 + g] = c11;
+        double* z1 = sm + m.oZG + db * NSLOT * m.ldzg;
+        z1[(2 * t) * m.ldzg + mt2 * 8 + g] = c10;
+        z1[(2 * t + 1) * m.ldzg + mt2 * 8 + g] = c11;
       }
     }
   }
@@ -467,10 +598,16 @@ __device__ inline double engine_eval(const BdrtModel& m, double* sm, bool active
 
   // ---------------------------------------------------------------- phase 5: assemble d lp / d u_x (per slot)
   if (active) {
-    for (int k = lane; k < K; k += 32) {
-      double gx = sZ[k] + grad[2 + k];
-      if (pos) gx = gx * exp(u[2 + k]) + jac;
-      grad[2 + k] = gx;
+    const double gsum = (ND > 1) ? xsum * m.x_sum_invscale * m.x_sum_invscale : 0.0;
+#pragma unroll
+    for (int dd = 0; dd < ND; ++dd) {
+      const BdrtDist& Dd = m.d[dd];
+      const double* sG = rowZ(dd);
+      for (int k = lane; k < Dd.K; k += 32) {
+        double gx = sG[k] + grad[Dd.off_x + k] - gsum;
+        if (Dd.pos) gx = gx * exp(u[Dd.off_x + k]) + jac;
+        grad[Dd.off_x + k] = gx;
+      }
     }
     lp = warp_sum(lp);
     __syncwarp();
@@ -484,7 +621,7 @@ int bdrt_model_prepare(bdrt_ctx* ctx, const bdrt_series_data* data, BdrtModel* m
                        void** extra_ws);
 
 // Shared-memory plan of a persistent solver kernel: the engine region plus as many of the solver's per-slot work
-// vectors (Dpad doubles each, NSLOT slots) as fit.  With Toeplitz-resident A two CTAs share an SM.
+// vectors (Dpad doubles each, NSLOT slots) as fit.  With Toeplitz-resident operands two CTAs share an SM.
 struct BdrtPlan {
   int ctas_per_sm, nvec;
   size_t smem;
@@ -509,16 +646,18 @@ static inline BdrtPlan bdrt_plan(const bdrt_ctx* ctx, const BdrtModel& m, int Dp
   return pl;
 }
 
-// launch KERNEL<1> (Toeplitz-resident A) or KERNEL<0> (dense-resident A)
-#define BDRT_LAUNCH(ctx, m, KERNEL, grid, smem, ...)                                                         \
-  do {                                                                                                       \
-    if ((m).toepA) {                                                                                         \
-      BDRT_CUDA(ctx, cudaFuncSetAttribute(KERNEL<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(smem))); \
-      KERNEL<1><<<grid, NTHREADS, smem, (ctx)->stream>>>(__VA_ARGS__);                                       \
-    } else {                                                                                                 \
-      BDRT_CUDA(ctx, cudaFuncSetAttribute(KERNEL<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(smem))); \
-      KERNEL<0><<<grid, NTHREADS, smem, (ctx)->stream>>>(__VA_ARGS__);                                       \
-    }                                                                                                        \
-    (ctx)->launches++;                                                                                       \
-    BDRT_CUDA(ctx, cudaGetLastError());                                                                      \
+// launch KERNEL<TOEP, ND>: Toeplitz- or dense-resident operands, one (Series) or two (Series-Parallel) distributions
+#define BDRT_LAUNCH_ONE(ctx, KERNEL, T, N, grid, smem, ...)                                                       \
+  do {                                                                                                            \
+    BDRT_CUDA(ctx, cudaFuncSetAttribute(KERNEL<T, N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(smem))); \
+    KERNEL<T, N><<<grid, NTHREADS, smem, (ctx)->stream>>>(__VA_ARGS__);                                           \
+  } while (0)
+#define BDRT_LAUNCH(ctx, m, KERNEL, grid, smem, ...)                                  \
+  do {                                                                                \
+    if ((m).toepA && (m).ND == 1) BDRT_LAUNCH_ONE(ctx, KERNEL, 1, 1, grid, smem, __VA_ARGS__);      \
+    else if ((m).toepA) BDRT_LAUNCH_ONE(ctx, KERNEL, 1, 2, grid, smem, __VA_ARGS__);  \
+    else if ((m).ND == 1) BDRT_LAUNCH_ONE(ctx, KERNEL, 0, 1, grid, smem, __VA_ARGS__); \
+    else BDRT_LAUNCH_ONE(ctx, KERNEL, 0, 2, grid, smem, __VA_ARGS__);                 \
+    (ctx)->launches++;                                                                \
+    BDRT_CUDA(ctx, cudaGetLastError());                                               \
   } while (0)

@@ -136,7 +136,7 @@ __device__ __forceinline__ void two_loop(const double* S, const double* Y, const
 
 }  // namespace
 
-template <int TOEP>
+template <int TOEP, int ND>
 __global__ void __launch_bounds__(NTHREADS, TOEP ? 2 : 1)
 lbfgs_kernel(BdrtModel m, bdrt_lbfgs_opts o, double* __restrict__ U, double* lp_out, int* iters_out, int* neval_out,
              int* status_out, int* queue, double* hist, double* gvec, int nvec_smem, int Dpad) {
@@ -167,7 +167,7 @@ lbfgs_kernel(BdrtModel m, bdrt_lbfgs_opts o, double* __restrict__ U, double* lp_
 
   // f(xn) -> f, gn = grad f ; returns false when not finite
   auto feval = [&](double& f) -> bool {
-    const double lp = engine_eval<TOEP>(m, sm, true, xn, gn, Zs, 0);
+    const double lp = engine_eval<TOEP, ND>(m, sm, true, xn, gn, Zs, 0);
     ++neval;
     int fin = isfinite(lp);
     for (int i = lane; i < D; i += 32) {
@@ -374,7 +374,7 @@ lbfgs_kernel(BdrtModel m, bdrt_lbfgs_opts o, double* __restrict__ U, double* lp_
   // drain: keep serving the cooperative matrix products until every slot of the CTA is out of work
   if (lane == 0) atomicSub((int*)n_active, 1);
   while (true) {
-    engine_eval<TOEP>(m, sm, false, nullptr, nullptr, nullptr, 0, n_active, &snap);
+    engine_eval<TOEP, ND>(m, sm, false, nullptr, nullptr, nullptr, 0, n_active, &snap);
     if (snap == 0) break;
   }
 }

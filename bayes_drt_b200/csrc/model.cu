@@ -37,10 +37,12 @@ extern "C" long long bdrt_launch_count(const bdrt_ctx* ctx) { return ctx ? ctx->
 
 extern "C" int bdrt_num_params(const bdrt_series_data* d) {
   if (!d) return BDRT_E_NULL;
+  if ((d->model & 15) == BDRT_MODEL_SERIES_PARALLEL) return 2 * (d->K + d->Kp) + 12;
   return 2 * d->K + 9 + ((d->model & BDRT_MODEL_OUTLIERS) ? 2 * d->Nf : 0);
 }
 extern "C" int bdrt_num_outputs(const bdrt_series_data* d) {
   if (!d) return BDRT_E_NULL;
+  if ((d->model & 15) == BDRT_MODEL_SERIES_PARALLEL) return d->K + d->Kp + 6 + 2 * d->Nf;
   return d->K + 6 + 2 * d->Nf + ((d->model & BDRT_MODEL_OUTLIERS) ? d->Nf : 0);
 }
 
@@ -108,12 +110,17 @@ __global__ void toep_check_kernel(const double* A, int Nf, int K, int* info) {
     s_max = v;
   }
   __syncthreads();
-  const double tol = 1e-14 * s_max;
+  // entries of a diagonal must agree to 1e-12 relative (the table then reproduces every entry to that accuracy, far
+  // inside the 1e-10 parity tolerance of the matrices themselves); entries below 1e-16 of the largest are noise
+  const double floor_ = 1e-16 * s_max;
   int ok = 1;
   for (int i = threadIdx.x; i < 2 * Nf * K; i += blockDim.x) {
     const int r = i / K, c = i - r * K;
     const int rl = r >= Nf ? r - Nf : r;
-    if (rl + 1 < Nf && c + 1 < K && !(fabs(A[i] - A[i + K + 1]) <= tol)) ok = 0;
+    if (rl + 1 < Nf && c + 1 < K) {
+      const double a = A[i], b = A[i + K + 1];
+      if (!(fabs(a - b) <= 1e-12 * fmax(fabs(a), fabs(b)) + floor_)) ok = 0;
+    }
   }
   if (!ok) atomicAnd(&info[2], 0);
 }
@@ -123,19 +130,41 @@ int bdrt_model_prepare(bdrt_ctx* ctx, const bdrt_series_data* d, BdrtModel* m, s
   if (!d) BDRT_FAIL(ctx, BDRT_E_NULL, "null data");
   if (!d->A || !d->Z || !d->freq || !d->L) BDRT_FAIL(ctx, BDRT_E_NULL, "bdrt_series_data: null matrix pointer");
   const int base = d->model & 15;
-  if (base != BDRT_MODEL_SERIES)
-    BDRT_FAIL(ctx, BDRT_E_UNSUPPORTED, "model id %d: only the Series family is implemented in this build", d->model);
+  if (base != BDRT_MODEL_SERIES && base != BDRT_MODEL_SERIES_PARALLEL)
+    BDRT_FAIL(ctx, BDRT_E_UNSUPPORTED, "model id %d: only the Series and Series-Parallel families are implemented", d->model);
   if (d->model & ~(15 | BDRT_MODEL_POS | BDRT_MODEL_OUTLIERS)) BDRT_FAIL(ctx, BDRT_E_MODEL, "unknown model flags");
+  const int nd = base == BDRT_MODEL_SERIES_PARALLEL ? 2 : 1;
+  if (nd == 2 && (d->model & BDRT_MODEL_OUTLIERS))
+    BDRT_FAIL(ctx, BDRT_E_UNSUPPORTED,
+              "Series-Parallel*_outliers is dimensionally inconsistent as shipped by the reference and is not implemented");
   if (d->Nf < 2 || d->K < 3 || d->B < 0 || d->Nf > 4096 || d->K > 4096) BDRT_FAIL(ctx, BDRT_E_SIZE, "bad Nf/K/B");
+  if (nd == 2) {
+    if (!d->Ap || !d->Lp) BDRT_FAIL(ctx, BDRT_E_NULL, "bdrt_series_data: null Ap / Lp for a Series-Parallel model");
+    if (d->Kp < 3 || d->Kp > 4096) BDRT_FAIL(ctx, BDRT_E_SIZE, "bad Kp");
+    if (!(d->x_sum_invscale >= 0) || !(d->xp_scale > 0)) BDRT_FAIL(ctx, BDRT_E_SIZE, "bad x_sum_invscale / xp_scale");
+  }
   if (!(d->sigma_min >= 0) || !(d->ups_alpha > 0) || !(d->ups_beta > 0) || !(d->induc_scale > 0))
     BDRT_FAIL(ctx, BDRT_E_SIZE, "model constants must be positive");
   memset(m, 0, sizeof(*m));
   m->flags = ((d->model & BDRT_MODEL_POS) ? F_POS : 0) | ((d->model & BDRT_MODEL_OUTLIERS) ? F_OUT : 0);
+  m->ND = nd;
   m->Nf = d->Nf;
-  m->K = d->K;
   m->B = d->B;
-  m->A = d->A;
-  m->A_stride = d->per_spectrum_grid ? (long long)2 * d->Nf * d->K : 0;
+  const int Ks[2] = {d->K, d->Kp};
+  const double* As[2] = {d->A, d->Ap};
+  const double* Ls[2] = {d->L, d->Lp};
+  for (int i = 0; i < nd; ++i) {
+    m->d[i].K = Ks[i];
+    m->d[i].A = As[i];
+    m->d[i].A_stride = d->per_spectrum_grid ? (long long)2 * d->Nf * Ks[i] : 0;
+    m->d[i].ascale = 1.0;
+  }
+  m->d[0].pos = (d->model & BDRT_MODEL_POS) ? 1 : 0;
+  if (nd == 2) {
+    m->d[1].pos = 1;                 // vector<lower=0>[Kp] xp_raw
+    m->d[1].ascale = d->xp_scale;    // xp = xp_raw * xp_scale
+    m->x_sum_invscale = d->x_sum_invscale;
+  }
   m->freq = d->freq;
   m->f_stride = d->per_spectrum_grid ? d->Nf : 0;
   m->Z = d->Z;
@@ -146,41 +175,51 @@ int bdrt_model_prepare(bdrt_ctx* ctx, const bdrt_series_data* d, BdrtModel* m, s
   m->so_lambda = d->sigma_out_lambda;
   m->so_alpha = d->sigma_out_alpha;
   m->so_beta = d->sigma_out_beta;
-  // workspace: [info (16 B) | Lb | extra]
-  const size_t lb_bytes = (size_t)3 * d->K * LBW * sizeof(double);
-  const size_t head = 256 + ((lb_bytes + 255) & ~(size_t)255);
+  // workspace: [info (256 B) | Lb of every distribution | extra]
+  size_t lb_off[2], head = 256;
+  for (int i = 0; i < nd; ++i) {
+    lb_off[i] = head;
+    head += ((size_t)3 * Ks[i] * LBW * sizeof(double) + 255) & ~(size_t)255;
+  }
   int rc = bdrt_ws_reserve(ctx, head + extra_ws_bytes);
   if (rc) return rc;
   int* info = (int*)ctx->ws;
-  double* Lb = (double*)((char*)ctx->ws + 256);
   // BDRT_FORCE_DENSE=1 keeps the dense-resident A path even for Toeplitz grids (used by the tests to cover both)
   const char* fd = getenv("BDRT_FORCE_DENSE");
   const int try_toep = !d->per_spectrum_grid && !(fd && fd[0] == '1');
-  const int init[3] = {0, 1, try_toep};
+  const int init[8] = {0, 1, try_toep, 0, 0, 1, 0, 0};  // per distribution i: info[4i] = bw, info[4i+1] = L Toeplitz
   BDRT_CUDA(ctx, cudaMemcpyAsync(info, init, sizeof(init), cudaMemcpyHostToDevice, ctx->stream));
-  band_prep_kernel<<<3, 256, 0, ctx->stream>>>(d->L, d->K, Lb, info);
-  ctx->launches++;
-  if (try_toep) {
-    toep_check_kernel<<<1, 512, 0, ctx->stream>>>(d->A, d->Nf, d->K, info);
+  for (int i = 0; i < nd; ++i) {
+    double* Lb = (double*)((char*)ctx->ws + lb_off[i]);
+    band_prep_kernel<<<3, 256, 0, ctx->stream>>>(Ls[i], Ks[i], Lb, info + 4 * i);
     ctx->launches++;
+    m->d[i].Lb = Lb;
+    if (try_toep) {
+      toep_check_kernel<<<1, 512, 0, ctx->stream>>>(As[i], d->Nf, Ks[i], info);
+      ctx->launches++;
+    }
   }
   BDRT_CUDA(ctx, cudaGetLastError());
-  int hinfo[3];
+  int hinfo[8];
   BDRT_CUDA(ctx, cudaMemcpyAsync(hinfo, info, sizeof(hinfo), cudaMemcpyDeviceToHost, ctx->stream));
   BDRT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-  if (hinfo[0] > MAXBW)
-    BDRT_FAIL(ctx, BDRT_E_UNSUPPORTED,
-              "penalty matrices L0/L1/L2 are not banded within %d off-diagonals (found %d): epsilon is too small "
-              "relative to the basis spacing for this build",
-              MAXBW, hinfo[0]);
-  m->bw = hinfo[0];
-  m->toeplitz = hinfo[1] && (d->K >= 2 * hinfo[0] + 1);
+  int bw = 0;
+  for (int i = 0; i < nd; ++i) {
+    if (hinfo[4 * i] > MAXBW)
+      BDRT_FAIL(ctx, BDRT_E_UNSUPPORTED,
+                "penalty matrices L0/L1/L2 are not banded within %d off-diagonals (found %d): epsilon is too small "
+                "relative to the basis spacing for this build",
+                MAXBW, hinfo[4 * i]);
+    if (hinfo[4 * i] > bw) bw = hinfo[4 * i];
+  }
+  m->bw = bw;
+  for (int i = 0; i < nd; ++i) m->d[i].toepL = hinfo[4 * i + 1] && (Ks[i] >= 2 * bw + 1);
   m->toepA = hinfo[2];
-  m->Lb = Lb;
   const int eng = bdrt_model_layout(m);
   if ((size_t)eng * 8 > (size_t)ctx->smem_optin)
-    BDRT_FAIL(ctx, BDRT_E_SMEM, "problem needs %zu B of shared memory per CTA, device offers %d", (size_t)eng * 8,
-              ctx->smem_optin);
+    BDRT_FAIL(ctx, BDRT_E_SMEM, "problem needs %zu B of shared memory per CTA, device offers %d%s", (size_t)eng * 8,
+              ctx->smem_optin,
+              m->toepA ? "" : " (dense-resident kernel matrices; log-uniform grids with equal spacing need far less)");
   if (extra_ws) *extra_ws = (char*)ctx->ws + head;
   return BDRT_OK;
 }
@@ -188,7 +227,7 @@ int bdrt_model_prepare(bdrt_ctx* ctx, const bdrt_series_data* d, BdrtModel* m, s
 // ---------------------------------------------------------------------------------------------------------------------
 // log_prob + gradient test hook
 // ---------------------------------------------------------------------------------------------------------------------
-template <int TOEP>
+template <int TOEP, int ND>
 __global__ void __launch_bounds__(NTHREADS, TOEP ? 2 : 1)
 logpost_kernel(BdrtModel m, const double* u, const int* spec, int n_cols, int jacobian, double* lp, double* grad,
                int cta_per_spec) {
@@ -201,7 +240,7 @@ logpost_kernel(BdrtModel m, const double* u, const int* spec, int n_cols, int ja
       const int c = gidx * NSLOT + warp;
       const bool active = c < n_cols;
       const int b = active ? (spec ? spec[c] : c % m.B) : 0;
-      const double v = engine_eval<TOEP>(m, sm, active, u + (long long)c * m.D, grad + (long long)c * m.D,
+      const double v = engine_eval<TOEP, ND>(m, sm, active, u + (long long)c * m.D, grad + (long long)c * m.D,
                                    m.Z + (long long)b * m.N2, jacobian);
       if (active && lane == 0) lp[c] = v;
     }
@@ -226,7 +265,7 @@ logpost_kernel(BdrtModel m, const double* u, const int* spec, int n_cols, int ja
         c = nf ? found[nf - 1] : c;
         const bool active = warp < nf;
         const int col = active ? found[warp] : 0;
-        const double v = engine_eval<TOEP>(m, sm, active, u + (long long)col * m.D, grad + (long long)col * m.D,
+        const double v = engine_eval<TOEP, ND>(m, sm, active, u + (long long)col * m.D, grad + (long long)col * m.D,
                                      m.Z + (long long)b * m.N2, jacobian);
         if (active && lane == 0) lp[col] = v;
       }
@@ -266,43 +305,58 @@ __global__ void constrain_kernel(BdrtModel m, const double* u, const int* spec, 
   const int lane = threadIdx.x & 31;
   const long long c = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (c >= n) return;
-  const int K = m.K, Nf = m.Nf;
-  const bool pos = m.flags & F_POS, outl = m.flags & F_OUT;
+  const int Nf = m.Nf;
+  const bool outl = m.flags & F_OUT;
   const double* uc = u + c * m.D;
   double* o = out + c * P;
   const int b = spec ? spec[c] : (int)(c % m.B);
-  const double* A = m.A + (long long)b * m.A_stride;
   const double* f = m.freq + (long long)b * m.f_stride;
-  for (int k = lane; k < K; k += 32) o[k] = pos ? exp(uc[2 + k]) : uc[2 + k];
+  int KT = 0;  // total number of coefficients
+  for (int dd = 0; dd < m.ND; ++dd) {
+    const BdrtDist& D = m.d[dd];
+    for (int k = lane; k < D.K; k += 32) o[KT + k] = (D.pos ? exp(uc[D.off_x + k]) : uc[D.off_x + k]) * D.ascale;
+    KT += D.K;
+  }
   const double Rinf = 100.0 * exp(uc[0]), induc = exp(uc[1]) * m.induc_scale;
-  const double sr = 0.05 * exp(uc[2 + K]), ap = 0.05 * exp(uc[3 + K]), are = 0.05 * exp(uc[4 + K]),
-               aim = 0.05 * exp(uc[5 + K]);
+  const double sr = 0.05 * exp(uc[m.off_err]), ap = 0.05 * exp(uc[m.off_err + 1]), are = 0.05 * exp(uc[m.off_err + 2]),
+               aim = 0.05 * exp(uc[m.off_err + 3]);
   if (lane == 0) {
-    o[K] = Rinf;
-    o[K + 1] = induc;
-    o[K + 2] = sr;
-    o[K + 3] = ap;
-    o[K + 4] = are;
-    o[K + 5] = aim;
+    o[KT] = Rinf;
+    o[KT + 1] = induc;
+    o[KT + 2] = sr;
+    o[KT + 3] = ap;
+    o[KT + 4] = are;
+    o[KT + 5] = aim;
   }
   __syncwarp();
   for (int nn = lane; nn < Nf; nn += 32) {
-    double zre = 0, zim = 0;
-    for (int k = 0; k < K; ++k) {
-      const double xk = pos ? exp(uc[2 + k]) : uc[2 + k];
-      zre = fma(A[(long long)nn * K + k], xk, zre);
-      zim = fma(A[(long long)(Nf + nn) * K + k], xk, zim);
+    double zz[MAXD][2];
+    for (int dd = 0; dd < m.ND; ++dd) {
+      const BdrtDist& D = m.d[dd];
+      const double* A = D.A + (long long)b * D.A_stride;
+      double zre = 0, zim = 0;
+      for (int k = 0; k < D.K; ++k) {
+        const double xk = (D.pos ? exp(uc[D.off_x + k]) : uc[D.off_x + k]) * D.ascale;
+        zre = fma(A[(long long)nn * D.K + k], xk, zre);
+        zim = fma(A[(long long)(Nf + nn) * D.K + k], xk, zim);
+      }
+      zz[dd][0] = zre;
+      zz[dd][1] = zim;
     }
-    zre += Rinf;
-    zim += induc * 2.0 * M_PI * f[nn];
+    double zre = zz[0][0] + Rinf, zim = zz[0][1] + induc * 2.0 * M_PI * f[nn];
+    if (m.ND > 1) {  // Z_p = 1 / Y  (Series-Parallel_modelcode.txt:63-66)
+      const double Yr = zz[1][0], Yi = zz[1][1], iM = 1.0 / (Yr * Yr + Yi * Yi);
+      zre += Yr * iM;
+      zim -= Yi * iM;
+    }
     double common = (are * zre) * (are * zre) + (aim * zim) * (aim * zim);
     if (outl) {
       const double so = 0.05 * exp(uc[m.off_so + nn]) * exp(uc[m.off_so + Nf + nn]);
-      o[K + 6 + 2 * Nf + nn] = so;
+      o[KT + 6 + 2 * Nf + nn] = so;
       common += so * so;
     }
-    o[K + 6 + nn] = sqrt(m.sigma_min2 + sr * sr + (ap * zre) * (ap * zre) + common);
-    o[K + 6 + Nf + nn] = sqrt(m.sigma_min2 + sr * sr + (ap * zim) * (ap * zim) + common);
+    o[KT + 6 + nn] = sqrt(m.sigma_min2 + sr * sr + (ap * zre) * (ap * zre) + common);
+    o[KT + 6 + Nf + nn] = sqrt(m.sigma_min2 + sr * sr + (ap * zim) * (ap * zim) + common);
   }
 }
 

@@ -63,7 +63,7 @@ __device__ void chol_solve_packed(double* Hp, int n, double* r, volatile int* fl
 
 }  // namespace
 
-template <int TOEP>
+template <int TOEP, int ND>
 __global__ void __launch_bounds__(NTHREADS, 1)
 newton_kernel(BdrtModel m, bdrt_newton_opts o, double* __restrict__ U, double* lp_out, double* gnorm_out, int* iters_out,
               int* neval_out, double* scratch, long long scratch_per_cta, int chol_in_smem, int Dpad) {
@@ -87,7 +87,6 @@ newton_kernel(BdrtModel m, bdrt_newton_opts o, double* __restrict__ U, double* l
   double* Hp = chol_in_smem ? sm : Hp_g;
   __shared__ double s_val[8];
   __shared__ int s_flag[4];
-  const bool pos = m.flags & F_POS;
 
   for (int b = blockIdx.x; b < m.B; b += gridDim.x) {
     engine_load(m, sm, 0);
@@ -99,7 +98,7 @@ newton_kernel(BdrtModel m, bdrt_newton_opts o, double* __restrict__ U, double* l
     bool stop = false;
     // f, g at u (slot 0 evaluates; the other slots idle through the barriers)
     {
-      const double lp = engine_eval<TOEP>(m, sm, warp == 0, u, g, Zs, 0);
+      const double lp = engine_eval<TOEP, ND>(m, sm, warp == 0, u, g, Zs, 0);
       ++neval;
       if (tid == 0) s_val[0] = -lp;
       __syncthreads();
@@ -137,7 +136,7 @@ newton_kernel(BdrtModel m, bdrt_newton_opts o, double* __restrict__ U, double* l
           __syncwarp();
           h = (u[j] + h) - u[j];
         }
-        engine_eval<TOEP>(m, sm, act, my_u, my_g, Zs, 0);
+        engine_eval<TOEP, ND>(m, sm, act, my_u, my_g, Zs, 0);
         if (act) {
           const double ih = 1.0 / h;
           for (int i = lane; i < D; i += 32) H[(long long)j * Dpad + i] = (-my_g[i] - g[i]) * ih;
@@ -175,7 +174,7 @@ newton_kernel(BdrtModel m, bdrt_newton_opts o, double* __restrict__ U, double* l
         if (notpd) { mu *= 10.0; __syncthreads(); continue; }
         // tail jump of boundary-bound lower=0 coordinates (see header)
         for (int i = tid; i < D; i += NTHREADS) {
-          const bool expc = pos || !(i >= 2 && i < 2 + m.K);
+          const bool expc = bdrt_is_exp(m, i);
           double s = step[i];
           int jump = 0;
           if (expc && !frozen[i] && s < -0.5 && u[i] + s < -6.0) { s = U_FLOOR - u[i]; jump = 1; }
@@ -194,7 +193,7 @@ newton_kernel(BdrtModel m, bdrt_newton_opts o, double* __restrict__ U, double* l
         // remember the jump flags (gtry is about to be overwritten by the gradient)
         for (int i = tid; i < D; i += NTHREADS) step[i] = gtry[i];
         __syncthreads();
-        const double lp = engine_eval<TOEP>(m, sm, warp == 0, utry, gtry, Zs, 0);
+        const double lp = engine_eval<TOEP, ND>(m, sm, warp == 0, utry, gtry, Zs, 0);
         ++neval;
         if (tid == 0) s_val[0] = -lp;
         __syncthreads();

@@ -56,7 +56,7 @@ __device__ __forceinline__ double logaddexp(double a, double b) {
 
 }  // namespace
 
-template <int TOEP>
+template <int TOEP, int ND>
 __global__ void __launch_bounds__(NTHREADS, TOEP ? 2 : 1)
 nuts_kernel(BdrtModel m, bdrt_nuts_opts o, const double* __restrict__ U0, double* draws, double* stepsize_out,
             long long* nleap_out, int* ndiv_out, int* nmax_out, double* accept_out, int* queue, double* gvec,
@@ -92,7 +92,7 @@ nuts_kernel(BdrtModel m, bdrt_nuts_opts o, const double* __restrict__ U0, double
       q[i] = fma(eps * mi[i], pi, q[i]);
     }
     __syncwarp();
-    const double lp = engine_eval<TOEP>(m, sm, true, q, g, Zs, 1);
+    const double lp = engine_eval<TOEP, ND>(m, sm, true, q, g, Zs, 1);
     ++n_grad;
     for (int i = lane; i < D; i += 32) p[i] = fma(0.5 * eps, g[i], p[i]);
     __syncwarp();
@@ -125,7 +125,7 @@ nuts_kernel(BdrtModel m, bdrt_nuts_opts o, const double* __restrict__ U0, double
     vcopy(v[V_SQ], U0 + wi * D);
     for (int i = lane; i < D; i += 32) v[V_MINV][i] = 1.0;
     __syncwarp();
-    double s_lp = engine_eval<TOEP>(m, sm, true, v[V_SQ], v[V_SG], Zs, 1);
+    double s_lp = engine_eval<TOEP, ND>(m, sm, true, v[V_SQ], v[V_SG], Zs, 1);
     ++n_grad;
     bool bad = !isfinite(s_lp);
 
@@ -360,7 +360,7 @@ nuts_kernel(BdrtModel m, bdrt_nuts_opts o, const double* __restrict__ U0, double
   int snap;
   if (lane == 0) atomicSub((int*)n_active, 1);
   while (true) {
-    engine_eval<TOEP>(m, sm, false, nullptr, nullptr, nullptr, 0, n_active, &snap);
+    engine_eval<TOEP, ND>(m, sm, false, nullptr, nullptr, nullptr, 0, n_active, &snap);
     if (snap == 0) break;
   }
 }

@@ -44,7 +44,7 @@ enum { BDRT_BC_TRANSMISSIVE = 0, BDRT_BC_BLOCKING = 1 };
  * model id = base | flags. */
 enum {
   BDRT_MODEL_SERIES = 0,          /* stan_model_files/Series_modelcode.txt */
-  BDRT_MODEL_SERIES_PARALLEL = 1, /* stan_model_files/Series-Parallel_modelcode.txt */
+  BDRT_MODEL_SERIES_PARALLEL = 1, /* stan_model_files/Series-Parallel_modelcode.txt (xp_raw is always lower=0) */
   BDRT_MODEL_POS = 16,            /* *_pos_modelcode.txt: vector<lower=0> x */
   BDRT_MODEL_OUTLIERS = 32        /* *_outliers_modelcode.txt */
 };
@@ -113,9 +113,16 @@ typedef struct {
   const double* L;    /* [3,K,K]: scaled L0, L1, L2 (shared by the batch) */
   double sigma_min, ups_alpha, ups_beta, induc_scale;
   double sigma_out_lambda, sigma_out_alpha, sigma_out_beta; /* outlier models only */
+  /* BDRT_MODEL_SERIES_PARALLEL only (Series-Parallel[_pos]_modelcode.txt; Stan data of inversion.py:1886-1959):
+   * K / A / L above describe the series distribution (Ks, As, L0s..L2s); the parallel distribution is */
+  int Kp;             /* basis functions of the parallel distribution */
+  const double* Ap;   /* [2Nf,Kp] or [B,2Nf,Kp] stacked kernel matrix of the parallel distribution */
+  const double* Lp;   /* [3,Kp,Kp] scaled L0p, L1p, L2p */
+  double x_sum_invscale, xp_scale;
 } bdrt_series_data;
 
-/* number of unconstrained parameters D of the model (2K+9, +2Nf with outliers) */
+/* number of unconstrained parameters D of the model: Series 2K+9 (+2Nf with outliers);
+ * Series-Parallel 2(Ks+Kp)+12 */
 int bdrt_num_params(const bdrt_series_data* data);
 
 /* Test hook == Stan's log_prob + grad_log_prob (what .optimizing / .sampling evaluate internally):
@@ -177,7 +184,7 @@ int bdrt_nuts(bdrt_ctx* ctx, const bdrt_series_data* data, const bdrt_nuts_opts*
 /* Unconstrained draws -> constrained / transformed parameters the reference reads back
  * (_extract_parameter, inversion.py:2494-2519): out [n, P] with P = bdrt_num_outputs():
  * [x(K) | Rinf | induc | sigma_res | alpha_prop | alpha_re | alpha_im | sigma_tot(2Nf) | sigma_out(Nf if outliers)]
- * spec as in bdrt_logpost_grad. */
+ * (Series-Parallel: x(K) is replaced by [xs(Ks) | xp(Kp)], xp = xp_raw * xp_scale);  spec as in bdrt_logpost_grad. */
 int bdrt_num_outputs(const bdrt_series_data* data);
 int bdrt_constrain(bdrt_ctx* ctx, const bdrt_series_data* data, const double* u, const int* spec, int n,
                    double* out);

@@ -1,0 +1,102 @@
+"""GPU: the two-distribution 'Series-Parallel[_pos]' model (DRT + transmissive planar DDT, the paper's shape) --
+fused log-posterior / gradient against the oracle restatement, constrain read-out, L-BFGS MAP and NUTS through the same
+engine, on both resident-operand layouts."""
+import numpy as np
+import pytest
+import torch
+
+from helpers import gpu_problem_sp, sp_dists, sp_spectrum
+from oracle import lbfgs as olb, model_sp as osp
+
+pytestmark = pytest.mark.gpu
+
+
+def _data(mode, nonneg, Nf=81, Ks=81, Kp=81, nspec=3):
+    freq = np.logspace(6, -2, Nf)
+    ser, par = sp_dists(np.logspace(6, -2, Ks), np.logspace(6, -2, Kp))
+    return [osp.prep_series_parallel(freq, sp_spectrum(freq, seed=s, td=0.1 * (s + 1)), ser, par, mode=mode,
+                                     nonneg=nonneg) for s in range(nspec)]
+
+
+@pytest.mark.parametrize('nonneg', [True, False])
+@pytest.mark.parametrize('mode', ['optimize', 'sample'])
+def test_sp_logpost_matches_oracle(nonneg, mode, resident_A):
+    Ks = 81 if resident_A == 'toeplitz' else 49  # two dense 162 x 81 matrices do not fit one SM's shared memory
+    ds = _data(mode, nonneg, Ks=Ks, Kp=Ks)
+    prob = gpu_problem_sp(ds)
+    assert prob.D == osp.n_params(ds[0]) == 2 * (Ks + Ks) + 12
+    rng = np.random.RandomState(4)
+    u = rng.uniform(-1.5, 1.5, (11, prob.D))
+    if not nonneg:
+        u[:, 2:2 + Ks] = np.abs(u[:, 2:2 + Ks]) * 0.1
+    spec = rng.randint(0, 3, 11)
+    for jac in (False, True):
+        lp, grad = prob.logpost_grad(torch.tensor(u), spec=spec, jacobian=jac)
+        lp, grad = lp.cpu().numpy(), grad.cpu().numpy()
+        for c in range(11):
+            lo, go = osp.logpost(u[c], ds[spec[c]], jacobian=jac)
+            assert abs(lp[c] - lo) <= 1e-11 * abs(lo), (c, lp[c], lo)
+            assert np.max(np.abs(grad[c] - go)) <= 1e-9 * np.max(np.abs(go)), (c, np.max(np.abs(grad[c] - go)))
+    if not nonneg:  # x_sum_raw < 0 is rejected (real<lower=0> x_sum_raw, Series-Parallel_modelcode.txt:56)
+        u[0, 2:2 + Ks] = -5.0
+        lp, _ = prob.logpost_grad(torch.tensor(u[:1]), spec=spec[:1])
+        assert lp[0].item() == -np.inf
+
+
+def test_sp_dense_too_large_fails_loudly(monkeypatch):
+    from bayes_drt_b200._lib import BdrtError
+    monkeypatch.setenv('BDRT_FORCE_DENSE', '1')
+    prob = gpu_problem_sp(_data('optimize', True, nspec=1))
+    with pytest.raises(BdrtError, match='shared memory'):
+        prob.logpost_grad(torch.zeros(1, prob.D, dtype=torch.float64))
+
+
+def test_sp_constrain_and_map(resident_A):
+    Ks = 81 if resident_A == 'toeplitz' else 49
+    ds = _data('optimize', True, Ks=Ks, Kp=Ks, nspec=2)
+    prob = gpu_problem_sp(ds)
+    rng = np.random.RandomState(1)
+    u0 = rng.uniform(-2, 2, (2, prob.D))
+
+    def func(d):
+        def f(u):
+            with np.errstate(all='ignore'):
+                lp, g = osp.logpost(u, d)
+            if not np.isfinite(lp) or not np.all(np.isfinite(g)):
+                return None
+            return -lp, -g
+        return f
+    with np.errstate(all='ignore'):
+        u1 = np.stack([olb.minimize(func(ds[b]), u0[b], max_iter=60)['x'] for b in range(2)])
+    # same algorithm from the same (sane) start: identical evaluation counts, iterates agree closely
+    r = prob.map_lbfgs(torch.tensor(u1), max_iter=20)
+    for b in range(2):
+        o = olb.minimize(func(ds[b]), u1[b], max_iter=20)
+        assert r['iters'][b].item() == o['iters'] == 20
+        assert r['n_eval'][b].item() == o['n_eval']
+        assert abs(r['lp'][b].item() + o['f']) <= 1e-9 * abs(o['f'])
+        assert np.max(np.abs(r['u'][b].cpu().numpy() - o['x'])) <= 1e-7 * np.max(np.abs(o['x']))
+    out = prob.split_outputs(prob.constrain(r['u']))
+    for b in range(2):
+        c = osp.constrain(r['u'][b].cpu().numpy(), ds[b])
+        assert np.allclose(out['xs'][b].cpu().numpy(), c['xs'], rtol=1e-13)
+        assert np.allclose(out['xp'][b].cpu().numpy(), c['xp'], rtol=1e-13)
+        assert np.allclose(out['sigma_tot'][b].cpu().numpy(), c['sigma_tot'], rtol=1e-10)
+        assert abs(out['Rinf'][b].item() - c['Rinf']) <= 1e-13 * c['Rinf']
+    # a long run improves the objective a lot and recovers the series resistance of the synthetic cell
+    r2 = prob.map_lbfgs(torch.tensor(u0), max_iter=3000)
+    assert (r2['lp'] > r['lp']).all()
+    o2 = prob.split_outputs(prob.constrain(r2['u']))
+    assert np.allclose((o2['Rinf'].cpu().numpy() * np.array([d['Z_scale'] for d in ds])), 0.5, atol=0.05)
+
+
+def test_sp_nuts_runs_and_is_deterministic():
+    ds = _data('sample', True, nspec=2)
+    prob = gpu_problem_sp(ds)
+    g = torch.Generator().manual_seed(0)
+    u0 = torch.rand(2, 2, prob.D, generator=g, dtype=torch.float64) * 4 - 2
+    kw = dict(chains=2, warmup=40, samples=10, seed=5)
+    a = prob.nuts(u0, **kw)
+    b = prob.nuts(u0, **kw)
+    assert torch.equal(a['draws'], b['draws']) and torch.isfinite(a['draws']).all()
+    assert (a['stepsize'] > 0).all() and (a['accept'] > 0.05).all()
