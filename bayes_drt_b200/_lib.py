@@ -53,7 +53,8 @@ class NewtonOpts(C.Structure):
 class NutsOpts(C.Structure):
     _fields_ = [('chains', C.c_int), ('warmup', C.c_int), ('samples', C.c_int), ('max_treedepth', C.c_int),
                 ('adapt_delta', C.c_double), ('adapt_t0', C.c_double), ('adapt_gamma', C.c_double),
-                ('adapt_kappa', C.c_double), ('seed', C.c_ulonglong), ('spectrum_offset', C.c_longlong)]
+                ('adapt_kappa', C.c_double), ('seed', C.c_ulonglong), ('spectrum_offset', C.c_longlong),
+                ('spectrum_ids', C.c_void_p)]
 
 
 class RidgeOpts(C.Structure):

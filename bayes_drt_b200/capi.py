@@ -151,7 +151,7 @@ class SeriesProblem:
         return dict(u=u, lp=lp, gnorm=gnorm, iters=iters, n_eval=nev)
 
     def nuts(self, u0, chains=2, warmup=200, samples=200, seed=1234, adapt_delta=0.9, adapt_t0=10.0,
-             max_treedepth=10, spectrum_offset=0, keep_draws=True):
+             max_treedepth=10, spectrum_offset=0, keep_draws=True, spectrum_ids=None):
         u0 = f64(u0, self.ctx.device)
         if tuple(u0.shape) != (self.B, chains, self.D):
             raise ValueError(f'u0 must be [{self.B}, {chains}, {self.D}]')
@@ -161,6 +161,12 @@ class SeriesProblem:
         o.adapt_delta, o.adapt_t0, o.seed, o.spectrum_offset = float(adapt_delta), float(adapt_t0), int(seed), \
             int(spectrum_offset)
         dev = u0.device
+        ids = None
+        if spectrum_ids is not None:
+            ids = torch.as_tensor(spectrum_ids, dtype=torch.int64, device=dev).contiguous()
+            if ids.numel() != self.B:
+                raise ValueError('spectrum_ids must have one entry per spectrum')
+            o.spectrum_ids = ids.data_ptr()
         draws = torch.empty((self.B, chains, samples, self.D), dtype=torch.float64, device=dev) if keep_draws else None
         stepsize = torch.empty((self.B, chains), dtype=torch.float64, device=dev)
         nleap = torch.empty((self.B, chains), dtype=torch.int64, device=dev)

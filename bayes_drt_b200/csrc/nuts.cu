@@ -115,7 +115,8 @@ nuts_kernel(BdrtModel m, bdrt_nuts_opts o, const double* __restrict__ U0, double
     if (wi >= n_work) break;
     const int b = (int)(wi / o.chains);
     Zs = m.Z + (long long)b * m.N2;
-    const long long wglob = (o.spectrum_offset + b) * (long long)o.chains + (wi % o.chains);
+    const long long sid = o.spectrum_ids ? o.spectrum_ids[b] : o.spectrum_offset + b;
+    const long long wglob = sid * (long long)o.chains + (wi % o.chains);
     Rng rng;
     rng.key = make_uint2((unsigned)(o.seed & 0xffffffffull), (unsigned)(o.seed >> 32) ^ (unsigned)(wglob >> 32));
     rng.w = (unsigned)wglob;
@@ -377,6 +378,7 @@ extern "C" void bdrt_nuts_default_opts(bdrt_nuts_opts* o) {
   o->adapt_kappa = 0.75;
   o->seed = 1234;  // inversion.py:1075
   o->spectrum_offset = 0;
+  o->spectrum_ids = nullptr;
 }
 
 extern "C" int bdrt_nuts(bdrt_ctx* ctx, const bdrt_series_data* data, const bdrt_nuts_opts* opts, const double* u0,

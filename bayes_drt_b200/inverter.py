@@ -26,11 +26,21 @@ _MODE = {
 }
 
 
-def _hash_uniform(seed, start, n, D, device, lo=-2.0, hi=2.0):
+# Series-Parallel constants (inversion.py:1913-1930): note the parallel L0 multiplier 1.5 * 0.36 in 'optimize'
+_MODE_SP = {
+    'sample': dict(ls=(1.0, 1.0, 0.75), lp=(1.0, 1.0, 0.75), x_sum_invscale=1.0),
+    'optimize': dict(ls=(1.5 * 0.24, 1.5 * 0.16, 1.5 * 0.08), lp=(1.5 * 0.36, 1.5 * 0.16, 1.5 * 0.08),
+                     x_sum_invscale=0.0),
+}
+
+
+def _hash_uniform(seed, start, n, D, device, lo=-2.0, hi=2.0, ids=None):
     """U(lo, hi) initial points keyed by the *global* spectrum index (splitmix64), so a spectrum gets the same init
-    whatever the sharding (Stan: init='random' draws U(-2, 2) per unconstrained coordinate [Stan-upstream])."""
-    idx = (torch.arange(start, start + n, dtype=torch.int64, device=device)[:, None] * D
-           + torch.arange(D, dtype=torch.int64, device=device)[None, :])
+    whatever the sharding (Stan: init='random' draws U(-2, 2) per unconstrained coordinate [Stan-upstream]).
+    ``ids``: explicit global row indices (overrides start .. start + n)."""
+    rows = torch.arange(start, start + n, dtype=torch.int64, device=device) if ids is None else \
+        torch.as_tensor(ids, dtype=torch.int64, device=device)
+    idx = rows[:, None] * D + torch.arange(D, dtype=torch.int64, device=device)[None, :]
     z = idx + (int(seed) * 0x9E3779B97F4A7C15 + 0x632BE59BD9B4E019) % (1 << 63)
     for sh, mul in ((30, 0xBF58476D1CE4E5B9), (27, 0x94D049BB133111EB)):
         z = (z ^ ((z >> sh) & ((1 << (64 - sh)) - 1))) * (mul - (1 << 64) if mul >= (1 << 63) else mul)
@@ -189,66 +199,165 @@ class Inverter:
             raise NotImplementedError('model_str / add_stan_data (Stan escape hatches) are not available')
         if mode not in ('optimize', 'sample'):
             raise ValueError(f"Invalid mode {mode}. Options are 'optimize', 'sample'")
-        if len(self.distributions) != 1:
-            raise NotImplementedError('multi-distribution (Series-Parallel / Series-2Parallel) models are not '
-                                      'implemented in this build')
-        name = list(self.distributions.keys())[0]
-        info = self.distributions[name]
-        if info['dist_type'] != 'series' or info['kernel'] != 'DRT':
-            raise NotImplementedError("only the single-DRT 'Series' model family is implemented in this build")
-        if outliers == 'auto' or init_from_ridge:
-            raise NotImplementedError("outliers='auto' / init_from_ridge need the ridge initialisation chain, "
-                                      "which this build does not wire up yet")
+        # model selection (Inverter._get_stan_model, inversion.py:1576-1610)
+        ser = [k for k, v in self.distributions.items() if v['dist_type'] == 'series']
+        par = [k for k, v in self.distributions.items() if v['dist_type'] == 'parallel']
+        if len(ser) == 1 and len(par) == 0:
+            model_type = 'Series'
+        elif len(ser) == 1 and len(par) == 1:
+            model_type = 'Series-Parallel'
+        else:
+            raise NotImplementedError("only the 'Series' (one series distribution) and 'Series-Parallel' (one series + "
+                                      "one parallel distribution) model families are implemented in this build")
+        if model_type == 'Series-Parallel' and outliers:
+            raise NotImplementedError("Series-Parallel*_outliers is dimensionally inconsistent as shipped by the "
+                                      "reference (N override vs matrix[N,Ks] As) and is not implemented")
+        if init_from_ridge and len(self.distributions) > 1:
+            raise ValueError('Ridge initialization can only be performed for single-distribution fits')  # :1155-1156
+        if outliers == 'auto' and model_type != 'Series':
+            raise NotImplementedError("outliers='auto' is implemented for single-distribution fits")
+        name = ser[0]
         freq, Zb = self._to_batch(frequencies, Z)
+        single = self._single
+        B = Zb.shape[0]
+        ids = torch.arange(spectrum_offset, spectrum_offset + B, dtype=torch.int64, device=self.device)
+        # ---- ridge initialisation and automatic outlier detection (inversion.py:1154-1187)
+        ridge_init, flags = None, None
+        if init_from_ridge:
+            ridge_init = self._get_init_from_ridge(freq, Zb, nonneg, inductance_scale, ridge_kw)
+        if outliers == 'auto':
+            # existing ridge fit if one was just made, else a fresh one with preset='Huang'; stringent threshold 4
+            flags = self._ridge_outlier_flags(freq, Zb, threshold=4, use_existing_fit=init_from_ridge, **ridge_kw)
+            has = flags.any(dim=1)
+            if single and bool(has[0]):
+                idx = torch.nonzero(flags[0])[:, 0].cpu().numpy()
+                warnings.warn('Identified likely outliers at indices {}, f={} Hz. An outlier-robust error model will '
+                              'be used. To disable this behavior, pass outliers=False.'.format(idx, freq.numpy()[idx]))
+            groups = [(torch.nonzero(has)[:, 0], True), (torch.nonzero(~has)[:, 0], False)]
+            groups = [(ix, fl) for ix, fl in groups if ix.numel() > 0]
+        else:
+            groups = [(None, bool(outliers))]
+        self._single = False
         self.f_train = freq.numpy()
         self.Z_train = Zb
         Zs = self._scale_Z(Zb, scale_Z)
+        self._outlier_model = torch.zeros(B, dtype=torch.bool, device=self.device)
+        results = []
+        for ix, fl in groups:
+            sel = slice(None) if ix is None else ix
+            u_init = None
+            if init is not None:
+                u_init = torch.as_tensor(init, dtype=torch.float64, device=self.device)
+                u_init = u_init.reshape(B, -1, u_init.shape[-1])[sel]
+            res = self._fit_core(freq, Zs[sel], ids[sel], model_type, name, par, mode, nonneg, fl, sigma_min,
+                                 inductance_scale, outlier_lambda, random_seed, max_iter, warmup, samples, chains,
+                                 u_init, None if ridge_init is None else {k: v[sel] for k, v in ridge_init.items()},
+                                 flags[sel] if (flags is not None and fl) else None, polish, keep_draws)
+            results.append((ix, fl, res))
+            if ix is None:
+                self._outlier_model[:] = fl
+            else:
+                self._outlier_model[ix] = fl
+        self._merge_results(results, B, model_type, name, par, mode, sigma_min, keep_draws)
+        self.stan_model_name = model_type + ('_pos' if nonneg else '') + \
+            ('_outliers' if bool(self._outlier_model.any()) else '') + '_StanModel.pkl'
+        self._single = single
+        if check_outliers and not bool(self._outlier_model.all()):
+            idx = self.check_outliers(threshold=3.5)
+            if single and len(idx) > 0 and not bool(self._outlier_model[0]):
+                warnings.warn(f'Possible outliers were identified at indices {idx}. Check the residuals and consider '
+                              f're-running with outliers=True')
+        if single:
+            self._squeeze()
+        return self
+
+    # ------------------------------------------------------------------------------------------------------------
+    def _fit_core(self, freq, Zs, ids, model_type, name, par, mode, nonneg, outliers, sigma_min, inductance_scale,
+                  outlier_lambda, random_seed, max_iter, warmup, samples, chains, init, ridge_init, flags, polish,
+                  keep_draws):
+        """One Stan program on one (sub-)batch: build the problem, initialise, run the solver, read back."""
         tau, eps, m = self._grid(freq, name)
         c = _MODE[mode]
-        L = torch.stack([c['l'][0] * m['L0'], c['l'][1] * m['L1'], c['l'][2] * m['L2']])
         Zst = torch.cat((Zs.real, Zs.imag), dim=1).contiguous()
-        prob = capi.SeriesProblem(torch.cat((m['A_re'], m['A_im'])), Zst, freq, L, nonneg=bool(nonneg),
-                                  outliers=bool(outliers), sigma_min=sigma_min, ups_alpha=c['ups_alpha'],
-                                  ups_beta=c['ups_beta'], induc_scale=float(inductance_scale),
-                                  sigma_out_lambda=10.0 if outlier_lambda is None else float(outlier_lambda),
-                                  sigma_out_alpha=c['sigma_out_alpha'], sigma_out_beta=1.0, device=self.device)
+        common = dict(nonneg=bool(nonneg), sigma_min=sigma_min, ups_alpha=c['ups_alpha'], ups_beta=c['ups_beta'],
+                      induc_scale=float(inductance_scale), device=self.device)
+        if model_type == 'Series':
+            L = torch.stack([c['l'][0] * m['L0'], c['l'][1] * m['L1'], c['l'][2] * m['L2']])
+            prob = capi.SeriesProblem(torch.cat((m['A_re'], m['A_im'])), Zst, freq, L, outliers=bool(outliers),
+                                      sigma_out_lambda=10.0 if outlier_lambda is None else float(outlier_lambda),
+                                      sigma_out_alpha=c['sigma_out_alpha'], sigma_out_beta=1.0, **common)
+        else:
+            _, _, mp = self._grid(freq, par[0])
+            csp = _MODE_SP[mode]
+            Ls = torch.stack([csp['ls'][j] * m[f'L{j}'] for j in range(3)])
+            Lp = torch.stack([csp['lp'][j] * mp[f'L{j}'] for j in range(3)])
+            prob = capi.SeriesProblem(torch.cat((m['A_re'], m['A_im'])), Zst, freq, Ls,
+                                      Ap=torch.cat((mp['A_re'], mp['A_im'])), Lp=Lp,
+                                      x_sum_invscale=csp['x_sum_invscale'],
+                                      xp_scale=float(self.distributions[par[0]].get('x_scale', 1)), **common)
         self._problem = prob
-        # the reference's model file name (Inverter._get_stan_model, inversion.py:1576-1610)
-        self.stan_model_name = 'Series' + ('_pos' if nonneg else '') + ('_outliers' if outliers else '') \
-            + '_StanModel.pkl'
-        B, D = prob.B, prob.D
-        self.distribution_fits, self.error_fit = {}, {}
+        B, D, K, Nf = prob.B, prob.D, prob.K, prob.Nf
+        nch = 1 if mode == 'optimize' else chains
+        if init is not None:
+            u0 = init.reshape(B, nch, D).clone()
+        else:
+            # Stan: init='random' -> U(-2, 2) per unconstrained coordinate; rows keyed by global (spectrum, chain) index
+            rows = (ids[:, None] * nch + torch.arange(nch, device=self.device)[None, :]).reshape(-1)
+            u0 = _hash_uniform(random_seed, 0, 0, D, self.device, ids=rows).reshape(B, nch, D)
+            if ridge_init is not None:
+                # partial init from the ridge fit (inversion.py:1649-1677); Stan draws the remaining parameters randomly
+                x = ridge_init['x']
+                if nonneg:  # exact zeros of the active-set QP cannot be log-transformed: floor them (cvxopt's interior
+                    x = torch.clamp(x, min=1e-8 * x.abs().max(dim=1, keepdim=True).values)  # iterates sit ~1e-9 above)
+                    x = torch.log(x)
+                u0[:, :, 2:2 + K] = x[:, None, :]
+                u0[:, :, 0] = torch.log(ridge_init['Rinf_raw'])[:, None]
+                u0[:, :, 1] = torch.log(ridge_init['induc_raw'])[:, None]
+                if outliers:
+                    so = torch.full((B, Nf), 0.1, dtype=torch.float64, device=self.device)
+                    if flags is not None:
+                        so[flags] = 1.0
+                    u0[:, :, 6 + K:6 + K + Nf] = torch.log(so)[:, None, :]
         if mode == 'optimize':
-            u0 = _hash_uniform(random_seed, spectrum_offset, B, D, self.device) if init is None else \
-                torch.as_tensor(init, dtype=torch.float64, device=self.device).reshape(B, D)
-            r = prob.map_lbfgs(u0, max_iter=max_iter)
+            r = prob.map_lbfgs(u0.reshape(B, D), max_iter=max_iter)
             if polish:
                 p = prob.map_newton(r['u'])
                 r.update(u=p['u'], lp=p['lp'], gnorm=p['gnorm'], newton_iters=p['iters'])
-            self._opt_result = r
-            out = prob.split_outputs(prob.constrain(r['u']))
-            point = out
-            self.fit_type = 'map'
-            self._sample_result = None
-        else:
-            u0 = _hash_uniform(random_seed, spectrum_offset * chains, B * chains, D, self.device).reshape(
-                B, chains, D) if init is None else torch.as_tensor(init, dtype=torch.float64,
-                                                                    device=self.device).reshape(B, chains, D)
-            r = prob.nuts(u0, chains=chains, warmup=warmup, samples=samples, seed=random_seed,
-                          spectrum_offset=spectrum_offset)
-            spec = torch.arange(B, dtype=torch.int32, device=self.device).repeat_interleave(chains * samples)
-            cons = prob.constrain(r['draws'].reshape(B * chains * samples, D), spec=spec).reshape(
-                B, chains * samples, prob.P)
-            draws = prob.split_outputs(cons)
-            # posterior mean over the merged chains (Inverter._extract_parameter, inversion.py:2514-2519)
-            point = {k: v.mean(dim=1) for k, v in draws.items()}
-            self._sample_result = draws if keep_draws else None
-            self._sample_stats = {k: r[k] for k in ('stepsize', 'n_leapfrog', 'n_divergent', 'n_maxdepth', 'accept')}
-            if not keep_draws:
-                r['draws'] = None
-            self.fit_type = 'bayes'
+            point = prob.split_outputs(prob.constrain(r['u']))
+            return dict(point=point, opt=r, draws=None, stats=None)
+        r = prob.nuts(u0, chains=chains, warmup=warmup, samples=samples, seed=random_seed, spectrum_ids=ids)
+        spec = torch.arange(B, dtype=torch.int32, device=self.device).repeat_interleave(chains * samples)
+        cons = prob.constrain(r['draws'].reshape(B * chains * samples, D), spec=spec).reshape(
+            B, chains * samples, prob.P)
+        draws = prob.split_outputs(cons)
+        # posterior mean over the merged chains (Inverter._extract_parameter, inversion.py:2514-2519)
+        point = {k: v.mean(dim=1) for k, v in draws.items()}
+        stats = {k: r[k] for k in ('stepsize', 'n_leapfrog', 'n_divergent', 'n_maxdepth', 'accept')}
+        return dict(point=point, opt=None, draws=draws if keep_draws else None, stats=stats)
+
+    def _merge_results(self, results, B, model_type, name, par, mode, sigma_min, keep_draws):
+        """Scatter the sub-batch results (one per Stan program) back into batch order and rescale
+        (Inverter._extract_parameter / _rescale_coef, inversion.py:2445-2450, :2494-2519)."""
+        def merge(get, fill=float('nan')):
+            parts = [(ix, get(res)) for ix, _, res in results if get(res) is not None]
+            if not parts:
+                return None
+            if len(results) == 1 and results[0][0] is None:
+                return parts[0][1]
+            ref = parts[0][1]
+            out = torch.full((B,) + tuple(ref.shape[1:]), fill, dtype=ref.dtype, device=ref.device)
+            for ix, v in parts:
+                out[ix] = v
+            return out
+        keys = list(results[0][2]['point'].keys())
+        point = {k: merge(lambda r, k=k: r['point'].get(k)) for k in set(keys) | {'sigma_out'}}
         s = self._Z_scale
-        self.distribution_fits[name] = {'coef': point['x'] * s[:, None]}
+        self.distribution_fits, self.error_fit = {}, {}
+        if model_type == 'Series':
+            self.distribution_fits[name] = {'coef': point['x'] * s[:, None]}
+        else:  # series coef * scale, parallel coef / scale
+            self.distribution_fits[name] = {'coef': point['xs'] * s[:, None]}
+            self.distribution_fits[par[0]] = {'coef': point['xp'] / s[:, None]}
         self.R_inf = point['Rinf'] * s
         self.inductance = point['induc'] * s
         self.error_fit['sigma_min'] = sigma_min * s
@@ -256,16 +365,58 @@ class Inverter:
         self.error_fit['sigma_res'] = point['sigma_res'] * s
         for k in ('alpha_prop', 'alpha_re', 'alpha_im'):
             self.error_fit[k] = point[k]
-        if outliers:
+        if point.get('sigma_out') is not None:
             self.error_fit['sigma_out'] = point['sigma_out'] * s[:, None]
-        if check_outliers and not outliers:
-            idx = self.check_outliers(threshold=3.5)
-            if self._single and len(idx) > 0:
-                warnings.warn(f'Possible outliers were identified at indices {idx}. Check the residuals and consider '
-                              f're-running with outliers=True')
-        if self._single:
-            self._squeeze()
-        return self
+        if mode == 'optimize':
+            self.fit_type = 'map'
+            self._sample_result = None
+            self._opt_result = {k: merge(lambda r, k=k: r['opt'].get(k), fill=0) for k in results[0][2]['opt']} \
+                if len(results) == 1 else {k: merge(lambda r, k=k: r['opt'].get(k), fill=0)
+                                           for k in ('lp', 'iters', 'n_eval', 'status')}
+        else:
+            self.fit_type = 'bayes'
+            self._sample_stats = {k: merge(lambda r, k=k: r['stats'][k], fill=0) for k in results[0][2]['stats']}
+            if keep_draws:
+                dk = set().union(*[set(res['draws'].keys()) for _, _, res in results])
+                self._sample_result = {k: merge(lambda r, k=k: r['draws'].get(k)) for k in dk}
+            else:
+                self._sample_result = None
+
+    def _get_init_from_ridge(self, freq, Zb, nonneg, inductance_scale, ridge_kw):
+        """inversion.py:1616-1682: under-fitted ridge solution -> Stan initial values (scaled units)."""
+        from .ridge import ridge_fit
+        kw = dict(penalty='integral', hyper_lambda=True, lambda_0=1, hl_beta=5, weights='modulus')  # :1642
+        kw.update(ridge_kw)
+        single = self._single
+        self._single = False
+        ridge_fit(self, freq, Zb, **kw)
+        self._single = single
+        name = list(self.distributions.keys())[0]
+        s = self._Z_scale
+        induc = self.inductance / s
+        induc = torch.where(induc <= 0, torch.full_like(induc, 1e-10), induc)  # :1665-1667
+        return {'x': self.distribution_fits[name]['coef'] / s[:, None], 'Rinf_raw': self.R_inf / s / 100.0,
+                'induc_raw': induc / inductance_scale}
+
+    def _ridge_outlier_flags(self, freq, Zb, threshold, use_existing_fit, **ridge_kw):
+        """check_outliers for a ridge fit (inversion.py:3351-3367): no error model yet, so residuals relative to |Z| are
+        flagged when they exceed the 75th percentile by ``threshold`` inter-quartile ranges (utils.py:143-146).
+        Returns bool [B, Nf]."""
+        from .ridge import ridge_fit
+        single = self._single
+        self._single = False
+        if not (use_existing_fit and self.fit_type == 'ridge'):
+            ridge_fit(self, freq, Zb, preset='Huang', **ridge_kw)
+        Zerr = self.predict_Z(freq.numpy()) - self.Z_train
+        self._single = single
+        Zmod = self.Z_train.abs()
+        er, ei = (Zerr.real / Zmod), (Zerr.imag / Zmod)
+
+        def thresh(y):
+            q = torch.quantile(y, torch.tensor([0.25, 0.75], dtype=torch.float64, device=y.device), dim=1)
+            return q[1] + threshold * (q[1] - q[0])
+        tr, ti = thresh(er.abs()), thresh(ei.abs())
+        return er ** 2 + ei ** 2 >= (tr ** 2 + ti ** 2)[:, None]
 
     def _squeeze(self):
         """single-spectrum call: reference shapes as numpy arrays"""
@@ -309,18 +460,30 @@ class Inverter:
         phi = torch.exp(-(info['epsilon'] * torch.log(et[:, None] / basis_tau[None, :])) ** 2)
         return self._ret(coef @ phi.T)
 
+    def _pred_matrices(self, f, name):
+        info = self.distributions[name]
+        return capi.build_A(f, torch.as_tensor(info['tau']), info['epsilon'], kernel=info['kernel'],
+                            dist_type=info['dist_type'], symmetry=info.get('symmetry') or 'planar',
+                            bc=info.get('bc') or 'transmissive', ct=info.get('ct', False), k_ct=info.get('k_ct'),
+                            device=self.device)
+
     def predict_Z(self, frequencies, times=None, distributions=None, include_offsets=True, percentile=None):
-        """inversion.py:2669 (generic branch :2942-2959) for the single series distribution."""
+        """inversion.py:2669 (generic branch :2942-2959): series distributions add A @ coef, parallel distributions add
+        1 / (A @ coef); R_inf and the inductance are added when include_offsets."""
         if times is not None:
             raise NotImplementedError('drift fits are out of scope')
-        name = list(self.distributions.keys())[0]
-        info = self.distributions[name]
+        if distributions is None:
+            names = list(self.distribution_fits.keys())
+        else:
+            names = [distributions] if isinstance(distributions, str) else list(distributions)
         f = torch.as_tensor(np.asarray(frequencies, dtype=np.float64))
-        A_re, A_im = capi.build_A(f, torch.as_tensor(info['tau']), info['epsilon'], device=self.device)
         fd = f.to(self.device)
         if percentile is not None:
             if self.fit_type != 'bayes' or self._sample_result is None:
                 raise ValueError('Percentile prediction is only available for bayes_fit results')
+            if len(self.distributions) != 1:
+                raise NotImplementedError('percentile prediction of Z is implemented for single-distribution fits')
+            A_re, A_im = self._pred_matrices(f, names[0])
             s = self._Z_scale[:, None, None]
             x = self._sample_result['x'] * s
             Zr = x @ A_re.T
@@ -331,18 +494,32 @@ class Inverter:
             Zp = torch.complex(torch.quantile(Zr, percentile / 100.0, dim=1),
                                torch.quantile(Zi, percentile / 100.0, dim=1))
             return self._ret(Zp)
-        coef = self._coef_batch(name)
-        Zr, Zi = coef @ A_re.T, coef @ A_im.T
+        Zp = None
+        for name in names:
+            A_re, A_im = self._pred_matrices(f, name)
+            coef = self._coef_batch(name)
+            z = torch.complex(coef @ A_re.T, coef @ A_im.T)
+            if self.distributions[name]['dist_type'] == 'parallel':
+                z = 1.0 / z
+            Zp = z if Zp is None else Zp + z
         if include_offsets:
             Rinf = torch.as_tensor(self.R_inf, dtype=torch.float64, device=self.device).reshape(-1, 1)
             ind = torch.as_tensor(self.inductance, dtype=torch.float64, device=self.device).reshape(-1, 1)
-            Zr = Zr + Rinf
-            Zi = Zi + 2 * np.pi * fd * ind
-        return self._ret(torch.complex(Zr, Zi))
+            Zp = Zp + torch.complex(Rinf.expand_as(Zp.real), (2 * np.pi * fd * ind).expand_as(Zp.real))
+        return self._ret(Zp)
 
     def predict_Rp(self, distributions=None, percentile=None, time=None):
         """inversion.py:3033: area under the DRT, sum(coef) sqrt(pi) / epsilon."""
-        name = list(self.distributions.keys())[0]
+        names = list(self.distribution_fits.keys()) if distributions is None else (
+            [distributions] if isinstance(distributions, str) else list(distributions))
+        if len(names) > 1 or self.distributions[names[0]]['kernel'] != 'DRT':  # inversion.py:3050-3052
+            single = self._single
+            self._single = False
+            Zr = self.predict_Z(np.array([1e20, 1e-20]), distributions=names, percentile=percentile)
+            self._single = single
+            rp = (Zr[:, 1] - Zr[:, 0]).real
+            return float(rp[0]) if self._single else rp
+        name = names[0]
         eps = self.distributions[name]['epsilon']
         if percentile is None:
             rp = self._coef_batch(name).sum(dim=1) * np.pi ** 0.5 / eps
@@ -374,14 +551,12 @@ class Inverter:
         error model.  Returns indices ([n] for one spectrum, [n, 2] (spectrum, frequency) for a batch)."""
         if self.fit_type not in ('map', 'bayes'):
             raise NotImplementedError('check_outliers from a ridge fit needs ridge_fit (not wired up in this build)')
-        name = list(self.distributions.keys())[0]
-        m = self.distribution_matrices[name]
-        coef = torch.as_tensor(self.distribution_fits[name]['coef'], device=self.device).reshape(-1, m['A_re'].shape[1])
-        Rinf = torch.as_tensor(self.R_inf, dtype=torch.float64, device=self.device).reshape(-1, 1)
-        ind = torch.as_tensor(self.inductance, dtype=torch.float64, device=self.device).reshape(-1, 1)
-        fd = torch.as_tensor(self.f_train, device=self.device)
-        err_re = coef @ m['A_re'].T + Rinf - self.Z_train.real
-        err_im = coef @ m['A_im'].T + 2 * np.pi * fd * ind - self.Z_train.imag
+        single = self._single
+        self._single = False
+        Zp = self.predict_Z(self.f_train)
+        self._single = single
+        err_re = Zp.real - self.Z_train.real
+        err_im = Zp.imag - self.Z_train.imag
         st = torch.as_tensor(self.error_fit['sigma_tot'], device=self.device).reshape(-1, 2 * len(self.f_train))
         nf = len(self.f_train)
         zs = torch.sqrt(((err_re / st[:, :nf]) ** 2 + (err_im / st[:, nf:]) ** 2) / 2)

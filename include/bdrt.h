@@ -169,6 +169,8 @@ typedef struct {
   unsigned long long seed;
   long long spectrum_offset; /* global index of spectrum 0 of this batch (Philox key; makes results independent of
                                 how the batch is sharded over GPUs) */
+  const long long* spectrum_ids; /* optional device array [B] of global spectrum indices (overrides
+                                    spectrum_offset + b); NULL for a contiguous batch */
 } bdrt_nuts_opts;
 void bdrt_nuts_default_opts(bdrt_nuts_opts* o);
 

@@ -4,7 +4,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, 'tests'))
 import numpy as np, torch
 from helpers import GOLD, gpu_problem, load_spectrum, oracle_batch
-from oracle.nuts import ess_bulk
+from oracle.nuts import ess_bulk, mcse_mean, mcse_quantile
 NAME = 'ZARC-RL_uniform_0.25'
 gold = np.load(os.path.join(GOLD, f'nuts_{NAME}.npz'))
 freq, Z = load_spectrum(NAME)
@@ -24,11 +24,13 @@ for dense in ('0', '1'):
         mean, sd = flat.mean(0), flat.std(0, ddof=1)
         q025, q975 = np.percentile(flat, 2.5, axis=0), np.percentile(flat, 97.5, axis=0)
         ess = np.array([ess_bulk(cons[:, :, i]) for i in range(K + 6)])
-        se = np.hypot(sd / np.sqrt(ess), gold['sd'] / np.sqrt(gold['ess']))
+        ses = {'mean': np.hypot([mcse_mean(cons[:, :, i]) for i in range(K + 6)], gold['mcse_mean']),
+               'q025': np.hypot([mcse_quantile(cons[:, :, i], 0.025) for i in range(K + 6)], gold['mcse_q025']),
+               'q975': np.hypot([mcse_quantile(cons[:, :, i], 0.975) for i in range(K + 6)], gold['mcse_q975'])}
         scale = np.abs(gold['mean'][:K]).max()
         msg = []
         for nm, a, b, f in (('mean', mean, gold['mean'], 1.0), ('q025', q025, gold['q025'], 2.67), ('q975', q975, gold['q975'], 2.67)):
-            z = np.abs(a - b) / (f * se)
+            z = np.abs(a - b) / ses[nm]
             big = np.abs(a - b) > 2e-3 * np.r_[np.full(K, scale), np.abs(b[K:]) + 1e-12]
             zz = np.where(big, z, 0)
             i = int(np.argmax(zz))

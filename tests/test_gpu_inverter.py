@@ -1,0 +1,165 @@
+"""GPU: the Inverter facade end to end (the call a user of the reference makes) -- single spectrum in reference shapes,
+batches, both modes, the outlier model, the two-distribution model, post-fit queries, and loud errors for what the CUDA
+path does not implement.  Loose goldens: the paper's published MAP / HMC DRT curves."""
+import numpy as np
+import pytest
+import torch
+
+from helpers import GOLD, load_spectrum, sp_dists, sp_spectrum
+
+pytestmark = pytest.mark.gpu
+
+
+def _gold():
+    import os
+    return np.load(os.path.join(GOLD, 'spectra.npz'))
+
+
+def test_fit_map_single_spectrum_reference_shapes():
+    from bayes_drt_b200 import Inverter
+    name = 'ZARC-RL_uniform_0.25'
+    freq, Z = load_spectrum(name)
+    inv = Inverter()
+    inv.fit(freq, Z, mode='optimize')
+    assert inv.fit_type == 'map' and inv.stan_model_name == 'Series_StanModel.pkl'
+    coef = inv.distribution_fits['DRT']['coef']
+    assert isinstance(coef, np.ndarray) and coef.shape == (101,)
+    assert isinstance(inv.R_inf, float) and isinstance(inv.inductance, float)
+    assert inv.error_fit['sigma_tot'].shape == (162,) and inv.error_fit['sigma_res'] > 0
+    assert abs(inv.R_inf - 1.0) < 0.02
+    g = _gold()
+    gamma = inv.predict_distribution('DRT', eval_tau=g[name + '/map_tau'])
+    gold = g[name + '/map_gamma']
+    assert np.max(np.abs(gamma - gold)) <= 0.03 * gold.max()  # paper curve (legacy code, Stan's own termination)
+    Zp = inv.predict_Z(freq)
+    assert Zp.shape == (81,) and np.max(np.abs(Zp - Z)) < 0.02
+    assert abs(inv.predict_Rp() - 0.8) < 0.03  # truth R_p = 0.8 for ZARC-RL
+    s_re, s_im = inv.predict_sigma()
+    assert s_re.shape == (81,) and (s_re > 0).all() and (s_im > 0).all()
+    # frequencies in ascending order give the same fit (the reference sorts, inversion.py:2138-2141)
+    inv2 = Inverter()
+    inv2.fit(freq[::-1].copy(), Z[::-1].copy(), mode='optimize')
+    assert np.allclose(inv2.distribution_fits['DRT']['coef'], coef, rtol=0, atol=1e-12)
+
+
+def test_fit_map_batch_matches_single_and_polish():
+    from bayes_drt_b200 import Inverter
+    names = ['ZARC_uniform_0.25', 'ZARC-RL_uniform_0.25', '2ZARC_uniform_0.25']
+    freq = load_spectrum(names[0])[0]
+    Zb = np.stack([load_spectrum(n)[1] for n in names])
+    inv = Inverter()
+    inv.fit(freq, torch.tensor(Zb), mode='optimize', polish=True)
+    coef = inv.distribution_fits['DRT']['coef']
+    assert torch.is_tensor(coef) and coef.is_cuda and tuple(coef.shape) == (3, 101)
+    assert tuple(inv.R_inf.shape) == (3,) and tuple(inv.error_fit['sigma_tot'].shape) == (3, 162)
+    assert (inv._opt_result['gnorm'] < 1e-6).all()
+    # spectrum 1 fitted alone with the same global index -> identical init -> identical result
+    one = Inverter()
+    one.fit(freq, Zb[1], mode='optimize', polish=True, spectrum_offset=1)
+    assert np.allclose(one.distribution_fits['DRT']['coef'], coef[1].cpu().numpy(), rtol=0, atol=1e-9)
+    rp = inv.predict_Rp()
+    assert tuple(rp.shape) == (3,) and abs(rp[1].item() - 0.8) < 0.03
+
+
+def test_fit_sample_percentiles_and_outlier_model():
+    from bayes_drt_b200 import Inverter
+    name = 'ZARC-RL_uniform_0.25'
+    freq, Z = load_spectrum(name)
+    inv = Inverter()
+    inv.fit(freq, Z, mode='sample', chains=4, warmup=200, samples=100, nonneg=True, outliers=True)
+    assert inv.fit_type == 'bayes' and inv.stan_model_name == 'Series_pos_outliers_StanModel.pkl'
+    assert inv.error_fit['sigma_out'].shape == (81,)
+    lo, mid, hi = (inv.coef_percentile('DRT', p) for p in (2.5, 50, 97.5))
+    assert lo.shape == (101,) and (lo <= mid).all() and (mid <= hi).all() and (lo >= 0).all()
+    g = _gold()
+    tau = g[name + '/bayes_tau']
+    gm = inv.predict_distribution('DRT', eval_tau=tau)
+    glo = inv.predict_distribution('DRT', eval_tau=tau, percentile=2.5)
+    ghi = inv.predict_distribution('DRT', eval_tau=tau, percentile=97.5)
+    gold = g[name + '/bayes_gamma']
+    assert np.max(np.abs(gm - gold)) <= 0.08 * gold.max()  # different model variant + MC error of 400 draws
+    assert (glo <= ghi + 1e-12).all()
+    rp_lo, rp, rp_hi = inv.predict_Rp(percentile=2.5), inv.predict_Rp(), inv.predict_Rp(percentile=97.5)
+    assert rp_lo < rp < rp_hi and abs(rp - 0.8) < 0.05
+    Zlo = inv.predict_Z(freq, percentile=2.5)
+    Zhi = inv.predict_Z(freq, percentile=97.5)
+    assert (Zlo.real <= Zhi.real).all()
+    assert inv._sample_stats['n_leapfrog'].sum().item() > 0
+
+
+def test_fit_series_parallel_distributions():
+    from bayes_drt_b200 import Inverter
+    freq = np.logspace(6, -2, 81)
+    Z = np.stack([sp_spectrum(freq, seed=s, td=0.2 * (s + 1)) for s in range(2)])
+    ser, par = sp_dists(np.logspace(6, -2, 81), np.logspace(6, -2, 81))
+    inv = Inverter(distributions={'DRT': ser, 'TP-DDT': par})
+    inv.fit(freq, torch.tensor(Z), mode='optimize', nonneg=True, max_iter=5000)
+    assert inv.stan_model_name == 'Series-Parallel_pos_StanModel.pkl'
+    cs, cp = inv.distribution_fits['DRT']['coef'], inv.distribution_fits['TP-DDT']['coef']
+    assert tuple(cs.shape) == (2, 81) and tuple(cp.shape) == (2, 81) and (cs >= 0).all() and (cp >= 0).all()
+    Zp = inv.predict_Z(freq)
+    assert tuple(Zp.shape) == (2, 81)
+    assert (Zp.cpu() - torch.tensor(Z)).abs().max().item() < 0.03
+    assert torch.allclose(inv.R_inf.cpu(), torch.full((2,), 0.5, dtype=torch.float64), atol=0.05)
+    rp = inv.predict_Rp()  # R1 + Rd = 1.7
+    assert torch.allclose(rp.cpu(), torch.full((2,), 1.7, dtype=torch.float64), atol=0.15)
+    with pytest.raises(NotImplementedError):
+        inv.fit(freq, torch.tensor(Z), mode='optimize', nonneg=True, outliers=True)
+
+
+def test_unsupported_options_are_loud():
+    from bayes_drt_b200 import Inverter
+    freq, Z = load_spectrum('ZARC_uniform_0.25')
+    inv = Inverter()
+    for kw in (dict(part='real'), dict(fitY=True), dict(model_str='Series_StanModel.pkl'), dict(add_stan_data={'a': 1})):
+        with pytest.raises(NotImplementedError):
+            inv.fit(freq, Z, **kw)
+    with pytest.raises(ValueError):
+        inv.fit(freq, Z, mode='laplace')
+    with pytest.raises(ValueError):
+        inv.fit(freq[:-1], Z)
+    with pytest.raises(ValueError):
+        Inverter(basis='Zic')
+    with pytest.raises(NotImplementedError):
+        Inverter(distributions={'DDT': {'kernel': 'DDT', 'dist_type': 'parallel', 'symmetry': 'planar',
+                                        'bc': 'transmissive'}}).fit(freq, Z)
+    with pytest.raises(ValueError):
+        inv.coef_percentile('DRT', 50)  # no bayes fit yet
+
+
+def test_init_from_ridge_and_auto_outliers():
+    """The reference's recommended flow (inversion.py:1154-1187, :1616-1682): ridge solution -> Stan initial values;
+    outliers='auto' switches spectra with IQR-flagged residuals to the outlier-robust model."""
+    from bayes_drt_b200 import Inverter
+    freq, Z = load_spectrum('ZARC_uniform_0.25')
+    Zo = Z.copy()
+    Zo[40] += 0.15 * (1 + 1j)  # two gross outliers
+    Zo[41] -= 0.12j
+    Zb = torch.tensor(np.stack([Z, Zo]))
+    rnd = Inverter()
+    rnd.fit(freq, Zb, mode='optimize')
+    inv = Inverter()
+    inv.fit(freq, Zb, mode='optimize', init_from_ridge=True, outliers='auto')
+    assert inv._outlier_model.tolist() == [False, True]
+    assert inv.stan_model_name == 'Series_outliers_StanModel.pkl'
+    so = inv.error_fit['sigma_out']
+    assert torch.isnan(so[0]).all() and torch.isfinite(so[1]).all()
+    # the flagged points carry most of the outlier variance
+    assert set(torch.topk(so[1], 2).indices.tolist()) == {40, 41}
+    # ridge initialisation: far fewer L-BFGS iterations than Stan's random initialisation, same DRT on the clean spectrum
+    assert inv._opt_result['iters'][0].item() < 0.7 * rnd._opt_result['iters'][0].item()
+    c0, c1 = inv.distribution_fits['DRT']['coef'][0], rnd.distribution_fits['DRT']['coef'][0]
+    assert (c0 - c1).abs().max().item() < 0.03 * c1.abs().max().item()
+    # the robust fit of the contaminated spectrum stays close to the clean fit; the plain model is visibly distorted
+    c_rob, c_plain = inv.distribution_fits['DRT']['coef'][1], rnd.distribution_fits['DRT']['coef'][1]
+    assert (c_rob - c0).abs().max().item() < (c_plain - c0).abs().max().item()
+    assert torch.isfinite(inv.R_inf).all() and abs(inv.R_inf[1].item() - 1.0) < 0.03
+    # single-spectrum call warns like the reference
+    one = Inverter()
+    with pytest.warns(UserWarning, match='likely outliers'):
+        one.fit(freq, Zo, mode='optimize', outliers='auto')
+    assert one.stan_model_name == 'Series_outliers_StanModel.pkl' and one.error_fit['sigma_out'].shape == (81,)
+    # nonneg + ridge init (exact zeros of the QP are floored before the log transform)
+    pos = Inverter()
+    pos.fit(freq, Z, mode='optimize', nonneg=True, init_from_ridge=True)
+    assert np.isfinite(pos.distribution_fits['DRT']['coef']).all() and abs(pos.R_inf - 1.0) < 0.02

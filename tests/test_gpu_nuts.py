@@ -1,5 +1,5 @@
 """GPU: batched on-device NUTS against a long run of the oracle's restatement of Stan's sampler
-(tests/golden/nuts_*.npz from scripts/make_golden_nuts.py): posterior means and 95 % interval end points of every DRT
+(tests/golden/nuts_*.npz from scripts/make_golden_nuts.py: 16 chains x (300 + 2000)): posterior means and 95 % interval end points of every DRT
 coefficient and of R_inf / inductance / error-model parameters within 3 Monte-Carlo standard errors (north star).
 Random streams cannot match (Philox vs numpy), so parity is statistical."""
 import os
@@ -39,22 +39,27 @@ def test_nuts_posterior_matches_oracle():
     cons = torch.cat([out['x'], out['Rinf'][..., None], out['induc'][..., None], out['sigma_res'][..., None],
                       out['alpha_prop'][..., None], out['alpha_re'][..., None], out['alpha_im'][..., None]],
                      dim=-1)[0].cpu().numpy()  # [chains, samples, K+6]
+    from oracle.nuts import mcse_mean, mcse_quantile
     flat = cons.reshape(-1, K + 6)
-    mean, sd = flat.mean(0), flat.std(0, ddof=1)
+    mean = flat.mean(0)
     q025, q975 = np.percentile(flat, 2.5, axis=0), np.percentile(flat, 97.5, axis=0)
-    ess = np.array([_ess(cons[:, :, i]) for i in range(K + 6)])
-    # Monte-Carlo standard errors: mean sd/sqrt(ESS); 2.5 / 97.5 % points ~ 2.67 sd/sqrt(ESS) (normal approximation)
-    se_mean = np.hypot(sd / np.sqrt(ess), gold['sd'] / np.sqrt(gold['ess']))
-    se_q = 2.67 * se_mean
+    # Monte-Carlo standard errors of both sides (Vehtari et al. 2021): sd / sqrt(ESS) for the mean; for a quantile the ESS
+    # of the indicator I(x <= q) gives a Beta interval in probability that is mapped back through the empirical
+    # quantile function.  The golden file (16 oracle chains x 2000 draws) carries its own MCSEs.
+    se_mean = np.hypot([mcse_mean(cons[:, :, i]) for i in range(K + 6)], gold['mcse_mean'])
+    se_lo = np.hypot([mcse_quantile(cons[:, :, i], 0.025) for i in range(K + 6)], gold['mcse_q025'])
+    se_hi = np.hypot([mcse_quantile(cons[:, :, i], 0.975) for i in range(K + 6)], gold['mcse_q975'])
     z_mean = np.abs(mean - gold['mean']) / se_mean
-    z_lo = np.abs(q025 - gold['q025']) / se_q
-    z_hi = np.abs(q975 - gold['q975']) / se_q
-    # coefficients far in the tails of the DRT are ~0 with tiny sd: judge them on the scale of the peak as well
+    z_lo = np.abs(q025 - gold['q025']) / se_lo
+    z_hi = np.abs(q975 - gold['q975']) / se_hi
+    # north star: within 3 MCSE.  With 3 x 107 comparisons a few excursions beyond 3 are expected by chance (and the
+    # MCSEs are themselves estimates), so: at most 3 % beyond 3 and none beyond 6; coefficients far in the tails of the
+    # DRT are ~0 with tiny sd and are judged on the scale of the peak as well
     scale = np.abs(gold['mean'][:K]).max()
     for z, a, b in ((z_mean, mean, gold['mean']), (z_lo, q025, gold['q025']), (z_hi, q975, gold['q975'])):
         viol = (z > 3.0) & (np.abs(a - b) > 2e-3 * np.r_[np.full(K, scale), np.abs(b[K:]) + 1e-12])
         assert viol.mean() <= 0.03, (np.where(viol)[0], z[viol])
-        assert np.all(z[viol] < 6.0) if viol.any() else True
+        assert np.all(z[viol] < 6.0) if viol.any() else True, (np.where(viol)[0], z[viol])
     # step sizes and tree depths of the same order as the oracle's chains
     assert 0.3 < np.median(r['stepsize'].cpu().numpy()) / np.median(gold['stepsize']) < 3.0
 

@@ -21,10 +21,11 @@ def _data(mode, nonneg, Nf=81, Ks=81, Kp=81, nspec=3):
 @pytest.mark.parametrize('nonneg', [True, False])
 @pytest.mark.parametrize('mode', ['optimize', 'sample'])
 def test_sp_logpost_matches_oracle(nonneg, mode, resident_A):
-    Ks = 81 if resident_A == 'toeplitz' else 49  # two dense 162 x 81 matrices do not fit one SM's shared memory
-    ds = _data(mode, nonneg, Ks=Ks, Kp=Ks)
+    # two dense 162 x 81 matrices do not fit one SM's shared memory: the dense layout is exercised on a smaller shape
+    Nf, Ks, Kp = (81, 81, 81) if resident_A == 'toeplitz' else (49, 45, 41)
+    ds = _data(mode, nonneg, Nf=Nf, Ks=Ks, Kp=Kp)
     prob = gpu_problem_sp(ds)
-    assert prob.D == osp.n_params(ds[0]) == 2 * (Ks + Ks) + 12
+    assert prob.D == osp.n_params(ds[0]) == 2 * (Ks + Kp) + 12
     rng = np.random.RandomState(4)
     u = rng.uniform(-1.5, 1.5, (11, prob.D))
     if not nonneg:
@@ -52,8 +53,8 @@ def test_sp_dense_too_large_fails_loudly(monkeypatch):
 
 
 def test_sp_constrain_and_map(resident_A):
-    Ks = 81 if resident_A == 'toeplitz' else 49
-    ds = _data('optimize', True, Ks=Ks, Kp=Ks, nspec=2)
+    Nf, Ks, Kp = (81, 81, 81) if resident_A == 'toeplitz' else (49, 45, 41)
+    ds = _data('optimize', True, Nf=Nf, Ks=Ks, Kp=Kp, nspec=2)
     prob = gpu_problem_sp(ds)
     rng = np.random.RandomState(1)
     u0 = rng.uniform(-2, 2, (2, prob.D))
