@@ -184,11 +184,7 @@ lbfgs_kernel(BdrtModel m, bdrt_lbfgs_opts o, double* __restrict__ U, double* lp_
     __syncwarp();
   };
 
-  while (true) {
-    int b = 0;
-    if (lane == 0) b = atomicAdd(queue, 1);
-    b = __shfl_sync(0xffffffffu, b, 0);
-    if (b >= m.B) break;
+  auto run_spectrum = [&](int b) {
     Zs = m.Z + (long long)b * m.N2;
     double* ub = U + (long long)b * D;
     for (int i = lane; i < D; i += 32) xn[i] = ub[i];
@@ -370,12 +366,48 @@ lbfgs_kernel(BdrtModel m, bdrt_lbfgs_opts o, double* __restrict__ U, double* lp_
       if (neval_out) neval_out[b] = neval;
       if (status_out) status_out[b] = code;
     }
-  }
+  };
   // drain: keep serving the cooperative matrix products until every slot of the CTA is out of work
-  if (lane == 0) atomicSub((int*)n_active, 1);
-  while (true) {
-    engine_eval<TOEP, ND>(m, sm, false, nullptr, nullptr, nullptr, 0, n_active, &snap);
-    if (snap == 0) break;
+  auto drain = [&]() {
+    if (lane == 0) atomicSub((int*)n_active, 1);
+    while (true) {
+      engine_eval<TOEP, ND>(m, sm, false, nullptr, nullptr, nullptr, 0, n_active, &snap);
+      if (snap == 0) break;
+    }
+  };
+  if (m.d[0].A_stride == 0) {
+    while (true) {
+      int b = 0;
+      if (lane == 0) b = atomicAdd(queue, 1);
+      b = __shfl_sync(0xffffffffu, b, 0);
+      if (b >= m.B) break;
+      run_spectrum(b);
+    }
+    drain();
+  } else {
+    // per-spectrum grids: the slots of a CTA share the resident operands, so a CTA takes one spectrum at a time; slot 0
+    // optimises it, the other warps only serve the cooperative products
+    __shared__ int s_spec;
+    while (true) {
+      cta_sync();
+      if (threadIdx.x == 0) {
+        s_spec = atomicAdd(queue, 1);
+        *n_active = 1;
+      }
+      cta_sync();
+      const int b = s_spec;
+      if (b >= m.B) break;
+      engine_load(m, sm, b);
+      if (warp == 0) {
+        run_spectrum(b);
+        drain();
+      } else {
+        while (true) {
+          engine_eval<TOEP, ND>(m, sm, false, nullptr, nullptr, nullptr, 0, n_active, &snap);
+          if (snap == 0) break;
+        }
+      }
+    }
   }
 }
 
@@ -397,8 +429,6 @@ extern "C" int bdrt_map_lbfgs(bdrt_ctx* ctx, const bdrt_series_data* data, const
   if (!u || !opts) BDRT_FAIL(ctx, BDRT_E_NULL, "bdrt_map_lbfgs: null pointer");
   if (opts->history < 1 || opts->history > MAXHIST) BDRT_FAIL(ctx, BDRT_E_SIZE, "history must be in 1..%d", MAXHIST);
   if (opts->max_iter < 1) BDRT_FAIL(ctx, BDRT_E_SIZE, "max_iter must be >= 1");
-  if (data && data->per_spectrum_grid)
-    BDRT_FAIL(ctx, BDRT_E_UNSUPPORTED, "bdrt_map_lbfgs: per-spectrum grids are not implemented in this build");
   BdrtModel m;
   {
     // sizes first (model_prepare needs the scratch size)
@@ -407,7 +437,8 @@ extern "C" int bdrt_map_lbfgs(bdrt_ctx* ctx, const bdrt_series_data* data, const
   const int D = bdrt_num_params(data);
   const int Dpad = (D + 1) & ~1;
   const int max_ctas = 2 * ctx->sm_count;  // scratch is sized for the two-CTAs-per-SM (Toeplitz) plan
-  const int grid_max = data->B == 0 ? 0 : ((data->B + NSLOT - 1) / NSLOT < max_ctas ? (data->B + NSLOT - 1) / NSLOT : max_ctas);
+  const int groups = data->per_spectrum_grid ? data->B : (data->B + NSLOT - 1) / NSLOT;
+  const int grid_max = data->B == 0 ? 0 : (groups < max_ctas ? groups : max_ctas);
   int grid = grid_max;
   const size_t hist_bytes = (size_t)grid_max * NSLOT * 2 * MAXHIST * Dpad * sizeof(double);
   const size_t gvec_bytes = (size_t)grid_max * NSLOT * 5 * Dpad * sizeof(double);

@@ -96,7 +96,8 @@ __global__ void band_prep_kernel(const double* L, int K, double* Lb, int* info) 
 
 // Is the stacked kernel matrix [A_re; A_im] Toeplitz in each part (shared log-uniform grid with the measurement
 // frequencies on the basis grid -- the case the reference special-cases too, matrices.py:145-242)?  info[2] &= yes.
-__global__ void toep_check_kernel(const double* A, int Nf, int K, int* info) {
+__global__ void toep_check_kernel(const double* A0, long long stride, int Nf, int K, int* info) {
+  const double* A = A0 + blockIdx.x * stride;  // one block per grid
   __shared__ double s_red[32];
   __shared__ double s_max;
   double mx = 0.0;
@@ -186,7 +187,7 @@ int bdrt_model_prepare(bdrt_ctx* ctx, const bdrt_series_data* d, BdrtModel* m, s
   int* info = (int*)ctx->ws;
   // BDRT_FORCE_DENSE=1 keeps the dense-resident A path even for Toeplitz grids (used by the tests to cover both)
   const char* fd = getenv("BDRT_FORCE_DENSE");
-  const int try_toep = !d->per_spectrum_grid && !(fd && fd[0] == '1');
+  const int try_toep = !(fd && fd[0] == '1');
   const int init[8] = {0, 1, try_toep, 0, 0, 1, 0, 0};  // per distribution i: info[4i] = bw, info[4i+1] = L Toeplitz
   BDRT_CUDA(ctx, cudaMemcpyAsync(info, init, sizeof(init), cudaMemcpyHostToDevice, ctx->stream));
   for (int i = 0; i < nd; ++i) {
@@ -194,8 +195,9 @@ int bdrt_model_prepare(bdrt_ctx* ctx, const bdrt_series_data* d, BdrtModel* m, s
     band_prep_kernel<<<3, 256, 0, ctx->stream>>>(Ls[i], Ks[i], Lb, info + 4 * i);
     ctx->launches++;
     m->d[i].Lb = Lb;
-    if (try_toep) {
-      toep_check_kernel<<<1, 512, 0, ctx->stream>>>(As[i], d->Nf, Ks[i], info);
+    if (try_toep && d->B > 0) {
+      toep_check_kernel<<<d->per_spectrum_grid ? (d->B > 0 ? d->B : 1) : 1, 512, 0, ctx->stream>>>(
+          As[i], m->d[i].A_stride, d->Nf, Ks[i], info);
       ctx->launches++;
     }
   }

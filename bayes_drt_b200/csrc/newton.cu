@@ -89,7 +89,7 @@ newton_kernel(BdrtModel m, bdrt_newton_opts o, double* __restrict__ U, double* l
   __shared__ int s_flag[4];
 
   for (int b = blockIdx.x; b < m.B; b += gridDim.x) {
-    engine_load(m, sm, 0);
+    engine_load(m, sm, b);
     const double* Zs = m.Z + (long long)b * m.N2;
     for (int i = tid; i < D; i += NTHREADS) { u[i] = U[(long long)b * D + i]; frozen[i] = 0; }
     __syncthreads();
@@ -170,7 +170,7 @@ newton_kernel(BdrtModel m, bdrt_newton_opts o, double* __restrict__ U, double* l
         __syncthreads();
         chol_solve_packed(Hp, D, step, s_flag);
         const bool notpd = s_flag[0] != 0;
-        if (chol_in_smem) engine_load(m, sm, 0);  // the factor overlaid the engine's resident operands
+        if (chol_in_smem) engine_load(m, sm, b);  // the factor overlaid the engine's resident operands
         if (notpd) { mu *= 10.0; __syncthreads(); continue; }
         // tail jump of boundary-bound lower=0 coordinates (see header)
         for (int i = tid; i < D; i += NTHREADS) {
@@ -238,8 +238,6 @@ extern "C" int bdrt_map_newton(bdrt_ctx* ctx, const bdrt_series_data* data, cons
                                double* lp, double* gnorm, int* iters, int* n_eval) {
   if (!ctx) return BDRT_E_NULL;
   if (!data || !opts || !u) BDRT_FAIL(ctx, BDRT_E_NULL, "bdrt_map_newton: null pointer");
-  if (data->per_spectrum_grid)
-    BDRT_FAIL(ctx, BDRT_E_UNSUPPORTED, "bdrt_map_newton: per-spectrum grids are not implemented in this build");
   if (opts->max_iter < 0 || !(opts->fd_step > 0)) BDRT_FAIL(ctx, BDRT_E_SIZE, "bad newton options");
   const int D = bdrt_num_params(data);
   const int Dpad = (D + 1) & ~1;

@@ -108,11 +108,8 @@ nuts_kernel(BdrtModel m, bdrt_nuts_opts o, const double* __restrict__ U0, double
     for (int i = lane; i < D; i += 32) dst[i] = src[i];
   };
 
-  while (true) {
-    long long wi = 0;
-    if (lane == 0) wi = atomicAdd(queue, 1);
-    wi = __shfl_sync(0xffffffffu, wi, 0);
-    if (wi >= n_work) break;
+  // one adaptive chain: work item wi = spectrum * chains + chain
+  auto run_chain = [&](long long wi) {
     const int b = (int)(wi / o.chains);
     Zs = m.Z + (long long)b * m.N2;
     const long long sid = o.spectrum_ids ? o.spectrum_ids[b] : o.spectrum_offset + b;
@@ -357,12 +354,52 @@ nuts_kernel(BdrtModel m, bdrt_nuts_opts o, const double* __restrict__ U0, double
       if (nmax_out) nmax_out[wi] = n_maxd;
       if (accept_out) accept_out[wi] = o.samples > 0 ? acc_sum / o.samples : 0.0;
     }
-  }
-  int snap;
-  if (lane == 0) atomicSub((int*)n_active, 1);
-  while (true) {
-    engine_eval<TOEP, ND>(m, sm, false, nullptr, nullptr, nullptr, 0, n_active, &snap);
-    if (snap == 0) break;
+  };
+  // drain: keep serving the cooperative matrix products until every slot of the CTA is out of work
+  auto drain = [&]() {
+    int snap;
+    if (lane == 0) atomicSub((int*)n_active, 1);
+    while (true) {
+      engine_eval<TOEP, ND>(m, sm, false, nullptr, nullptr, nullptr, 0, n_active, &snap);
+      if (snap == 0) break;
+    }
+  };
+
+  if (m.d[0].A_stride == 0) {
+    // shared grid: every warp pulls (spectrum, chain) items from the queue until it is empty
+    while (true) {
+      long long wi = 0;
+      if (lane == 0) wi = atomicAdd(queue, 1);
+      wi = __shfl_sync(0xffffffffu, wi, 0);
+      if (wi >= n_work) break;
+      run_chain(wi);
+    }
+    drain();
+  } else {
+    // per-spectrum grids: the 8 slots of a CTA share the resident operands, so a CTA takes one spectrum at a time and
+    // its slots run that spectrum's chains (chain = warp, warp + 8, ...)
+    __shared__ int s_spec;
+    while (true) {
+      cta_sync();
+      if (threadIdx.x == 0) {
+        s_spec = atomicAdd(queue, 1);
+        *n_active = o.chains < NWARP ? o.chains : NWARP;
+      }
+      cta_sync();
+      const int b = s_spec;
+      if (b >= m.B) break;
+      engine_load(m, sm, b);
+      if (warp < o.chains) {
+        for (int c = warp; c < o.chains; c += NWARP) run_chain((long long)b * o.chains + c);
+        drain();
+      } else {
+        int snap;
+        while (true) {
+          engine_eval<TOEP, ND>(m, sm, false, nullptr, nullptr, nullptr, 0, n_active, &snap);
+          if (snap == 0) break;
+        }
+      }
+    }
   }
 }
 
@@ -389,13 +426,11 @@ extern "C" int bdrt_nuts(bdrt_ctx* ctx, const bdrt_series_data* data, const bdrt
   if (opts->chains < 1 || opts->warmup < 0 || opts->samples < 0) BDRT_FAIL(ctx, BDRT_E_SIZE, "bad chains/warmup/samples");
   if (opts->max_treedepth < 1 || opts->max_treedepth > MAXDEPTH)
     BDRT_FAIL(ctx, BDRT_E_SIZE, "max_treedepth must be in 1..%d", MAXDEPTH);
-  if (data->per_spectrum_grid)
-    BDRT_FAIL(ctx, BDRT_E_UNSUPPORTED, "bdrt_nuts: per-spectrum grids are not implemented in this build");
   const int D = bdrt_num_params(data);
   const int Dpad = (D + 1) & ~1;
   const long long n_work = (long long)data->B * opts->chains;
   if (n_work > 2000000000LL) BDRT_FAIL(ctx, BDRT_E_SIZE, "too many chains in one call");
-  const long long groups = (n_work + NSLOT - 1) / NSLOT;
+  const long long groups = data->per_spectrum_grid ? data->B : (n_work + NSLOT - 1) / NSLOT;
   const int max_ctas = 2 * ctx->sm_count;  // scratch is sized for the two-CTAs-per-SM (Toeplitz) plan
   const int grid_max = n_work == 0 ? 0 : (int)(groups < max_ctas ? groups : max_ctas);
   int grid = grid_max;
