@@ -156,7 +156,13 @@ lbfgs_kernel(BdrtModel m, bdrt_lbfgs_opts o, double* __restrict__ U, double* lp_
     for (int i = 0; i < 5; ++i)
       vec[i] = (i < nvec_smem) ? (suser + ((long long)warp * nvec_smem + i) * Dpad) : (gbase + (long long)i * Dpad);
   }
-  double *xk = vec[0], *gk = vec[1], *pk = vec[2], *xn = vec[3], *gn = vec[4];
+  // xn / gn are what the engine reads and writes (scattered accesses): they always live in the first (shared-memory)
+  // vectors; gk, which is touched once per iteration, is the one that overflows to global scratch
+  double* const xn = vec[0];
+  double* const gn = vec[1];
+  double* const pk = vec[2];
+  double* const xk = vec[3];
+  double* const gk = vec[4];
   double* S = hist + ((long long)blockIdx.x * NSLOT + warp) * 2 * MAXHIST * Dpad;
   double* Y = S + (long long)MAXHIST * Dpad;
   int snap;
@@ -195,8 +201,12 @@ lbfgs_kernel(BdrtModel m, bdrt_lbfgs_opts o, double* __restrict__ U, double* lp_
     if (!feval(fk)) {
       code = BDRT_TERM_BADINIT;
     } else {
-      { double* t_ = xk; xk = xn; xn = t_; t_ = gk; gk = gn; gn = t_; }
-      for (int i = lane; i < D; i += 32) pk[i] = -gk[i];
+      for (int i = lane; i < D; i += 32) {
+        const double g = gn[i];
+        xk[i] = xn[i];
+        gk[i] = g;
+        pk[i] = -g;
+      }
       __syncwarp();
       int nh = 0, head = 0;  // history: entries head-nh .. head-1 (mod H), newest = head-1
       double rho[MAXHIST], al[MAXHIST];
@@ -222,40 +232,15 @@ lbfgs_kernel(BdrtModel m, bdrt_lbfgs_opts o, double* __restrict__ U, double* lp_
           const double c1dfp = 1e-4 * dfp, c2dfp = 0.9 * dfp;
           double alpha0 = 1e-12, prevF = fk, prevDFp = dfp;
           int nits = 0, restarts = 0, ret = -1;  // ret: 0 ok, 1 fail
-          // zoom bracket
-          bool zoom = false;
+          // One loop for both stages of Stan's line search (bracketing: WolfeLineSearch, then WolfLSZoom with
+          // min_range 1e-16), so that the objective is evaluated at a single call site (the engine is inlined there).
+          bool zoom = false, retry = false;
           double alo = 0, aloF = 0, aloDFp = 0, ahi = 0, ahiF = 0, ahiDFp = 0;
-          while (ret < 0 && !zoom) {
-            if (nits >= 20) { ret = 1; break; }
-            step_to(alpha);
-            if (!feval(f1)) {
-              if (restarts >= 10) { ret = 1; break; }
-              alpha = 0.5 * (alpha0 + alpha);
-              ++restarts;
-              continue;
-            }
-            restarts = 0;
-            newDFp = vdot(gn, pk, D, lane);
-            if (f1 > fk + alpha * c1dfp || (f1 >= prevF && nits > 0)) {
-              alo = alpha0; aloF = prevF; aloDFp = prevDFp; ahi = alpha; ahiF = f1; ahiDFp = newDFp;
-              zoom = true;
-              break;
-            }
-            if (fabs(newDFp) <= -c2dfp) { ret = 0; break; }
-            if (newDFp >= 0) {
-              alo = alpha; aloF = f1; aloDFp = newDFp; ahi = alpha0; ahiF = prevF; ahiDFp = prevDFp;
-              zoom = true;
-              break;
-            }
-            alpha0 = alpha; prevF = f1; prevDFp = newDFp;
-            alpha *= 10.0;
-            ++nits;
-          }
-          if (zoom) {
-            // ---------------- WolfLSZoom (min_range 1e-16)
-            int itn = 0;
-            ret = -1;
-            while (ret < 0) {
+          int itn = 0;
+          while (ret < 0) {
+            if (!zoom) {
+              if (nits >= 20) { ret = 1; break; }
+            } else if (!retry) {
               ++itn;
               if (fabs(alo - ahi) < 1e-16) { ret = 1; break; }
               if (itn % 5 == 0) {
@@ -268,15 +253,40 @@ lbfgs_kernel(BdrtModel m, bdrt_lbfgs_opts o, double* __restrict__ U, double* lp_
                 const double lo = fmin(alo, ahi), hi = fmax(alo, ahi), rng = fabs(alo - ahi);
                 if (!isfinite(alpha) || alpha < lo + 0.01 * rng || alpha > hi - 0.01 * rng) alpha = 0.5 * (alo + ahi);
               }
-              bool okev;
-              while (true) {
-                step_to(alpha);
-                okev = feval(f1);
-                if (okev) break;
-                alpha = 0.5 * (alpha + fmin(alo, ahi));
-                if (fabs(fmin(alo, ahi) - alpha) < 1e-16) break;
+            }
+            step_to(alpha);
+            const bool okev = feval(f1);
+            if (!zoom) {
+              if (!okev) {
+                if (restarts >= 10) { ret = 1; break; }
+                alpha = 0.5 * (alpha0 + alpha);
+                ++restarts;
+                continue;
               }
-              if (!okev) { ret = 1; break; }
+              restarts = 0;
+              newDFp = vdot(gn, pk, D, lane);
+              if (f1 > fk + alpha * c1dfp || (f1 >= prevF && nits > 0)) {
+                alo = alpha0; aloF = prevF; aloDFp = prevDFp; ahi = alpha; ahiF = f1; ahiDFp = newDFp;
+                zoom = true;
+                continue;
+              }
+              if (fabs(newDFp) <= -c2dfp) { ret = 0; break; }
+              if (newDFp >= 0) {
+                alo = alpha; aloF = f1; aloDFp = newDFp; ahi = alpha0; ahiF = prevF; ahiDFp = prevDFp;
+                zoom = true;
+                continue;
+              }
+              alpha0 = alpha; prevF = f1; prevDFp = newDFp;
+              alpha *= 10.0;
+              ++nits;
+            } else {
+              if (!okev) {
+                alpha = 0.5 * (alpha + fmin(alo, ahi));
+                if (fabs(fmin(alo, ahi) - alpha) < 1e-16) { ret = 1; break; }
+                retry = true;
+                continue;
+              }
+              retry = false;
               newDFp = vdot(gn, pk, D, lane);
               if (f1 > (fk + alpha * c1dfp) || f1 >= aloF) {
                 ahi = alpha; ahiF = f1; ahiDFp = newDFp;
@@ -302,14 +312,17 @@ lbfgs_kernel(BdrtModel m, bdrt_lbfgs_opts o, double* __restrict__ U, double* lp_
         double* Sn = S + (long long)head * Dpad;
         double* Yn = Y + (long long)head * Dpad;
         double skyk = 0, yy = 0, gg = 0, ss = 0;
-        for (int i = lane; i < D; i += 32) {
-          const double s = xn[i] - xk[i], y = gn[i] - gk[i];
+        for (int i = lane; i < D; i += 32) {  // and the accepted point becomes the current one
+          const double xv = xn[i], gv = gn[i];
+          const double s = xv - xk[i], y = gv - gk[i];
           Sn[i] = s;
           Yn[i] = y;
+          xk[i] = xv;
+          gk[i] = gv;
           skyk = fma(s, y, skyk);
           yy = fma(y, y, yy);
           ss = fma(s, s, ss);
-          gg = fma(gn[i], gn[i], gg);
+          gg = fma(gv, gv, gg);
         }
         skyk = warp_sum(skyk); yy = warp_sum(yy); ss = warp_sum(ss); gg = warp_sum(gg);
         const double gradNorm = sqrt(gg), stepNorm = sqrt(ss);
@@ -332,19 +345,18 @@ lbfgs_kernel(BdrtModel m, bdrt_lbfgs_opts o, double* __restrict__ U, double* lp_
         if (nh < H) ++nh;
         fk_1 = fk;
         fk = f1;
-        { double* t_ = xk; xk = xn; xn = t_; t_ = gk; gk = gn; gn = t_; }
         __syncwarp();
         __threadfence_block();
         // ---------------- two-loop recursion -> pk
         if (D <= 32 * 7)
-          two_loop<7>(S, Y, rho, al, gk, pk, D, Dpad, nh, head, H, gamma, lane);
+          two_loop<7>(S, Y, rho, al, gn, pk, D, Dpad, nh, head, H, gamma, lane);
         else if (D <= 32 * 12)
-          two_loop<12>(S, Y, rho, al, gk, pk, D, Dpad, nh, head, H, gamma, lane);
+          two_loop<12>(S, Y, rho, al, gn, pk, D, Dpad, nh, head, H, gamma, lane);
         else
-          two_loop<0>(S, Y, rho, al, gk, pk, D, Dpad, nh, head, H, gamma, lane);
+          two_loop<0>(S, Y, rho, al, gn, pk, D, Dpad, nh, head, H, gamma, lane);
         // ---------------- convergence tests, Stan's order
         const double df = fabs(fk_1 - fk);
-        const double gp = vdot(gk, pk, D, lane);
+        const double gp = vdot(gn, pk, D, lane);
         if (df < o.tol_obj)
           code = BDRT_TERM_ABSF;
         else if (df < o.tol_rel_obj * fmax(fabs(fk_1), fmax(fabs(fk), 1.0)) * EPS)
@@ -367,47 +379,42 @@ lbfgs_kernel(BdrtModel m, bdrt_lbfgs_opts o, double* __restrict__ U, double* lp_
       if (status_out) status_out[b] = code;
     }
   };
-  // drain: keep serving the cooperative matrix products until every slot of the CTA is out of work
-  auto drain = [&]() {
-    if (lane == 0) atomicSub((int*)n_active, 1);
-    while (true) {
-      engine_eval<TOEP, ND>(m, sm, false, nullptr, nullptr, nullptr, 0, n_active, &snap);
-      if (snap == 0) break;
-    }
-  };
-  if (m.d[0].A_stride == 0) {
-    while (true) {
-      int b = 0;
-      if (lane == 0) b = atomicAdd(queue, 1);
-      b = __shfl_sync(0xffffffffu, b, 0);
-      if (b >= m.B) break;
-      run_spectrum(b);
-    }
-    drain();
-  } else {
-    // per-spectrum grids: the slots of a CTA share the resident operands, so a CTA takes one spectrum at a time; slot 0
-    // optimises it, the other warps only serve the cooperative products
-    __shared__ int s_spec;
-    while (true) {
+  // Work distribution.  Shared grid: every warp pulls spectra from the queue until it is empty.  Per-spectrum grids: the
+  // slots of a CTA share the resident operands, so the CTA takes one spectrum at a time, slot 0 optimises it and the
+  // other warps only serve the cooperative products.  Either way a warp that is out of work keeps serving engine_eval()
+  // until every slot of the CTA is done (single call site: the engine is inlined there).
+  const bool per_spec = m.d[0].A_stride != 0;
+  __shared__ int s_spec;
+  while (true) {
+    int b_cta = -1;
+    if (per_spec) {
       cta_sync();
       if (threadIdx.x == 0) {
         s_spec = atomicAdd(queue, 1);
         *n_active = 1;
       }
       cta_sync();
-      const int b = s_spec;
-      if (b >= m.B) break;
-      engine_load(m, sm, b);
-      if (warp == 0) {
-        run_spectrum(b);
-        drain();
-      } else {
-        while (true) {
-          engine_eval<TOEP, ND>(m, sm, false, nullptr, nullptr, nullptr, 0, n_active, &snap);
-          if (snap == 0) break;
-        }
-      }
+      b_cta = s_spec;
+      if (b_cta >= m.B) break;
+      engine_load(m, sm, b_cta);
     }
+    if (!per_spec || warp == 0) {
+      while (true) {
+        int b = b_cta;
+        if (!per_spec) {
+          if (lane == 0) b = atomicAdd(queue, 1);
+          b = __shfl_sync(0xffffffffu, b, 0);
+        }
+        if (b < 0 || b >= m.B) break;
+        run_spectrum(b);
+        b_cta = -1;
+      }
+      if (lane == 0) atomicSub((int*)n_active, 1);
+    }
+    do {
+      engine_eval<TOEP, ND>(m, sm, false, nullptr, nullptr, nullptr, 0, n_active, &snap);
+    } while (snap != 0);
+    if (!per_spec) break;
   }
 }
 

@@ -171,12 +171,15 @@ nuts_kernel(BdrtModel m, bdrt_nuts_opts o, const double* __restrict__ U0, double
     double acc_sum = 0.0;
     int n_div = 0, n_maxd = 0;
     for (int i = lane; i < D; i += 32) { v[V_WMEAN][i] = 0.0; v[V_WM2][i] = 0.0; }
-    if (!bad) {
-      init_stepsize();
-      da_mu = log(10.0 * eps);
-    }
+    bool need_stepsize = !bad;  // the heuristic runs before the first iteration and after every metric update
 
     for (int it = 0; it < n_iter && !bad; ++it) {
+      if (need_stepsize) {  // single call site (the engine is inlined into it)
+        init_stepsize();
+        da_mu = log(10.0 * eps);
+        need_stepsize = false;
+        if (bad) break;
+      }
       // ---------------------------------------------------------------- one NUTS transition from (SQ, SG, s_lp)
       unsigned udraw = 0;
       for (int i = lane; i < D; i += 32) {
@@ -324,8 +327,7 @@ nuts_kernel(BdrtModel m, bdrt_nuts_opts o, const double* __restrict__ U0, double
             }
             w_n = 0;
             __syncwarp();
-            init_stepsize();
-            da_mu = log(10.0 * eps);
+            need_stepsize = true;  // re-initialised from the current step size at the top of the next iteration
             da_count = 0;
             da_sbar = 0.0;
             da_xbar = 0.0;
@@ -355,51 +357,47 @@ nuts_kernel(BdrtModel m, bdrt_nuts_opts o, const double* __restrict__ U0, double
       if (accept_out) accept_out[wi] = o.samples > 0 ? acc_sum / o.samples : 0.0;
     }
   };
-  // drain: keep serving the cooperative matrix products until every slot of the CTA is out of work
-  auto drain = [&]() {
-    int snap;
-    if (lane == 0) atomicSub((int*)n_active, 1);
-    while (true) {
-      engine_eval<TOEP, ND>(m, sm, false, nullptr, nullptr, nullptr, 0, n_active, &snap);
-      if (snap == 0) break;
-    }
-  };
-
-  if (m.d[0].A_stride == 0) {
-    // shared grid: every warp pulls (spectrum, chain) items from the queue until it is empty
-    while (true) {
-      long long wi = 0;
-      if (lane == 0) wi = atomicAdd(queue, 1);
-      wi = __shfl_sync(0xffffffffu, wi, 0);
-      if (wi >= n_work) break;
-      run_chain(wi);
-    }
-    drain();
-  } else {
-    // per-spectrum grids: the 8 slots of a CTA share the resident operands, so a CTA takes one spectrum at a time and
-    // its slots run that spectrum's chains (chain = warp, warp + 8, ...)
-    __shared__ int s_spec;
-    while (true) {
+  // Work distribution.  Shared grid: every warp pulls (spectrum, chain) items from the queue until it is empty.
+  // Per-spectrum grids: the 8 slots of a CTA share the resident operands, so a CTA takes one spectrum at a time and
+  // its slots run that spectrum's chains (chain = warp, warp + 8, ...).  A warp that is out of work keeps serving
+  // engine_eval() until every slot of the CTA is done (single call site: the engine is inlined there).
+  const bool per_spec = m.d[0].A_stride != 0;
+  __shared__ int s_spec;
+  while (true) {
+    int b_cta = -1;
+    if (per_spec) {
       cta_sync();
       if (threadIdx.x == 0) {
         s_spec = atomicAdd(queue, 1);
         *n_active = o.chains < NWARP ? o.chains : NWARP;
       }
       cta_sync();
-      const int b = s_spec;
-      if (b >= m.B) break;
-      engine_load(m, sm, b);
-      if (warp < o.chains) {
-        for (int c = warp; c < o.chains; c += NWARP) run_chain((long long)b * o.chains + c);
-        drain();
-      } else {
-        int snap;
-        while (true) {
-          engine_eval<TOEP, ND>(m, sm, false, nullptr, nullptr, nullptr, 0, n_active, &snap);
-          if (snap == 0) break;
-        }
-      }
+      b_cta = s_spec;
+      if (b_cta >= m.B) break;
+      engine_load(m, sm, b_cta);
     }
+    if (!per_spec || warp < o.chains) {
+      int c = warp;
+      while (true) {
+        long long wi;
+        if (per_spec) {
+          wi = c < o.chains ? (long long)b_cta * o.chains + c : n_work;
+          c += NWARP;
+        } else {
+          wi = 0;
+          if (lane == 0) wi = atomicAdd(queue, 1);
+          wi = __shfl_sync(0xffffffffu, wi, 0);
+        }
+        if (wi >= n_work) break;
+        run_chain(wi);
+      }
+      if (lane == 0) atomicSub((int*)n_active, 1);
+    }
+    int snap;
+    do {
+      engine_eval<TOEP, ND>(m, sm, false, nullptr, nullptr, nullptr, 0, n_active, &snap);
+    } while (snap != 0);
+    if (!per_spec) break;
   }
 }
 

@@ -37,7 +37,7 @@ def parse():
     p.add_argument('--batch', type=int, default=12500, help='spectra per GPU per step')
     p.add_argument('--max-iter', type=int, default=50000)
     p.add_argument('--no-hmc', action='store_true')
-    p.add_argument('--hmc-batch', type=int, default=592)
+    p.add_argument('--hmc-batch', type=int, default=1184)
     p.add_argument('--cpu-sample', type=int, default=0, help='spectra in the CPU-baseline sample (0: 2 per core)')
     return p.parse_args()
 
