@@ -1,11 +1,21 @@
 #!/bin/bash
 # Build libbdrt.so in-tree for sm_100a (the only target).  Usage: build.sh [extra nvcc flags]
+# Every .cu is compiled in parallel (nvcc -c), then linked; ptxas statistics of all files end up in build.log.
 set -e
 cd "$(dirname "$0")"
 NVCC=${NVCC:-/usr/local/cuda/bin/nvcc}
-SRCS=$(ls *.cu)
 OUT=../libbdrt.so
-$NVCC -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -Xcompiler -fPIC -shared \
-  -Xptxas -v "$@" $SRCS -o $OUT 2> build.log || { cat build.log; exit 1; }
+FLAGS="-gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -Xcompiler -fPIC -Xptxas -v"
+mkdir -p build
+pids=()
+for f in *.cu; do
+  ( $NVCC $FLAGS "$@" -c "$f" -o "build/${f%.cu}.o" > "build/${f%.cu}.log" 2>&1 ) &
+  pids+=($!)
+done
+rc=0
+for p in "${pids[@]}"; do wait "$p" || rc=1; done
+cat build/*.log > build.log
+if [ $rc -ne 0 ]; then grep -E "error" -A3 build.log | head -60; exit 1; fi
+$NVCC -gencode arch=compute_100a,code=sm_100a -shared -Xcompiler -fPIC build/*.o -o $OUT
 grep -E "error|warning" build.log | grep -v "Wno" | head -20 || true
 echo "built $(realpath $OUT)"

@@ -32,6 +32,7 @@
 #define LBW (2 * MAXBW + 1)
 #define LOG_015 (-1.8971199848858813)  // log(0.15)
 #define MAXD 2                          // distributions per model
+#define FBW 6                           // stencil half-width of the register-tiled fast path (default epsilon: bw = 6)
 
 #define F_POS 1  // lower=0 coefficients of the series distribution (x = exp(u))
 #define F_OUT 2  // outlier error model (Series family only)
@@ -46,6 +47,7 @@ struct BdrtDist {
   long long A_stride;         // per-spectrum stride (0: shared)
   const double* Lb;           // [3][K][LBW] banded copies of the scaled L0, L1, L2
   double ascale;              // the resident operand is A * ascale (xp = xp_raw * xp_scale, Series-Parallel :52)
+  double tapc[3][2 * FBW + 1]; // Toeplitz taps of L0/L1/L2 for |d| <= FBW, read straight from the parameter bank
 };
 
 struct BdrtModel {
@@ -55,6 +57,7 @@ struct BdrtModel {
   int nfp;    // Nf rounded up to a multiple of 8
   int n2p;    // 2 * nfp
   int toepA;  // Toeplitz-resident operands
+  int fast;   // register-tiled per-slot phases: Toeplitz L with bw <= FBW and K <= 128 for every distribution
   int off_err, off_so;
   int bw;
   const double* freq;
@@ -64,8 +67,10 @@ struct BdrtModel {
   // shared-memory carve-up, in doubles
   int oXV, oZG, oSt, oOm, oUser;
   int xoff;  // offset of the data inside an X/V row (= bw: zero margin for the stencils)
-  int ws;    // stride of one stencil scratch vector (Kmax + 2 bw, zero margins)
-  int sd;    // per-slot, per-distribution scratch: W0 | W1 | W2 (ws each) | ups (Kmax) | 1/ups (Kmax)
+  int wm;    // zero margin on both sides of a stencil scratch vector: max(bw, FBW)
+  int ws;    // stride of one stencil scratch vector (Kmax + 2 wm, even)
+  int kup;   // Kmax rounded up to even
+  int sd;    // per-slot, per-distribution scratch: W0 | W1 | W2 (ws each) | ups (kup) | 1/ups (kup)
   int st;    // per-slot scratch size: ND * sd | scalars (16) | sigma_out raw, scale (2 Nf)
 };
 
@@ -81,7 +86,8 @@ static inline int bdrt_model_layout(BdrtModel* m) {
   m->N2 = 2 * m->Nf;
   m->nfp = (m->Nf + 7) / 8 * 8;
   m->n2p = 2 * m->nfp;
-  m->xoff = m->bw;
+  m->xoff = m->bw > FBW ? m->bw : FBW;  // even, so that 4-element windows of a row are 16-byte aligned
+  m->xoff += m->xoff & 1;
   m->Kmax = 0;
   int kx = 0, k8 = 0;
   for (int i = 0; i < m->ND; ++i) {
@@ -91,16 +97,21 @@ static inline int bdrt_model_layout(BdrtModel* m) {
     d.lt = m->nfp + d.kpad8;
     d.lda = bdrt_pad_stride(d.K);
     if (d.K > m->Kmax) m->Kmax = d.K;
-    const int k = d.kpad4 > d.K + m->bw ? d.kpad4 : d.K + m->bw;
+    int k = d.kpad4 > d.K + m->bw ? d.kpad4 : d.K + m->bw;
+    if (m->fast && k < 128 + FBW + 4) k = 128 + FBW + 4;  // the fast path addresses 4 x 32 entries + window
     if (k > kx) kx = k;
     if (d.kpad8 > k8) k8 = d.kpad8;
   }
   const int mx = kx > m->n2p ? kx : m->n2p;
   m->ldxv = bdrt_pad_stride(m->xoff + mx);
-  m->ws = m->Kmax + 2 * m->bw;
-  m->sd = 3 * m->ws + 2 * m->Kmax;
+  m->wm = m->bw > FBW ? m->bw : FBW;
+  m->ws = m->Kmax + 2 * m->wm;
+  m->ws += m->ws & 1;  // even
+  m->kup = (m->Kmax + 1) & ~1;
+  m->sd = 3 * m->ws + 2 * m->kup;
   m->st = m->ND * m->sd + 16 + ((m->flags & F_OUT) ? 2 * m->Nf : 0);
-  const int mz = k8 > m->n2p ? k8 : m->n2p;
+  int mz = k8 > m->n2p ? k8 : m->n2p;
+  if (m->fast && mz < 128) mz = 128;  // the fast path reads 4 x 32 gradient entries per row
   m->ldzg = mz + 4;  // % 8 == 4
   // unconstrained vector, Stan declaration order:
   //   Rinf_raw induc_raw | x_0 .. x_{ND-1} | sigma_res alpha_prop alpha_re alpha_im | [sigma_out_raw sigma_out_scale] |
@@ -138,6 +149,13 @@ __device__ __forceinline__ void cta_sync() {
   __syncwarp();
   asm volatile("bar.sync 0;" ::: "memory");
 }
+
+__device__ __forceinline__ void ld2(const double* p, double& a, double& b) {  // 16-byte aligned shared-memory pair
+  const double2 v = *reinterpret_cast<const double2*>(p);
+  a = v.x;
+  b = v.y;
+}
+__device__ __forceinline__ void st2(double* p, double a, double b) { *reinterpret_cast<double2*>(p) = make_double2(a, b); }
 
 // Is coordinate i of the unconstrained vector a lower=0 parameter (theta = exp(u))?
 __device__ __forceinline__ bool bdrt_is_exp(const BdrtModel& m, int i) {
@@ -191,7 +209,7 @@ __device__ inline void engine_load(const BdrtModel& m, double* sm, long long spe
 //   nact/snap: optional CTA-wide "slots still working" counter; *snap receives its value at a point where no warp can
 //           be modifying it (between the first and last barrier), so every warp of the CTA reads the same value.
 // Returns lp (non-finite lp or gradient entries must be checked by the caller).
-template <int TOEP, int ND>
+template <int TOEP, int ND, int FAST>
 __device__ inline double engine_eval(const BdrtModel& m, double* sm, bool active, const double* u, double* grad,
                                      const double* Zs, int jacobian, const volatile int* nact = nullptr,
                                      int* snap = nullptr) {
@@ -210,6 +228,7 @@ __device__ inline double engine_eval(const BdrtModel& m, double* sm, bool active
 
   double lp = 0.0;
   double xsum = 0.0;  // sum(xs) + sum(xp_raw)  (Series-Parallel :56)
+  double gpr[ND][4];  // fast path: the prior part of d lp / d x of the lane's 4 coefficients, kept until phase 5
   // ---------------------------------------------------------------- phase 1: transforms, priors, stencils (per slot)
   if (active) {
     double ujac = 0.0;
@@ -227,20 +246,143 @@ __device__ inline double engine_eval(const BdrtModel& m, double* sm, bool active
         sSo[i] = exp(ui);
       }
     }
+    if (FAST) {
+      // Register-tiled per-slot phase (Toeplitz L with |d| <= FBW, K <= 128): lane owns the 4 consecutive coefficients
+      // kq .. kq+3, stencil windows are fetched as 16-byte pairs, the taps come straight from the parameter bank.
+      const int kq = 4 * lane;
+#pragma unroll
+      for (int dd = 0; dd < ND; ++dd) {
+        const BdrtDist& Dd = m.d[dd];
+        const int K = Dd.K;
+        double* sX = rowX(dd);
+        double* sW = sSt + dd * m.sd + m.wm;
+        double* sUps = sSt + dd * m.sd + 3 * m.ws;
+        double* sIu = sUps + m.kup;
+        double uu[4], ups[4], iu[4], xr[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int k = kq + j;
+          const bool v = k < K;
+          const double ux = v ? u[Dd.off_x + k] : 0.0;
+          uu[j] = v ? u[Dd.off_ups + k] : 0.0;
+          double xv = Dd.pos ? exp(ux) : ux;
+          xv = v ? xv : 0.0;
+          xr[j] = xv;
+          ups[j] = 0.15 * exp(uu[j]);
+          iu[j] = __drcp_rn(ups[j]);
+          ujac += uu[j] + (Dd.pos ? ux : 0.0);
+          if (ND > 1) xsum += xv;
+          if (v) {
+            sUps[k] = ups[j];
+            sIu[k] = iu[j];
+          }
+        }
+        st2(sX + kq, xr[0], xr[1]);  // x row [0, 128): zeros past K (phase 3 of the previous call wrote V here)
+        st2(sX + kq + 2, xr[2], xr[3]);
+        if (lane < FBW + 2) sX[128 + lane] = 0.0;
+        __syncwarp();
+        // 1b. a_j = L_j x, q^2, hyper-priors, d lp / d ups, W_j = d_j a_j / ups^2
+        const double d0 = sTh[6 + 3 * dd], d1 = sTh[7 + 3 * dd], d2 = sTh[8 + 3 * dd];
+        double sa0 = 0, sa1 = 0, sa2 = 0;
+        {
+          double xw[16];  // x[kq - 6 .. kq + 9]
+#pragma unroll
+          for (int i = 0; i < 8; ++i) ld2(sX + kq - FBW + 2 * i, xw[2 * i], xw[2 * i + 1]);
+          double a0[4] = {0, 0, 0, 0}, a1[4] = {0, 0, 0, 0}, a2[4] = {0, 0, 0, 0};
+#pragma unroll
+          for (int t = 0; t < 2 * FBW + 1; ++t) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              a0[j] = fma(Dd.tapc[0][t], xw[j + t], a0[j]);
+              a1[j] = fma(Dd.tapc[1][t], xw[j + t], a1[j]);
+              a2[j] = fma(Dd.tapc[2][t], xw[j + t], a2[j]);
+            }
+          }
+          double upw[8], iuw[8];  // ups / (1/ups) [kq - 2 .. kq + 5]
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            ld2(sUps + kq - 2 + 2 * i, upw[2 * i], upw[2 * i + 1]);
+            ld2(sIu + kq - 2 + 2 * i, iuw[2 * i], iuw[2 * i + 1]);
+          }
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const int k = kq + j;
+            if (k < K) {
+              const double upk = ups[j], iuk = iu[j], iu2 = iuk * iuk, uk = uu[j];
+              const double q2 = d0 * a0[j] * a0[j] + d1 * a1[j] * a1[j] + d2 * a2[j] * a2[j];
+              lp += -0.5 * q2 * iu2 - (LOG_015 + uk) - (m.ups_alpha + 1.0) * uk - m.ups_beta * 0.15 * iuk;
+              sa0 = fma(a0[j] * a0[j], iu2, sa0);
+              sa1 = fma(a1[j] * a1[j], iu2, sa1);
+              sa2 = fma(a2[j] * a2[j], iu2, sa2);
+              sW[k] = d0 * a0[j] * iu2;
+              sW[m.ws + k] = d1 * a1[j] * iu2;
+              sW[2 * m.ws + k] = d2 * a2[j] * iu2;
+              // dups_i = 0.5 - 0.25 (ups_i + ups_{i+2}) / ups_{i+1}  (Series_modelcode.txt:51-53); window index j + 2 + e
+              double gu = q2 * iu2 * iuk - iuk;
+              if (k + 2 < K) {
+                const double e = 0.5 - 0.25 * (upk + upw[j + 4]) * iuw[j + 3];
+                gu += e * 0.25 * iuw[j + 3];
+                lp += -0.5 * e * e;
+              }
+              if (k >= 1 && k + 1 < K) {
+                const double sum = upw[j + 1] + upw[j + 3];
+                const double e = 0.5 - 0.25 * sum * iuk;
+                gu -= e * 0.25 * sum * iu2;
+              }
+              if (k >= 2) {
+                const double e = 0.5 - 0.25 * (upw[j] + upk) * iuw[j + 1];
+                gu += e * 0.25 * iuw[j + 1];
+              }
+              grad[Dd.off_ups + k] = gu * upk - (m.ups_alpha + 1.0) + m.ups_beta * 0.15 * iuk + jac;
+            }
+          }
+        }
+        __syncwarp();
+        // 1c. prior part of d lp / d x:  - sum_j L_j^T W_j  (kept in registers until phase 5)
+        {
+          double acc[4] = {0, 0, 0, 0};
+          if (kq < K) {
+#pragma unroll
+            for (int q = 0; q < 3; ++q) {
+              double ww[16];  // W_q[kq - 6 .. kq + 9]
+#pragma unroll
+              for (int i = 0; i < 8; ++i) ld2(sW + q * m.ws + kq - FBW + 2 * i, ww[2 * i], ww[2 * i + 1]);
+#pragma unroll
+              for (int t = 0; t < 2 * FBW + 1; ++t) {  // row n = k + d, column k -> tap_q[-d]
+#pragma unroll
+                for (int j = 0; j < 4; ++j) acc[j] = fma(Dd.tapc[q][2 * FBW - t], ww[j + t], acc[j]);
+              }
+            }
+          }
+#pragma unroll
+          for (int j = 0; j < 4; ++j) gpr[dd][j] = -acc[j];
+        }
+        sa0 = warp_sum(sa0);
+        sa1 = warp_sum(sa1);
+        sa2 = warp_sum(sa2);
+        if (lane == 0) {
+          // d_j ~ inv_gamma(5, 5): -6 log d - 5/d
+          lp += -6.0 * (u[Dd.off_d] + u[Dd.off_d + 1] + u[Dd.off_d + 2]) - 5.0 / d0 - 5.0 / d1 - 5.0 / d2;
+          grad[Dd.off_d] = -0.5 * sa0 * d0 - 6.0 + 5.0 / d0 + jac;
+          grad[Dd.off_d + 1] = -0.5 * sa1 * d1 - 6.0 + 5.0 / d1 + jac;
+          grad[Dd.off_d + 2] = -0.5 * sa2 * d2 - 6.0 + 5.0 / d2 + jac;
+        }
+      }
+    } else {
 #pragma unroll
     for (int dd = 0; dd < ND; ++dd) {
       const BdrtDist& Dd = m.d[dd];
       const int K = Dd.K;
       double* sX = rowX(dd);
       double* sUps = sSt + dd * m.sd + 3 * m.ws;
-      double* sIu = sUps + m.Kmax;
+      double* sIu = sUps + m.kup;
       for (int k = lane; k < K; k += 32) {
         const double ux = u[Dd.off_x + k], uu = u[Dd.off_ups + k];
         const double xv = Dd.pos ? exp(ux) : ux;
         const double ups = 0.15 * exp(uu);
         sX[k] = xv;
         sUps[k] = ups;
-        sIu[k] = 1.0 / ups;
+        sIu[k] = __drcp_rn(ups);
         ujac += uu + (Dd.pos ? ux : 0.0);
         if (ND > 1) xsum += xv;
       }
@@ -254,9 +396,9 @@ __device__ inline double engine_eval(const BdrtModel& m, double* sm, bool active
       const BdrtDist& Dd = m.d[dd];
       const int K = Dd.K;
       const double* sX = rowX(dd);
-      double* sW = sSt + dd * m.sd + bw;  // W_j[k] at sW[j * ws + k], zero margins
+      double* sW = sSt + dd * m.sd + m.wm;  // W_j[k] at sW[j * ws + k], zero margins
       const double* sUps = sSt + dd * m.sd + 3 * m.ws;
-      const double* sIu = sUps + m.Kmax;
+      const double* sIu = sUps + m.kup;
       const double* sTap = sm + Dd.oTap + MAXBW;  // tap_j[d] at sTap[j * LBW + d]
       const double d0 = sTh[6 + 3 * dd], d1 = sTh[7 + 3 * dd], d2 = sTh[8 + 3 * dd];
       double sa0 = 0, sa1 = 0, sa2 = 0;
@@ -377,6 +519,7 @@ __device__ inline double engine_eval(const BdrtModel& m, double* sm, bool active
         grad[Dd.off_d + 2] = -0.5 * sa2 * d2 - 6.0 + 5.0 / d2 + jac;
       }
     }
+    }
     if (lane == 0) {  // half-normal priors on the six scalar raw parameters
       double ss = 0.0;
 #pragma unroll
@@ -460,7 +603,13 @@ __device__ inline double engine_eval(const BdrtModel& m, double* sm, bool active
     const double base = m.sigma_min2 + sr * sr;
     const double ap2 = ap * ap, are2 = are * are, aim2 = aim * aim;
     double Sv = 0, Swv = 0, Sg = 0, Sgz = 0, SGre = 0, SGim = 0;
-    for (int n = lane; n < Nf; n += 32) {
+    // three independent frequencies per lane and pass (instruction-level parallelism: the body is a long chain of
+    // reciprocals / a logarithm)
+    for (int nb = 0; nb < Nf; nb += 96) {
+#pragma unroll
+     for (int jn = 0; jn < 3; ++jn) {
+      const int n = nb + lane + 32 * jn;
+      if (n >= Nf) continue;
       const double om = sOm[n];
       double zre = sZ[n] + Rinf, zim = sZ[nfp + n] + induc * om;
       double Yr = 0, Yi = 0, iM = 0;
@@ -469,7 +618,7 @@ __device__ inline double engine_eval(const BdrtModel& m, double* sm, bool active
         const double* sY = rowZ(ND - 1);
         Yr = sY[n];
         Yi = sY[nfp + n];
-        iM = 1.0 / (Yr * Yr + Yi * Yi);
+        iM = __drcp_rn(Yr * Yr + Yi * Yi);
         zre += Yr * iM;
         zim -= Yi * iM;
       }
@@ -484,7 +633,7 @@ __device__ inline double engine_eval(const BdrtModel& m, double* sm, bool active
         lp += -m.so_lambda * so_raw - (m.so_alpha + 1.0) * u[m.off_so + Nf + n] - m.so_beta / so_scale;
       }
       const double s_re = base + ap2 * zre * zre + common, s_im = base + ap2 * zim * zim + common;
-      const double i_re = 1.0 / s_re, i_im = 1.0 / s_im;
+      const double i_re = __drcp_rn(s_re), i_im = __drcp_rn(s_im);
       const double r_re = Zs[n] - zre, r_im = Zs[Nf + n] - zim;
       lp += -0.5 * (r_re * r_re * i_re + r_im * r_im * i_im) - 0.5 * log(s_re * s_im);
       const double g_re = 0.5 * r_re * r_re * i_re * i_re - 0.5 * i_re;
@@ -511,6 +660,7 @@ __device__ inline double engine_eval(const BdrtModel& m, double* sm, bool active
         grad[m.off_so + n] = dso - m.so_lambda * so_raw + jac;
         grad[m.off_so + Nf + n] = dso - (m.so_alpha + 1.0) + m.so_beta / so_scale + jac;
       }
+     }
     }
 #pragma unroll
     for (int dd = 0; dd < ND; ++dd) {
@@ -603,6 +753,21 @@ __device__ inline double engine_eval(const BdrtModel& m, double* sm, bool active
     for (int dd = 0; dd < ND; ++dd) {
       const BdrtDist& Dd = m.d[dd];
       const double* sG = rowZ(dd);
+      if (FAST) {
+        const int kq = 4 * lane;
+        double g4[4];
+        ld2(sG + kq, g4[0], g4[1]);
+        ld2(sG + kq + 2, g4[2], g4[3]);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          if (kq + j < Dd.K) {
+            double gx = g4[j] + gpr[dd][j] - gsum;
+            if (Dd.pos) gx = gx * exp(u[Dd.off_x + kq + j]) + jac;
+            grad[Dd.off_x + kq + j] = gx;
+          }
+        }
+        continue;
+      }
       for (int k = lane; k < Dd.K; k += 32) {
         double gx = sG[k] + grad[Dd.off_x + k] - gsum;
         if (Dd.pos) gx = gx * exp(u[Dd.off_x + k]) + jac;
@@ -646,18 +811,22 @@ static inline BdrtPlan bdrt_plan(const bdrt_ctx* ctx, const BdrtModel& m, int Dp
   return pl;
 }
 
-// launch KERNEL<TOEP, ND>: Toeplitz- or dense-resident operands, one (Series) or two (Series-Parallel) distributions
-#define BDRT_LAUNCH_ONE(ctx, KERNEL, T, N, grid, smem, ...)                                                       \
-  do {                                                                                                            \
-    BDRT_CUDA(ctx, cudaFuncSetAttribute(KERNEL<T, N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(smem))); \
-    KERNEL<T, N><<<grid, NTHREADS, smem, (ctx)->stream>>>(__VA_ARGS__);                                           \
+// launch KERNEL<TOEP, ND, FAST>: Toeplitz- or dense-resident operands, one (Series) or two (Series-Parallel)
+// distributions, register-tiled or generic per-slot phases (FAST only exists with TOEP)
+#define BDRT_LAUNCH_ONE(ctx, KERNEL, T, N, F, grid, smem, ...)                                                       \
+  do {                                                                                                               \
+    BDRT_CUDA(ctx, cudaFuncSetAttribute(KERNEL<T, N, F>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(smem))); \
+    KERNEL<T, N, F><<<grid, NTHREADS, smem, (ctx)->stream>>>(__VA_ARGS__);                                           \
   } while (0)
-#define BDRT_LAUNCH(ctx, m, KERNEL, grid, smem, ...)                                  \
-  do {                                                                                \
-    if ((m).toepA && (m).ND == 1) BDRT_LAUNCH_ONE(ctx, KERNEL, 1, 1, grid, smem, __VA_ARGS__);      \
-    else if ((m).toepA) BDRT_LAUNCH_ONE(ctx, KERNEL, 1, 2, grid, smem, __VA_ARGS__);  \
-    else if ((m).ND == 1) BDRT_LAUNCH_ONE(ctx, KERNEL, 0, 1, grid, smem, __VA_ARGS__); \
-    else BDRT_LAUNCH_ONE(ctx, KERNEL, 0, 2, grid, smem, __VA_ARGS__);                 \
-    (ctx)->launches++;                                                                \
-    BDRT_CUDA(ctx, cudaGetLastError());                                               \
+#define BDRT_LAUNCH(ctx, m, KERNEL, grid, smem, ...)                                                   \
+  do {                                                                                                 \
+    const int t_ = (m).toepA, f_ = (m).toepA && (m).fast;                                              \
+    if (f_ && (m).ND == 1) BDRT_LAUNCH_ONE(ctx, KERNEL, 1, 1, 1, grid, smem, __VA_ARGS__);             \
+    else if (f_) BDRT_LAUNCH_ONE(ctx, KERNEL, 1, 2, 1, grid, smem, __VA_ARGS__);                       \
+    else if (t_ && (m).ND == 1) BDRT_LAUNCH_ONE(ctx, KERNEL, 1, 1, 0, grid, smem, __VA_ARGS__);        \
+    else if (t_) BDRT_LAUNCH_ONE(ctx, KERNEL, 1, 2, 0, grid, smem, __VA_ARGS__);                       \
+    else if ((m).ND == 1) BDRT_LAUNCH_ONE(ctx, KERNEL, 0, 1, 0, grid, smem, __VA_ARGS__);              \
+    else BDRT_LAUNCH_ONE(ctx, KERNEL, 0, 2, 0, grid, smem, __VA_ARGS__);                               \
+    (ctx)->launches++;                                                                                 \
+    BDRT_CUDA(ctx, cudaGetLastError());                                                                \
   } while (0)

@@ -217,6 +217,22 @@ int bdrt_model_prepare(bdrt_ctx* ctx, const bdrt_series_data* d, BdrtModel* m, s
   m->bw = bw;
   for (int i = 0; i < nd; ++i) m->d[i].toepL = hinfo[4 * i + 1] && (Ks[i] >= 2 * bw + 1);
   m->toepA = hinfo[2];
+  // register-tiled per-slot phases: every distribution has Toeplitz L within FBW off-diagonals and K <= 128
+  // (BDRT_FORCE_GENERIC=1 keeps the generic per-slot code, for tests)
+  const char* fg = getenv("BDRT_FORCE_GENERIC");
+  m->fast = m->toepA && bw <= FBW && !(fg && fg[0] == '1');
+  for (int i = 0; i < nd; ++i) m->fast = m->fast && m->d[i].toepL && Ks[i] <= 128 && Ks[i] >= 2 * FBW + 1;
+  if (m->fast) {  // taps = row K/2 of the banded copies, into the kernel parameter bank
+    for (int i = 0; i < nd; ++i) {
+      double row[3][LBW];
+      for (int j = 0; j < 3; ++j)
+        BDRT_CUDA(ctx, cudaMemcpyAsync(row[j], m->d[i].Lb + ((size_t)j * Ks[i] + Ks[i] / 2) * LBW, LBW * sizeof(double),
+                                       cudaMemcpyDeviceToHost, ctx->stream));
+      BDRT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+      for (int j = 0; j < 3; ++j)
+        for (int t = 0; t < 2 * FBW + 1; ++t) m->d[i].tapc[j][t] = row[j][MAXBW - FBW + t];
+    }
+  }
   const int eng = bdrt_model_layout(m);
   if ((size_t)eng * 8 > (size_t)ctx->smem_optin)
     BDRT_FAIL(ctx, BDRT_E_SMEM, "problem needs %zu B of shared memory per CTA, device offers %d%s", (size_t)eng * 8,
@@ -229,11 +245,11 @@ int bdrt_model_prepare(bdrt_ctx* ctx, const bdrt_series_data* d, BdrtModel* m, s
 // ---------------------------------------------------------------------------------------------------------------------
 // log_prob + gradient test hook
 // ---------------------------------------------------------------------------------------------------------------------
-template <int TOEP, int ND>
+template <int TOEP, int ND, int FAST>
 __global__ void __launch_bounds__(NTHREADS, TOEP ? 2 : 1)
 logpost_kernel(BdrtModel m, const double* u, const int* spec, int n_cols, int jacobian, double* lp, double* grad,
                int cta_per_spec) {
-  extern __shared__ double sm[];
+  extern __shared__ __align__(16) double sm[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (!cta_per_spec) {
     engine_load(m, sm, 0);
@@ -242,7 +258,7 @@ logpost_kernel(BdrtModel m, const double* u, const int* spec, int n_cols, int ja
       const int c = gidx * NSLOT + warp;
       const bool active = c < n_cols;
       const int b = active ? (spec ? spec[c] : c % m.B) : 0;
-      const double v = engine_eval<TOEP, ND>(m, sm, active, u + (long long)c * m.D, grad + (long long)c * m.D,
+      const double v = engine_eval<TOEP, ND, FAST>(m, sm, active, u + (long long)c * m.D, grad + (long long)c * m.D,
                                    m.Z + (long long)b * m.N2, jacobian);
       if (active && lane == 0) lp[c] = v;
     }
@@ -267,7 +283,7 @@ logpost_kernel(BdrtModel m, const double* u, const int* spec, int n_cols, int ja
         c = nf ? found[nf - 1] : c;
         const bool active = warp < nf;
         const int col = active ? found[warp] : 0;
-        const double v = engine_eval<TOEP, ND>(m, sm, active, u + (long long)col * m.D, grad + (long long)col * m.D,
+        const double v = engine_eval<TOEP, ND, FAST>(m, sm, active, u + (long long)col * m.D, grad + (long long)col * m.D,
                                      m.Z + (long long)b * m.N2, jacobian);
         if (active && lane == 0) lp[col] = v;
       }

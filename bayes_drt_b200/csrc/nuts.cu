@@ -56,12 +56,12 @@ __device__ __forceinline__ double logaddexp(double a, double b) {
 
 }  // namespace
 
-template <int TOEP, int ND>
+template <int TOEP, int ND, int FAST>
 __global__ void __launch_bounds__(NTHREADS, TOEP ? 2 : 1)
 nuts_kernel(BdrtModel m, bdrt_nuts_opts o, const double* __restrict__ U0, double* draws, double* stepsize_out,
             long long* nleap_out, int* ndiv_out, int* nmax_out, double* accept_out, int* queue, double* gvec,
             double* ckpt, int nvec_smem, int Dpad) {
-  extern __shared__ double sm[];
+  extern __shared__ __align__(16) double sm[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int D = m.D;
   volatile int* n_active = (volatile int*)(sm + m.oUser);
@@ -92,7 +92,7 @@ nuts_kernel(BdrtModel m, bdrt_nuts_opts o, const double* __restrict__ U0, double
       q[i] = fma(eps * mi[i], pi, q[i]);
     }
     __syncwarp();
-    const double lp = engine_eval<TOEP, ND>(m, sm, true, q, g, Zs, 1);
+    const double lp = engine_eval<TOEP, ND, FAST>(m, sm, true, q, g, Zs, 1);
     ++n_grad;
     for (int i = lane; i < D; i += 32) p[i] = fma(0.5 * eps, g[i], p[i]);
     __syncwarp();
@@ -123,7 +123,7 @@ nuts_kernel(BdrtModel m, bdrt_nuts_opts o, const double* __restrict__ U0, double
     vcopy(v[V_SQ], U0 + wi * D);
     for (int i = lane; i < D; i += 32) v[V_MINV][i] = 1.0;
     __syncwarp();
-    double s_lp = engine_eval<TOEP, ND>(m, sm, true, v[V_SQ], v[V_SG], Zs, 1);
+    double s_lp = engine_eval<TOEP, ND, FAST>(m, sm, true, v[V_SQ], v[V_SG], Zs, 1);
     ++n_grad;
     bool bad = !isfinite(s_lp);
 
@@ -395,7 +395,7 @@ nuts_kernel(BdrtModel m, bdrt_nuts_opts o, const double* __restrict__ U0, double
     }
     int snap;
     do {
-      engine_eval<TOEP, ND>(m, sm, false, nullptr, nullptr, nullptr, 0, n_active, &snap);
+      engine_eval<TOEP, ND, FAST>(m, sm, false, nullptr, nullptr, nullptr, 0, n_active, &snap);
     } while (snap != 0);
     if (!per_spec) break;
   }

@@ -17,12 +17,15 @@ def golden_dir():
     return os.path.join(ROOT, 'tests', 'golden')
 
 
-@pytest.fixture(params=['toeplitz', 'dense'])
+@pytest.fixture(params=['toeplitz', 'toeplitz-generic', 'dense'])
 def resident_A(request, monkeypatch):
-    """Run a GPU test on both resident-operand layouts of the engine: the Toeplitz tables (picked automatically for
-    shared log-uniform grids, two CTAs per SM) and the dense A (forced with BDRT_FORCE_DENSE=1)."""
+    """Run a GPU test on every code path of the engine: the Toeplitz tables (picked automatically for shared log-uniform
+    grids, two CTAs per SM) with the register-tiled per-slot phases, the same with the generic per-slot phases
+    (BDRT_FORCE_GENERIC=1), and the dense-resident A (BDRT_FORCE_DENSE=1)."""
+    monkeypatch.delenv('BDRT_FORCE_DENSE', raising=False)
+    monkeypatch.delenv('BDRT_FORCE_GENERIC', raising=False)
     if request.param == 'dense':
         monkeypatch.setenv('BDRT_FORCE_DENSE', '1')
-    else:
-        monkeypatch.delenv('BDRT_FORCE_DENSE', raising=False)
+    elif request.param == 'toeplitz-generic':
+        monkeypatch.setenv('BDRT_FORCE_GENERIC', '1')
     return request.param

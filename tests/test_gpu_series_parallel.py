@@ -22,7 +22,7 @@ def _data(mode, nonneg, Nf=81, Ks=81, Kp=81, nspec=3):
 @pytest.mark.parametrize('mode', ['optimize', 'sample'])
 def test_sp_logpost_matches_oracle(nonneg, mode, resident_A):
     # two dense 162 x 81 matrices do not fit one SM's shared memory: the dense layout is exercised on a smaller shape
-    Nf, Ks, Kp = (81, 81, 81) if resident_A == 'toeplitz' else (49, 45, 41)
+    Nf, Ks, Kp = (81, 81, 81) if resident_A != 'dense' else (49, 45, 41)
     ds = _data(mode, nonneg, Nf=Nf, Ks=Ks, Kp=Kp)
     prob = gpu_problem_sp(ds)
     assert prob.D == osp.n_params(ds[0]) == 2 * (Ks + Kp) + 12
@@ -53,7 +53,7 @@ def test_sp_dense_too_large_fails_loudly(monkeypatch):
 
 
 def test_sp_constrain_and_map(resident_A):
-    Nf, Ks, Kp = (81, 81, 81) if resident_A == 'toeplitz' else (49, 45, 41)
+    Nf, Ks, Kp = (81, 81, 81) if resident_A != 'dense' else (49, 45, 41)
     ds = _data('optimize', True, Nf=Nf, Ks=Ks, Kp=Kp, nspec=2)
     prob = gpu_problem_sp(ds)
     rng = np.random.RandomState(1)
