@@ -59,7 +59,7 @@ __device__ __forceinline__ void two_loop(const double* S, const double* Y, const
     for (int i = lane; i < D; i += 32) pk[i] = -gk[i];
     __syncwarp();
     for (int j = 0; j < nh; ++j) {  // newest -> oldest
-      const int h = (head - 1 - j + 2 * H) % H;
+      const int h = head - 1 - j + (head - 1 - j < 0 ? H : 0);  // j < nh <= H
       const double* Sh = S + (long long)h * Dpad;
       const double* Yh = Y + (long long)h * Dpad;
       const double a = rho[h] * vdot(Sh, pk, D, lane);
@@ -70,7 +70,7 @@ __device__ __forceinline__ void two_loop(const double* S, const double* Y, const
     for (int i = lane; i < D; i += 32) pk[i] *= gamma;
     __syncwarp();
     for (int j = nh - 1; j >= 0; --j) {  // oldest -> newest
-      const int h = (head - 1 - j + 2 * H) % H;
+      const int h = head - 1 - j + (head - 1 - j < 0 ? H : 0);  // j < nh <= H
       const double* Sh = S + (long long)h * Dpad;
       const double* Yh = Y + (long long)h * Dpad;
       const double beta = rho[h] * vdot(Yh, pk, D, lane);
@@ -87,17 +87,22 @@ __device__ __forceinline__ void two_loop(const double* S, const double* Y, const
     const int i = lane + 32 * c;
     pr[c] = (i < D) ? -gk[i] : 0.0;
   }
-  for (int j = 0; j < nh; ++j) {  // newest -> oldest
-    const int h = (head - 1 - j + 2 * H) % H;
+  // history entry -> registers (both vectors of the entry in one go: one L2 round trip)
+  auto fetch = [&](int h, double (&sv)[NCC], double (&yv)[NCC]) {
     const double* Sh = S + (long long)h * Dpad;
     const double* Yh = Y + (long long)h * Dpad;
-    double sv[NCC], yv[NCC];
 #pragma unroll
     for (int c = 0; c < NCC; ++c) {
       const int i = lane + 32 * c;
       sv[c] = (i < D) ? Sh[i] : 0.0;
       yv[c] = (i < D) ? Yh[i] : 0.0;
     }
+  };
+  auto hidx = [&](int j) { return head - 1 - j + (head - 1 - j < 0 ? H : 0); };  // j < nh <= H
+  // (prefetching the next entry into a second register buffer was measured slower: it spills under the 128-register
+  // cap of the two-CTAs-per-SM kernels, 52.9 M vs 70.6 M gradients/s)
+  double sa[NCC], ya[NCC];
+  auto first = [&](int h, const double (&sv)[NCC], const double (&yv)[NCC]) {  // newest -> oldest
     double d = 0.0;
 #pragma unroll
     for (int c = 0; c < NCC; ++c) d = fma(sv[c], pr[c], d);
@@ -105,26 +110,26 @@ __device__ __forceinline__ void two_loop(const double* S, const double* Y, const
     al[h] = a;
 #pragma unroll
     for (int c = 0; c < NCC; ++c) pr[c] = fma(-a, yv[c], pr[c]);
-  }
-#pragma unroll
-  for (int c = 0; c < NCC; ++c) pr[c] *= gamma;
-  for (int j = nh - 1; j >= 0; --j) {  // oldest -> newest
-    const int h = (head - 1 - j + 2 * H) % H;
-    const double* Sh = S + (long long)h * Dpad;
-    const double* Yh = Y + (long long)h * Dpad;
-    double sv[NCC], yv[NCC];
-#pragma unroll
-    for (int c = 0; c < NCC; ++c) {
-      const int i = lane + 32 * c;
-      sv[c] = (i < D) ? Sh[i] : 0.0;
-      yv[c] = (i < D) ? Yh[i] : 0.0;
-    }
+  };
+  auto second = [&](int h, const double (&sv)[NCC], const double (&yv)[NCC]) {  // oldest -> newest
     double d = 0.0;
 #pragma unroll
     for (int c = 0; c < NCC; ++c) d = fma(yv[c], pr[c], d);
     const double cc = al[h] - rho[h] * warp_sum(d);
 #pragma unroll
     for (int c = 0; c < NCC; ++c) pr[c] = fma(cc, sv[c], pr[c]);
+  };
+  {
+    for (int j = 0; j < nh; ++j) {
+      fetch(hidx(j), sa, ya);
+      first(hidx(j), sa, ya);
+    }
+#pragma unroll
+    for (int c = 0; c < NCC; ++c) pr[c] *= gamma;
+    for (int j = nh - 1; j >= 0; --j) {
+      fetch(hidx(j), sa, ya);
+      second(hidx(j), sa, ya);
+    }
   }
 #pragma unroll
   for (int c = 0; c < NCC; ++c) {
@@ -211,6 +216,7 @@ lbfgs_kernel(BdrtModel m, bdrt_lbfgs_opts o, double* __restrict__ U, double* lp_
       int nh = 0, head = 0;  // history: entries head-nh .. head-1 (mod H), newest = head-1
       double rho[MAXHIST], al[MAXHIST];
       double gamma = 1.0, alpha = o.init_alpha;
+      double gp_prev = 0.0;  // g.p of the accepted point = the next line search's initial slope
       double fk_1 = 0.0, dfp_old = 0.0, dfp_new = 0.0;
 
       while (code == BDRT_TERM_RUNNING) {
@@ -228,7 +234,8 @@ lbfgs_kernel(BdrtModel m, bdrt_lbfgs_opts o, double* __restrict__ U, double* lp_
           else
             alpha = o.init_alpha;
           // ---------------- WolfeLineSearch (c1 = 1e-4, c2 = 0.9, minAlpha = 1e-12, <= 20 its, <= 10 restarts)
-          const double dfp = vdot(gk, pk, D, lane);
+          // same vectors, same summation order as the convergence test of the previous iteration: reuse its value
+          const double dfp = (it > 1 && !reset) ? gp_prev : vdot(gk, pk, D, lane);
           const double c1dfp = 1e-4 * dfp, c2dfp = 0.9 * dfp;
           double alpha0 = 1e-12, prevF = fk, prevDFp = dfp;
           int nits = 0, restarts = 0, ret = -1;  // ret: 0 ok, 1 fail
@@ -341,7 +348,7 @@ lbfgs_kernel(BdrtModel m, bdrt_lbfgs_opts o, double* __restrict__ U, double* lp_
         }
         gamma = skyk / yy;
         rho[head] = 1.0 / skyk;
-        head = (head + 1) % H;
+        head = head + 1 == H ? 0 : head + 1;
         if (nh < H) ++nh;
         fk_1 = fk;
         fk = f1;
@@ -357,6 +364,7 @@ lbfgs_kernel(BdrtModel m, bdrt_lbfgs_opts o, double* __restrict__ U, double* lp_
         // ---------------- convergence tests, Stan's order
         const double df = fabs(fk_1 - fk);
         const double gp = vdot(gn, pk, D, lane);
+        gp_prev = gp;
         if (df < o.tol_obj)
           code = BDRT_TERM_ABSF;
         else if (df < o.tol_rel_obj * fmax(fabs(fk_1), fmax(fabs(fk), 1.0)) * EPS)
