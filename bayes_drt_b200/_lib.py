@@ -24,7 +24,7 @@ KERNEL = {'DRT': 0, 'DDT': 1}
 DIST = {'series': 0, 'parallel': 1}
 SYM = {'planar': 0, 'spherical': 1}
 BC = {'transmissive': 0, 'blocking': 1}
-MODEL_SERIES, MODEL_SERIES_PARALLEL, MODEL_POS, MODEL_OUTLIERS = 0, 1, 16, 32
+MODEL_SERIES, MODEL_SERIES_PARALLEL, MODEL_PARALLEL, MODEL_POS, MODEL_OUTLIERS = 0, 1, 2, 16, 32
 
 TERM_NAMES = {0: 'running', 10: 'absx', 20: 'absf', 21: 'relf', 30: 'absgrad', 31: 'relgrad', 40: 'maxit',
               -1: 'lsfail', -2: 'badinit'}

@@ -69,9 +69,10 @@ class SeriesProblem:
 
     def __init__(self, A, Z, freq, L, nonneg=False, outliers=False, sigma_min=0.002, ups_alpha=0.05, ups_beta=0.1,
                  induc_scale=1.0, sigma_out_lambda=10.0, sigma_out_alpha=2.0, sigma_out_beta=1.0, device=None,
-                 Ap=None, Lp=None, x_sum_invscale=0.0, xp_scale=1.0):
+                 Ap=None, Lp=None, x_sum_invscale=0.0, xp_scale=1.0, parallel=False):
         """Series family: A, L describe the single DRT.  Series-Parallel (pass Ap, Lp): A, L describe the series
-        distribution, Ap [2Nf, Kp] / Lp [3, Kp, Kp] the parallel one (Stan data of inversion.py:1886-1959)."""
+        distribution, Ap [2Nf, Kp] / Lp [3, Kp, Kp] the parallel one (Stan data of inversion.py:1886-1959).
+        ``parallel=True``: the single distribution is a parallel one (Stan program 'Parallel', x is lower=0)."""
         self.ctx = context(device)
         dev = self.ctx.device
         self.A = f64(A, dev)
@@ -88,7 +89,12 @@ class SeriesProblem:
             raise ValueError('inconsistent shapes in SeriesProblem')
         self.series_parallel = Ap is not None
         d = SeriesData()
-        d.model = (_lib.MODEL_SERIES_PARALLEL if self.series_parallel else _lib.MODEL_SERIES) \
+        if parallel and (self.series_parallel or outliers):
+            raise ValueError("parallel=True is the single-distribution 'Parallel' program (no Ap, no outlier model)")
+        self.parallel = bool(parallel)
+        nonneg = bool(nonneg) or self.parallel
+        d.model = (_lib.MODEL_SERIES_PARALLEL if self.series_parallel else
+                   (_lib.MODEL_PARALLEL if parallel else _lib.MODEL_SERIES)) \
             | (_lib.MODEL_POS if nonneg else 0) | (_lib.MODEL_OUTLIERS if outliers else 0)
         d.Nf, d.K, d.B = self.Nf, self.K, self.B
         d.per_spectrum_grid = int(self.per_spectrum_grid)

@@ -42,6 +42,7 @@ struct BdrtDist {
   int off_x, off_ups, off_d;  // offsets of x, ups_raw, d_strength inside the unconstrained vector
   int oA, oTap;               // shared-memory offsets (doubles) of the resident operand and of the stencil taps
   int pos;                    // coefficients are lower=0
+  int par;                    // parallel distribution: contributes Z_p = 1 / (A x) (Parallel / Series-Parallel :63-66)
   int toepL;                  // L0/L1/L2 are Toeplitz: use the tap table
   const double* A;            // [2Nf, K] or [B, 2Nf, K]
   long long A_stride;         // per-spectrum stride (0: shared)
@@ -594,8 +595,6 @@ __device__ inline double engine_eval(const BdrtModel& m, double* sm, bool active
 
   // ---------------------------------------------------------------- phase 3: error model, residual weights (per slot)
   if (active) {
-    const double* sZ = rowZ(0);
-    double* sV = rowX(0);
     const double rinf_raw = sTh[0], ind_raw = sTh[1], sr_raw = sTh[2], ap_raw = sTh[3], are_raw = sTh[4],
                  aim_raw = sTh[5];
     const double Rinf = 100.0 * rinf_raw, induc = ind_raw * m.induc_scale;
@@ -611,16 +610,22 @@ __device__ inline double engine_eval(const BdrtModel& m, double* sm, bool active
       const int n = nb + lane + 32 * jn;
       if (n >= Nf) continue;
       const double om = sOm[n];
-      double zre = sZ[n] + Rinf, zim = sZ[nfp + n] + induc * om;
-      double Yr = 0, Yi = 0, iM = 0;
-      if (ND > 1) {
-        // Z_p = 1 / (Y' + i Y'')  (Series-Parallel :63-66)
-        const double* sY = rowZ(ND - 1);
-        Yr = sY[n];
-        Yi = sY[nfp + n];
-        iM = __drcp_rn(Yr * Yr + Yi * Yi);
-        zre += Yr * iM;
-        zim -= Yi * iM;
+      double zre = Rinf, zim = induc * om;
+      double Yr = 0, Yi = 0, iM = 0;  // at most one parallel distribution (the last one)
+#pragma unroll
+      for (int dd = 0; dd < ND; ++dd) {
+        const double* sZd = rowZ(dd);
+        if (m.d[dd].par) {
+          // Z_p = 1 / (Y' + i Y'')  (Parallel_modelcode.txt:46-50, Series-Parallel :63-66)
+          Yr = sZd[n];
+          Yi = sZd[nfp + n];
+          iM = __drcp_rn(Yr * Yr + Yi * Yi);
+          zre += Yr * iM;
+          zim -= Yi * iM;
+        } else {
+          zre += sZd[n];
+          zim += sZd[nfp + n];
+        }
       }
       double common = are2 * zre * zre + aim2 * zim * zim;
       double so_raw = 0, so_scale = 0, so = 0;
@@ -641,13 +646,17 @@ __device__ inline double engine_eval(const BdrtModel& m, double* sm, bool active
       const double G = g_re + g_im;
       const double v_re = r_re * i_re + 2.0 * zre * (ap2 * g_re + are2 * G);
       const double v_im = r_im * i_im + 2.0 * zim * (ap2 * g_im + aim2 * G);
-      sV[n] = v_re;
-      sV[nfp + n] = v_im;
-      if (ND > 1) {
-        double* sGY = rowX(ND - 1);
-        const double c1 = (Yi * Yi - Yr * Yr) * iM * iM, c2 = 2.0 * Yr * Yi * iM * iM;
-        sGY[n] = v_re * c1 + v_im * c2;
-        sGY[nfp + n] = -v_re * c2 + v_im * c1;
+#pragma unroll
+      for (int dd = 0; dd < ND; ++dd) {
+        double* sVd = rowX(dd);
+        if (m.d[dd].par) {  // d lp / d Y
+          const double c1 = (Yi * Yi - Yr * Yr) * iM * iM, c2 = 2.0 * Yr * Yi * iM * iM;
+          sVd[n] = v_re * c1 + v_im * c2;
+          sVd[nfp + n] = -v_re * c2 + v_im * c1;
+        } else {
+          sVd[n] = v_re;
+          sVd[nfp + n] = v_im;
+        }
       }
       Sv += v_re;
       Swv = fma(om, v_im, Swv);

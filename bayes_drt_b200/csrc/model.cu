@@ -131,13 +131,15 @@ int bdrt_model_prepare(bdrt_ctx* ctx, const bdrt_series_data* d, BdrtModel* m, s
   if (!d) BDRT_FAIL(ctx, BDRT_E_NULL, "null data");
   if (!d->A || !d->Z || !d->freq || !d->L) BDRT_FAIL(ctx, BDRT_E_NULL, "bdrt_series_data: null matrix pointer");
   const int base = d->model & 15;
-  if (base != BDRT_MODEL_SERIES && base != BDRT_MODEL_SERIES_PARALLEL)
-    BDRT_FAIL(ctx, BDRT_E_UNSUPPORTED, "model id %d: only the Series and Series-Parallel families are implemented", d->model);
+  if (base != BDRT_MODEL_SERIES && base != BDRT_MODEL_SERIES_PARALLEL && base != BDRT_MODEL_PARALLEL)
+    BDRT_FAIL(ctx, BDRT_E_UNSUPPORTED, "model id %d: only the Series, Parallel and Series-Parallel families are implemented",
+              d->model);
   if (d->model & ~(15 | BDRT_MODEL_POS | BDRT_MODEL_OUTLIERS)) BDRT_FAIL(ctx, BDRT_E_MODEL, "unknown model flags");
   const int nd = base == BDRT_MODEL_SERIES_PARALLEL ? 2 : 1;
-  if (nd == 2 && (d->model & BDRT_MODEL_OUTLIERS))
+  if (base != BDRT_MODEL_SERIES && (d->model & BDRT_MODEL_OUTLIERS))
     BDRT_FAIL(ctx, BDRT_E_UNSUPPORTED,
-              "Series-Parallel*_outliers is dimensionally inconsistent as shipped by the reference and is not implemented");
+              "Parallel_outliers / Series-Parallel*_outliers are dimensionally inconsistent as shipped by the reference "
+              "and are not implemented");
   if (d->Nf < 2 || d->K < 3 || d->B < 0 || d->Nf > 4096 || d->K > 4096) BDRT_FAIL(ctx, BDRT_E_SIZE, "bad Nf/K/B");
   if (nd == 2) {
     if (!d->Ap || !d->Lp) BDRT_FAIL(ctx, BDRT_E_NULL, "bdrt_series_data: null Ap / Lp for a Series-Parallel model");
@@ -161,7 +163,13 @@ int bdrt_model_prepare(bdrt_ctx* ctx, const bdrt_series_data* d, BdrtModel* m, s
     m->d[i].ascale = 1.0;
   }
   m->d[0].pos = (d->model & BDRT_MODEL_POS) ? 1 : 0;
+  if (base == BDRT_MODEL_PARALLEL) {
+    m->d[0].pos = 1;  // vector<lower=0>[K] x  (Parallel_modelcode.txt:27)
+    m->d[0].par = 1;
+    m->flags |= F_POS;
+  }
   if (nd == 2) {
+    m->d[1].par = 1;
     m->d[1].pos = 1;                 // vector<lower=0>[Kp] xp_raw
     m->d[1].ascale = d->xp_scale;    // xp = xp_raw * xp_scale
     m->x_sum_invscale = d->x_sum_invscale;
@@ -361,11 +369,16 @@ __global__ void constrain_kernel(BdrtModel m, const double* u, const int* spec, 
       zz[dd][0] = zre;
       zz[dd][1] = zim;
     }
-    double zre = zz[0][0] + Rinf, zim = zz[0][1] + induc * 2.0 * M_PI * f[nn];
-    if (m.ND > 1) {  // Z_p = 1 / Y  (Series-Parallel_modelcode.txt:63-66)
-      const double Yr = zz[1][0], Yi = zz[1][1], iM = 1.0 / (Yr * Yr + Yi * Yi);
-      zre += Yr * iM;
-      zim -= Yi * iM;
+    double zre = Rinf, zim = induc * 2.0 * M_PI * f[nn];
+    for (int dd = 0; dd < m.ND; ++dd) {
+      if (m.d[dd].par) {  // Z_p = 1 / Y  (Parallel_modelcode.txt:46-50, Series-Parallel_modelcode.txt:63-66)
+        const double Yr = zz[dd][0], Yi = zz[dd][1], iM = 1.0 / (Yr * Yr + Yi * Yi);
+        zre += Yr * iM;
+        zim -= Yi * iM;
+      } else {
+        zre += zz[dd][0];
+        zim += zz[dd][1];
+      }
     }
     double common = (are * zre) * (are * zre) + (aim * zim) * (aim * zim);
     if (outl) {

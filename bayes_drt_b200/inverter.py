@@ -138,10 +138,17 @@ class Inverter:
         Zt = Zt.to(self.device)[:, idx.to(self.device)].contiguous()
         return f, Zt
 
-    def _scale_Z(self, Z, scale_Z):
+    def _scale_Z(self, Z, scale_Z, fit_type='ridge'):
         if not scale_Z:
             self._Z_scale = torch.ones(Z.shape[0], dtype=torch.float64, device=Z.device)
             return Z
+        infos = list(self.distributions.values())
+        if len(infos) == 1 and infos[0]['dist_type'] == 'parallel' and fit_type != 'ridge' \
+                and infos[0]['kernel'] == 'DDT' and infos[0].get('symmetry', 'planar') == 'planar':
+            # pure parallel planar DDT (inversion.py:2417-2434): scale so that the scaled admittance has a fixed std
+            Ystar_std = 14.0 if infos[0]['bc'] == 'transmissive' else 2.4
+            self._Z_scale = Ystar_std * np.sqrt(Z.shape[1] / 81) / (1 / Z).abs().std(dim=1, unbiased=False)
+            return Z / self._Z_scale[:, None]
         # series / mixed branch (inversion.py:2437-2441): std(|Z|) / sqrt(Nf / 81), population std like np.std
         self._Z_scale = Z.abs().std(dim=1, unbiased=False) / np.sqrt(Z.shape[1] / 81)
         return Z / self._Z_scale[:, None]
@@ -204,19 +211,23 @@ class Inverter:
         par = [k for k, v in self.distributions.items() if v['dist_type'] == 'parallel']
         if len(ser) == 1 and len(par) == 0:
             model_type = 'Series'
+        elif len(ser) == 0 and len(par) == 1:
+            model_type = 'Parallel'
         elif len(ser) == 1 and len(par) == 1:
             model_type = 'Series-Parallel'
         else:
-            raise NotImplementedError("only the 'Series' (one series distribution) and 'Series-Parallel' (one series + "
-                                      "one parallel distribution) model families are implemented in this build")
-        if model_type == 'Series-Parallel' and outliers:
-            raise NotImplementedError("Series-Parallel*_outliers is dimensionally inconsistent as shipped by the "
-                                      "reference (N override vs matrix[N,Ks] As) and is not implemented")
+            raise NotImplementedError("only the 'Series', 'Parallel' (one distribution) and 'Series-Parallel' (one series "
+                                      "+ one parallel distribution) model families are implemented in this build")
+        if model_type != 'Series' and outliers:
+            raise NotImplementedError("Parallel_outliers / Series-Parallel*_outliers are dimensionally inconsistent as "
+                                      "shipped by the reference (N override vs matrix[N,K] A) and are not implemented")
+        if init_from_ridge and model_type == 'Parallel':
+            raise NotImplementedError('ridge initialisation is implemented for the DRT (series) kernel only')
         if init_from_ridge and len(self.distributions) > 1:
             raise ValueError('Ridge initialization can only be performed for single-distribution fits')  # :1155-1156
         if outliers == 'auto' and model_type != 'Series':
             raise NotImplementedError("outliers='auto' is implemented for single-distribution fits")
-        name = ser[0]
+        name = ser[0] if ser else par[0]
         freq, Zb = self._to_batch(frequencies, Z)
         single = self._single
         B = Zb.shape[0]
@@ -240,7 +251,7 @@ class Inverter:
         self._single = False
         self.f_train = freq.numpy()
         self.Z_train = Zb
-        Zs = self._scale_Z(Zb, scale_Z)
+        Zs = self._scale_Z(Zb, scale_Z, fit_type='map' if mode == 'optimize' else 'bayes')
         self._outlier_model = torch.zeros(B, dtype=torch.bool, device=self.device)
         results = []
         for ix, fl in groups:
@@ -259,7 +270,7 @@ class Inverter:
             else:
                 self._outlier_model[ix] = fl
         self._merge_results(results, B, model_type, name, par, mode, sigma_min, keep_draws)
-        self.stan_model_name = model_type + ('_pos' if nonneg else '') + \
+        self.stan_model_name = model_type + ('_pos' if nonneg and ser else '') + \
             ('_outliers' if bool(self._outlier_model.any()) else '') + '_StanModel.pkl'
         self._single = single
         if check_outliers and not bool(self._outlier_model.all()):
@@ -281,9 +292,10 @@ class Inverter:
         Zst = torch.cat((Zs.real, Zs.imag), dim=1).contiguous()
         common = dict(nonneg=bool(nonneg), sigma_min=sigma_min, ups_alpha=c['ups_alpha'], ups_beta=c['ups_beta'],
                       induc_scale=float(inductance_scale), device=self.device)
-        if model_type == 'Series':
+        if model_type in ('Series', 'Parallel'):  # same constants (inversion.py:1714-1754)
             L = torch.stack([c['l'][0] * m['L0'], c['l'][1] * m['L1'], c['l'][2] * m['L2']])
             prob = capi.SeriesProblem(torch.cat((m['A_re'], m['A_im'])), Zst, freq, L, outliers=bool(outliers),
+                                      parallel=model_type == 'Parallel',
                                       sigma_out_lambda=10.0 if outlier_lambda is None else float(outlier_lambda),
                                       sigma_out_alpha=c['sigma_out_alpha'], sigma_out_beta=1.0, **common)
         else:
@@ -355,6 +367,8 @@ class Inverter:
         self.distribution_fits, self.error_fit = {}, {}
         if model_type == 'Series':
             self.distribution_fits[name] = {'coef': point['x'] * s[:, None]}
+        elif model_type == 'Parallel':
+            self.distribution_fits[name] = {'coef': point['x'] / s[:, None]}
         else:  # series coef * scale, parallel coef / scale
             self.distribution_fits[name] = {'coef': point['xs'] * s[:, None]}
             self.distribution_fits[par[0]] = {'coef': point['xp'] / s[:, None]}

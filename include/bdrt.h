@@ -45,6 +45,8 @@ enum { BDRT_BC_TRANSMISSIVE = 0, BDRT_BC_BLOCKING = 1 };
 enum {
   BDRT_MODEL_SERIES = 0,          /* stan_model_files/Series_modelcode.txt */
   BDRT_MODEL_SERIES_PARALLEL = 1, /* stan_model_files/Series-Parallel_modelcode.txt (xp_raw is always lower=0) */
+  BDRT_MODEL_PARALLEL = 2,        /* stan_model_files/Parallel_modelcode.txt: one parallel distribution, Z_hat = 1/(A x)
+                                     + offsets, vector<lower=0> x (parameter layout of Series_pos) */
   BDRT_MODEL_POS = 16,            /* *_pos_modelcode.txt: vector<lower=0> x */
   BDRT_MODEL_OUTLIERS = 32        /* *_outliers_modelcode.txt */
 };

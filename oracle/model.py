@@ -51,6 +51,41 @@ MODE_CONSTANTS = {
 }
 
 
+def z_scale_parallel(Z, bc):
+    """inversion.py:2417-2434: pure parallel planar DDT fits scale Z so that the scaled admittance has a fixed std
+    (14 transmissive / 2.4 blocking)."""
+    Ystar_std = {'transmissive': 14.0, 'blocking': 2.4}[bc]
+    return Ystar_std * np.sqrt(len(Z) / 81) / np.std(np.abs(1 / Z))
+
+
+def prep_parallel(freq, Z, info, mode='optimize', sigma_min=0.002, inductance_scale=1.0, scale_Z=True):
+    """Stan data of the single-DDT 'Parallel' model (Parallel_modelcode.txt; same constants as Series,
+    inversion.py:1714-1754; ``vector<lower=0>[K] x``).  ``info``: the reference's distribution dict
+    ({'kernel': 'DDT', 'dist_type': 'parallel', 'symmetry': 'planar', 'bc': ..., 'basis_freq': ...})."""
+    freq = np.asarray(freq, dtype=np.float64)
+    Z = np.asarray(Z, dtype=np.complex128)
+    idx = np.argsort(freq)[::-1]
+    freq, Z = freq[idx], Z[idx]
+    if not scale_Z:
+        zs = 1.0
+    elif info['kernel'] == 'DDT' and info.get('symmetry', 'planar') == 'planar':
+        zs = z_scale_parallel(Z, info['bc'])
+    else:
+        zs = z_scale(Z)
+    bf = info.get('basis_freq')
+    tau = default_tau(freq) if bf is None else 1.0 / (2 * np.pi * np.asarray(bf, dtype=np.float64))
+    eps = info.get('epsilon') or default_epsilon(tau)
+    kw = dict(tau=tau, epsilon=eps, kernel=info['kernel'], dist_type='parallel',
+              symmetry=info.get('symmetry', 'planar'), bc=info.get('bc'), ct=info.get('ct', False),
+              k_ct=info.get('k_ct'))
+    A_re, A_im = om.construct_A(freq, 'real', **kw), om.construct_A(freq, 'imag', **kw)
+    d = prep_series(freq, Z / zs, basis_freq=1 / (2 * np.pi * tau), epsilon=eps, mode=mode, nonneg=True,
+                    sigma_min=sigma_min, inductance_scale=inductance_scale, scale_Z=False, A_re=A_re, A_im=A_im)
+    d['Z_scale'] = zs
+    d['parallel'] = True
+    return d
+
+
 def prep_series(freq, Z, basis_freq=None, epsilon=None, mode='optimize', nonneg=False, outliers=False,
                 sigma_min=0.002, inductance_scale=1.0, outlier_lambda=None, scale_Z=True, A_re=None, A_im=None):
     """Build the Stan data of the single-DRT ('Series*') models for one spectrum.
@@ -123,6 +158,9 @@ def constrain(u, d):
     for nm in ('sigma_res', 'alpha_prop', 'alpha_re', 'alpha_im'):
         out[nm] = 0.05 * out[nm + '_raw']
     zhat = d['A'] @ out['x']
+    if d.get('parallel'):  # Parallel_modelcode.txt:46-50: Z_hat_p = 1 / (Y' + i Y'')
+        M = zhat[:Nf] ** 2 + zhat[Nf:] ** 2
+        zhat = np.concatenate((zhat[:Nf] / M, -zhat[Nf:] / M))
     zhat[:Nf] += out['Rinf']
     zhat[Nf:] += out['induc'] * 2 * np.pi * d['freq']
     out['Z_hat'] = zhat
@@ -160,6 +198,11 @@ def logpost(u, d, jacobian=False, want_grad=True):
     sr, ap, are, aim = 0.05 * sr_raw, 0.05 * ap_raw, 0.05 * are_raw, 0.05 * aim_raw
 
     zhat = A @ x
+    par = bool(d.get('parallel'))
+    if par:  # Parallel_modelcode.txt:46-50: the distribution contributes an admittance, Z_hat_p = 1 / (Y' + i Y'')
+        Yr, Yi = zhat[:Nf].copy(), zhat[Nf:].copy()
+        M = Yr ** 2 + Yi ** 2
+        zhat = np.concatenate((Yr / M, -Yi / M))
     zhat[:Nf] += 100.0 * Rinf_raw
     zhat[Nf:] += induc_raw * d['induc_scale'] * w
     zre, zim = zhat[:Nf], zhat[Nf:]
@@ -200,7 +243,11 @@ def logpost(u, d, jacobian=False, want_grad=True):
     v[:Nf] += 2 * are ** 2 * zre * G
     v[Nf:] += 2 * aim ** 2 * zim * G
     iu2 = 1.0 / ups ** 2
-    gx = A.T @ v - (d['L0'].T @ (dstr[0] * a0 * iu2) + d['L1'].T @ (dstr[1] * a1 * iu2) + d['L2'].T @ (dstr[2] * a2 * iu2))
+    vx = v
+    if par:  # d lp / d Y from v = d lp / d Z_hat
+        c1, c2 = (Yi ** 2 - Yr ** 2) / M ** 2, 2 * Yr * Yi / M ** 2
+        vx = np.concatenate((v[:Nf] * c1 + v[Nf:] * c2, -v[:Nf] * c2 + v[Nf:] * c1))
+    gx = A.T @ vx - (d['L0'].T @ (dstr[0] * a0 * iu2) + d['L1'].T @ (dstr[1] * a1 * iu2) + d['L2'].T @ (dstr[2] * a2 * iu2))
 
     grad = np.empty_like(u)
     grad[0] = 100.0 * np.sum(v[:Nf]) - Rinf_raw

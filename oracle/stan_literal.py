@@ -68,7 +68,13 @@ def logpost_literal(u, d, jacobian=False):
     alpha_prop = alpha_prop_raw * 0.05
     alpha_re = alpha_re_raw * 0.05
     alpha_im = alpha_im_raw * 0.05
-    Z_hat = A @ x + Rinf * Rinf_vec + induc * induc_vec
+    if d.get('parallel'):  # Parallel_modelcode.txt:46-50
+        Y_hat = A @ x
+        Y_hat_re, Y_hat_im = Y_hat[:Nf], Y_hat[Nf:]
+        Z_hat_p = torch.cat((Y_hat_re / (Y_hat_re ** 2 + Y_hat_im ** 2), -Y_hat_im / (Y_hat_re ** 2 + Y_hat_im ** 2)))
+        Z_hat = Z_hat_p + Rinf * Rinf_vec + induc * induc_vec
+    else:
+        Z_hat = A @ x + Rinf * Rinf_vec + induc * induc_vec
     Z_hat_re = torch.cat((Z_hat[:Nf], Z_hat[:Nf]))
     Z_hat_im = torch.cat((Z_hat[Nf:], Z_hat[Nf:]))
     var = d['sigma_min'] ** 2 + sigma_res ** 2 + (alpha_prop * Z_hat) ** 2 + (alpha_re * Z_hat_re) ** 2 \

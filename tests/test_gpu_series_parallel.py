@@ -101,3 +101,58 @@ def test_sp_nuts_runs_and_is_deterministic():
     b = prob.nuts(u0, **kw)
     assert torch.equal(a['draws'], b['draws']) and torch.isfinite(a['draws']).all()
     assert (a['stepsize'] > 0).all() and (a['accept'] > 0.05).all()
+
+
+@pytest.mark.parametrize('bc', ['transmissive', 'blocking'])
+def test_parallel_model_logpost_map_and_inverter(bc, resident_A):
+    """Stan program 'Parallel' (single DDT, Z_hat = 1 / (A x) + offsets): engine vs oracle, and the Inverter flow with
+    the admittance-based Z scaling (inversion.py:2417-2434)."""
+    from bayes_drt_b200 import Inverter, capi
+    from oracle import model as omod
+    rng = np.random.RandomState(6)
+    Nf, K = 61, 71
+    freq = np.logspace(4, -2, Nf)
+    bf = np.logspace(4.5, -2.5, K)
+    w = 2 * np.pi * freq
+    info = {'kernel': 'DDT', 'dist_type': 'parallel', 'symmetry': 'planar', 'bc': bc, 'basis_freq': bf}
+    Zs = []
+    for s_ in range(2):
+        x = np.sqrt(1j * w * 0.5 * (s_ + 1))
+        Zd = 0.8 * (np.tanh(x) / x if bc == 'transmissive' else 1 / (x * np.tanh(x)))
+        Zs.append(0.3 + Zd + 0.002 * (rng.standard_normal(Nf) + 1j * rng.standard_normal(Nf)))
+    ds = [omod.prep_parallel(freq, Z, info, mode='optimize') for Z in Zs]
+    d0 = ds[0]
+    f = torch.tensor(d0['freq'])
+    A_re, A_im = capi.build_A(f, torch.tensor(d0['tau']), d0['epsilon'], kernel='DDT', dist_type='parallel',
+                              symmetry='planar', bc=bc)
+    c = omod.MODE_CONSTANTS['optimize']
+    L = torch.stack([c[f'l{o}'] * capi.build_L(torch.tensor(1 / (2 * np.pi * d0['tau'])), torch.tensor(d0['tau']),
+                                               d0['epsilon'], o) for o in range(3)])
+    prob = capi.SeriesProblem(torch.cat((A_re, A_im)), torch.tensor(np.stack([d['Z'] for d in ds])), f, L, parallel=True)
+    assert prob.D == 2 * K + 9
+    u = rng.uniform(-1.5, 1.5, (9, prob.D))
+    spec = rng.randint(0, 2, 9)
+    for jac in (False, True):
+        lp, grad = prob.logpost_grad(torch.tensor(u), spec=spec, jacobian=jac)
+        for k in range(9):
+            lo, go = omod.logpost(u[k], ds[spec[k]], jacobian=jac)
+            assert abs(lp[k].item() - lo) <= 1e-11 * abs(lo)
+            assert np.max(np.abs(grad[k].cpu().numpy() - go)) <= 1e-9 * np.max(np.abs(go))
+    out = prob.split_outputs(prob.constrain(torch.tensor(u[:2]), spec=spec[:2]))
+    for k in range(2):
+        co = omod.constrain(u[k], ds[spec[k]])
+        assert np.allclose(out['x'][k].cpu().numpy(), co['x'], rtol=1e-13)
+        assert np.allclose(out['sigma_tot'][k].cpu().numpy(), co['sigma_tot'], rtol=1e-10)
+    with pytest.raises(ValueError):
+        capi.SeriesProblem(torch.cat((A_re, A_im)), torch.tensor(np.stack([d['Z'] for d in ds])), f, L, parallel=True,
+                           outliers=True)
+    # the user-facing flow
+    inv = Inverter(distributions={'DDT': dict(info)})
+    inv.fit(freq, torch.tensor(np.stack(Zs)), mode='optimize', max_iter=8000)
+    assert inv.stan_model_name == 'Parallel_StanModel.pkl'
+    assert torch.allclose(inv._Z_scale.cpu(), torch.tensor([d['Z_scale'] for d in ds]), rtol=1e-12)
+    coef = inv.distribution_fits['DDT']['coef']
+    assert tuple(coef.shape) == (2, K) and (coef >= 0).all()
+    Zp = inv.predict_Z(freq)
+    assert (Zp.cpu() - torch.tensor(np.stack(Zs))).abs().max().item() < 0.03
+    assert torch.allclose(inv.R_inf.cpu(), torch.full((2,), 0.3, dtype=torch.float64), atol=0.05)

@@ -147,3 +147,40 @@ def test_series_parallel_constants_follow_reference():
     assert np.isclose(d['Ls'][0][k, k], 0.36) and np.isclose(d['Lp'][0][k, k], 0.54)
     s = _sp_data('sample', True)
     assert s['x_sum_invscale'] == 1.0 and np.isclose(s['Lp'][0][k, k], 1.0)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# Parallel (single DDT): Z_hat = 1 / (A x) + offsets
+# ---------------------------------------------------------------------------------------------------------------------
+def _par_data(mode, bc='transmissive', Nf=41, K=37):
+    rng = np.random.RandomState(6)
+    freq = np.logspace(4, -2, Nf)
+    w = 2 * np.pi * freq
+    x = np.sqrt(1j * w * 0.5)
+    Zd = 0.8 * (np.tanh(x) / x if bc == 'transmissive' else 1 / (x * np.tanh(x)))
+    Z = 0.3 + Zd + 0.002 * (rng.standard_normal(Nf) + 1j * rng.standard_normal(Nf))
+    info = {'kernel': 'DDT', 'dist_type': 'parallel', 'symmetry': 'planar', 'bc': bc, 'basis_freq': np.logspace(4.5, -2.5, K)}
+    return omod.prep_parallel(freq, Z, info, mode=mode), Z
+
+
+@pytest.mark.parametrize('mode', ['optimize', 'sample'])
+@pytest.mark.parametrize('bc', ['transmissive', 'blocking'])
+def test_parallel_logpost_matches_literal_autograd(mode, bc):
+    d, Z = _par_data(mode, bc)
+    assert d['parallel'] and d['pos']
+    # inversion.py:2417-2434: scaled admittance std 14 (transmissive) / 2.4 (blocking) x sqrt(Nf / 81)
+    assert np.isclose(np.std(np.abs(d['Z_scale'] / Z)), (14.0 if bc == 'transmissive' else 2.4) * np.sqrt(41 / 81))
+    D = omod.n_params(d)
+    rng = np.random.RandomState(10)
+    for jac in (False, True):
+        u = rng.uniform(-1, 1, D)
+        lp, g = omod.logpost(u, d, jacobian=jac)
+        ut = torch.tensor(u, requires_grad=True)
+        lt = logpost_literal(ut, d, jacobian=jac)
+        lt.backward()
+        assert abs(lp - lt.item()) <= 1e-12 * abs(lt.item())
+        assert np.max(np.abs(g - ut.grad.numpy())) <= 1e-10 * np.max(np.abs(ut.grad.numpy()))
+    c = omod.constrain(u, d)
+    Y = d['A'] @ c['x']
+    zc = 1 / (Y[:41] + 1j * Y[41:]) + c['Rinf'] + 1j * c['induc'] * 2 * np.pi * d['freq']
+    assert np.allclose(c['Z_hat'], np.r_[zc.real, zc.imag], rtol=1e-13)
