@@ -69,10 +69,11 @@ class SeriesProblem:
 
     def __init__(self, A, Z, freq, L, nonneg=False, outliers=False, sigma_min=0.002, ups_alpha=0.05, ups_beta=0.1,
                  induc_scale=1.0, sigma_out_lambda=10.0, sigma_out_alpha=2.0, sigma_out_beta=1.0, device=None,
-                 Ap=None, Lp=None, x_sum_invscale=0.0, xp_scale=1.0, parallel=False):
+                 Ap=None, Lp=None, x_sum_invscale=0.0, xp_scale=1.0, parallel=False, Ap2=None, Lp2=None, xp2_scale=1.0):
         """Series family: A, L describe the single DRT.  Series-Parallel (pass Ap, Lp): A, L describe the series
         distribution, Ap [2Nf, Kp] / Lp [3, Kp, Kp] the parallel one (Stan data of inversion.py:1886-1959).
-        ``parallel=True``: the single distribution is a parallel one (Stan program 'Parallel', x is lower=0)."""
+        ``parallel=True``: the single distribution is a parallel one (Stan program 'Parallel', x is lower=0).
+        Series-2Parallel: additionally pass Ap2 / Lp2 / xp2_scale (second parallel distribution, sorted-name order)."""
         self.ctx = context(device)
         dev = self.ctx.device
         self.A = f64(A, dev)
@@ -93,8 +94,12 @@ class SeriesProblem:
             raise ValueError("parallel=True is the single-distribution 'Parallel' program (no Ap, no outlier model)")
         self.parallel = bool(parallel)
         nonneg = bool(nonneg) or self.parallel
-        d.model = (_lib.MODEL_SERIES_PARALLEL if self.series_parallel else
-                   (_lib.MODEL_PARALLEL if parallel else _lib.MODEL_SERIES)) \
+        self.two_parallel = Ap2 is not None
+        if self.two_parallel and not self.series_parallel:
+            raise ValueError('Ap2 needs Ap')
+        d.model = (_lib.MODEL_SERIES_2PARALLEL if self.two_parallel else
+                   (_lib.MODEL_SERIES_PARALLEL if self.series_parallel else
+                    (_lib.MODEL_PARALLEL if parallel else _lib.MODEL_SERIES))) \
             | (_lib.MODEL_POS if nonneg else 0) | (_lib.MODEL_OUTLIERS if outliers else 0)
         d.Nf, d.K, d.B = self.Nf, self.K, self.B
         d.per_spectrum_grid = int(self.per_spectrum_grid)
@@ -110,6 +115,14 @@ class SeriesProblem:
                 raise ValueError('inconsistent shapes of the parallel distribution in SeriesProblem')
             d.Kp, d.Ap, d.Lp = self.Kp, self.Ap.data_ptr(), self.Lp.data_ptr()
             d.x_sum_invscale, d.xp_scale = float(x_sum_invscale), float(xp_scale)
+        self.Kp2 = 0
+        if self.two_parallel:
+            self.Ap2, self.Lp2 = f64(Ap2, dev), f64(Lp2, dev)
+            self.Kp2 = self.Ap2.shape[-1]
+            if self.Ap2.shape[-2] != n2 or (self.Ap2.dim() == 3) != self.per_spectrum_grid \
+                    or tuple(self.Lp2.shape) != (3, self.Kp2, self.Kp2):
+                raise ValueError('inconsistent shapes of the second parallel distribution in SeriesProblem')
+            d.Kp2, d.Ap2, d.Lp2, d.xp2_scale = self.Kp2, self.Ap2.data_ptr(), self.Lp2.data_ptr(), float(xp2_scale)
         self.c = d
         self.nonneg, self.outliers = bool(nonneg), bool(outliers)
         self.D = int(self.ctx.lib.bdrt_num_params(C.byref(d)))
@@ -195,14 +208,16 @@ class SeriesProblem:
 
     def split_outputs(self, out):
         """Named views of bdrt_constrain's packed output."""
-        K, Nf = self.K + self.Kp, self.Nf
+        K, Nf = self.K + self.Kp + self.Kp2, self.Nf
         d = {'x': out[..., :K], 'Rinf': out[..., K], 'induc': out[..., K + 1], 'sigma_res': out[..., K + 2],
              'alpha_prop': out[..., K + 3], 'alpha_re': out[..., K + 4], 'alpha_im': out[..., K + 5],
              'sigma_tot': out[..., K + 6:K + 6 + 2 * Nf]}
         if self.outliers:
             d['sigma_out'] = out[..., K + 6 + 2 * Nf:]
         if self.series_parallel:
-            d['xs'], d['xp'] = out[..., :self.K], out[..., self.K:K]
+            d['xs'], d['xp'] = out[..., :self.K], out[..., self.K:self.K + self.Kp]
+        if self.two_parallel:
+            d['xp1'], d['xp2'] = d['xp'], out[..., self.K + self.Kp:K]
         return d
 
 

@@ -1,7 +1,9 @@
 // Fused log-posterior + analytic-gradient engine for the reference's Stan programs
 //   'Series' family  (bayes_drt/stan_model_files/Series_modelcode.txt:24-69, Series_pos_modelcode.txt:27,
 //                     Series_outliers_modelcode.txt:22-72, Series_pos_outliers_modelcode.txt:25)            ND = 1
+//   'Parallel'        (Parallel_modelcode.txt:24-75)                                                         ND = 1
 //   'Series-Parallel' (Series-Parallel_modelcode.txt:32-107, Series-Parallel_pos_modelcode.txt:35)         ND = 2
+//   'Series-2Parallel' (Series-2Parallel_modelcode.txt:39-129, Series-2Parallel_pos_modelcode.txt:42)      ND = 3
 //
 // Execution model (B200): persistent CTAs of 8 warps.  A CTA owns NSLOT = 8 "column slots"; slot s is driven by warp s,
 // which runs its own copy of the calling algorithm (L-BFGS, NUTS, ...) with ordinary warp-uniform control flow.
@@ -31,7 +33,7 @@
 #define MAXBW 24
 #define LBW (2 * MAXBW + 1)
 #define LOG_015 (-1.8971199848858813)  // log(0.15)
-#define MAXD 2                          // distributions per model
+#define MAXD 3                          // distributions per model (Series-2Parallel: one series + two parallel)
 #define FBW 6                           // stencil half-width of the register-tiled fast path (default epsilon: bw = 6)
 
 #define F_POS 1  // lower=0 coefficients of the series distribution (x = exp(u))
@@ -552,7 +554,7 @@ __device__ inline double engine_eval(const BdrtModel& m, double* sm, bool active
       const int ti2 = ti + NWARP;
       const bool two = ti2 < ND * nmt;
       const int tj = two ? ti2 : ti;
-      const int da = (ND > 1 && ti >= nmt) ? 1 : 0, db = (ND > 1 && tj >= nmt) ? 1 : 0;
+      const int da = (ND > 1) ? ti / nmt : 0, db = (ND > 1) ? tj / nmt : 0;
       const int mt = ti - da * nmt, mt2 = tj - db * nmt;
       const BdrtDist &Da = m.d[da], &Db = m.d[db];
       const double *a0p, *a1p;
@@ -611,17 +613,17 @@ __device__ inline double engine_eval(const BdrtModel& m, double* sm, bool active
       if (n >= Nf) continue;
       const double om = sOm[n];
       double zre = Rinf, zim = induc * om;
-      double Yr = 0, Yi = 0, iM = 0;  // at most one parallel distribution (the last one)
+      double Yr[ND], Yi[ND], iM[ND];
 #pragma unroll
       for (int dd = 0; dd < ND; ++dd) {
         const double* sZd = rowZ(dd);
         if (m.d[dd].par) {
           // Z_p = 1 / (Y' + i Y'')  (Parallel_modelcode.txt:46-50, Series-Parallel :63-66)
-          Yr = sZd[n];
-          Yi = sZd[nfp + n];
-          iM = __drcp_rn(Yr * Yr + Yi * Yi);
-          zre += Yr * iM;
-          zim -= Yi * iM;
+          Yr[dd] = sZd[n];
+          Yi[dd] = sZd[nfp + n];
+          iM[dd] = __drcp_rn(Yr[dd] * Yr[dd] + Yi[dd] * Yi[dd]);
+          zre += Yr[dd] * iM[dd];
+          zim -= Yi[dd] * iM[dd];
         } else {
           zre += sZd[n];
           zim += sZd[nfp + n];
@@ -650,7 +652,8 @@ __device__ inline double engine_eval(const BdrtModel& m, double* sm, bool active
       for (int dd = 0; dd < ND; ++dd) {
         double* sVd = rowX(dd);
         if (m.d[dd].par) {  // d lp / d Y
-          const double c1 = (Yi * Yi - Yr * Yr) * iM * iM, c2 = 2.0 * Yr * Yi * iM * iM;
+          const double i2 = iM[dd] * iM[dd];
+          const double c1 = (Yi[dd] * Yi[dd] - Yr[dd] * Yr[dd]) * i2, c2 = 2.0 * Yr[dd] * Yi[dd] * i2;
           sVd[n] = v_re * c1 + v_im * c2;
           sVd[nfp + n] = -v_re * c2 + v_im * c1;
         } else {
@@ -714,8 +717,12 @@ __device__ inline double engine_eval(const BdrtModel& m, double* sm, bool active
       const int ti2 = ti + NWARP;
       const bool two = ti2 < nmt_tot;
       const int tj = two ? ti2 : ti;
-      const int da = (ND > 1 && ti >= nmt_d[0]) ? 1 : 0, db = (ND > 1 && tj >= nmt_d[0]) ? 1 : 0;
-      const int mt = ti - (da ? nmt_d[0] : 0), mt2 = tj - (db ? nmt_d[0] : 0);
+      int da = 0, db = 0, mt = ti, mt2 = tj;  // tile index -> (distribution, tile of that distribution)
+#pragma unroll
+      for (int dd = 0; dd + 1 < ND; ++dd) {
+        if (da == dd && mt >= nmt_d[dd]) { mt -= nmt_d[dd]; da = dd + 1; }
+        if (db == dd && mt2 >= nmt_d[dd]) { mt2 -= nmt_d[dd]; db = dd + 1; }
+      }
       const BdrtDist &Da = m.d[da], &Db = m.d[db];
       const int col0 = mt * 8 + g, col1 = mt2 * 8 + g;
       const double* b0p = sm + m.oXV + (da * NSLOT + g) * m.ldxv + m.xoff + t;
@@ -827,15 +834,17 @@ static inline BdrtPlan bdrt_plan(const bdrt_ctx* ctx, const BdrtModel& m, int Dp
     BDRT_CUDA(ctx, cudaFuncSetAttribute(KERNEL<T, N, F>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(smem))); \
     KERNEL<T, N, F><<<grid, NTHREADS, smem, (ctx)->stream>>>(__VA_ARGS__);                                           \
   } while (0)
-#define BDRT_LAUNCH(ctx, m, KERNEL, grid, smem, ...)                                                   \
-  do {                                                                                                 \
-    const int t_ = (m).toepA, f_ = (m).toepA && (m).fast;                                              \
-    if (f_ && (m).ND == 1) BDRT_LAUNCH_ONE(ctx, KERNEL, 1, 1, 1, grid, smem, __VA_ARGS__);             \
-    else if (f_) BDRT_LAUNCH_ONE(ctx, KERNEL, 1, 2, 1, grid, smem, __VA_ARGS__);                       \
-    else if (t_ && (m).ND == 1) BDRT_LAUNCH_ONE(ctx, KERNEL, 1, 1, 0, grid, smem, __VA_ARGS__);        \
-    else if (t_) BDRT_LAUNCH_ONE(ctx, KERNEL, 1, 2, 0, grid, smem, __VA_ARGS__);                       \
-    else if ((m).ND == 1) BDRT_LAUNCH_ONE(ctx, KERNEL, 0, 1, 0, grid, smem, __VA_ARGS__);              \
-    else BDRT_LAUNCH_ONE(ctx, KERNEL, 0, 2, 0, grid, smem, __VA_ARGS__);                               \
-    (ctx)->launches++;                                                                                 \
-    BDRT_CUDA(ctx, cudaGetLastError());                                                                \
+#define BDRT_LAUNCH_ND(ctx, m, KERNEL, T, F, grid, smem, ...)                                \
+  do {                                                                                       \
+    if ((m).ND == 1) BDRT_LAUNCH_ONE(ctx, KERNEL, T, 1, F, grid, smem, __VA_ARGS__);         \
+    else if ((m).ND == 2) BDRT_LAUNCH_ONE(ctx, KERNEL, T, 2, F, grid, smem, __VA_ARGS__);    \
+    else BDRT_LAUNCH_ONE(ctx, KERNEL, T, 3, F, grid, smem, __VA_ARGS__);                     \
+  } while (0)
+#define BDRT_LAUNCH(ctx, m, KERNEL, grid, smem, ...)                                          \
+  do {                                                                                        \
+    if ((m).toepA && (m).fast) BDRT_LAUNCH_ND(ctx, m, KERNEL, 1, 1, grid, smem, __VA_ARGS__); \
+    else if ((m).toepA) BDRT_LAUNCH_ND(ctx, m, KERNEL, 1, 0, grid, smem, __VA_ARGS__);        \
+    else BDRT_LAUNCH_ND(ctx, m, KERNEL, 0, 0, grid, smem, __VA_ARGS__);                       \
+    (ctx)->launches++;                                                                        \
+    BDRT_CUDA(ctx, cudaGetLastError());                                                       \
   } while (0)

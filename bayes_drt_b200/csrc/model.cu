@@ -38,11 +38,13 @@ extern "C" long long bdrt_launch_count(const bdrt_ctx* ctx) { return ctx ? ctx->
 extern "C" int bdrt_num_params(const bdrt_series_data* d) {
   if (!d) return BDRT_E_NULL;
   if ((d->model & 15) == BDRT_MODEL_SERIES_PARALLEL) return 2 * (d->K + d->Kp) + 12;
+  if ((d->model & 15) == BDRT_MODEL_SERIES_2PARALLEL) return 2 * (d->K + d->Kp + d->Kp2) + 15;
   return 2 * d->K + 9 + ((d->model & BDRT_MODEL_OUTLIERS) ? 2 * d->Nf : 0);
 }
 extern "C" int bdrt_num_outputs(const bdrt_series_data* d) {
   if (!d) return BDRT_E_NULL;
   if ((d->model & 15) == BDRT_MODEL_SERIES_PARALLEL) return d->K + d->Kp + 6 + 2 * d->Nf;
+  if ((d->model & 15) == BDRT_MODEL_SERIES_2PARALLEL) return d->K + d->Kp + d->Kp2 + 6 + 2 * d->Nf;
   return d->K + 6 + 2 * d->Nf + ((d->model & BDRT_MODEL_OUTLIERS) ? d->Nf : 0);
 }
 
@@ -131,20 +133,25 @@ int bdrt_model_prepare(bdrt_ctx* ctx, const bdrt_series_data* d, BdrtModel* m, s
   if (!d) BDRT_FAIL(ctx, BDRT_E_NULL, "null data");
   if (!d->A || !d->Z || !d->freq || !d->L) BDRT_FAIL(ctx, BDRT_E_NULL, "bdrt_series_data: null matrix pointer");
   const int base = d->model & 15;
-  if (base != BDRT_MODEL_SERIES && base != BDRT_MODEL_SERIES_PARALLEL && base != BDRT_MODEL_PARALLEL)
-    BDRT_FAIL(ctx, BDRT_E_UNSUPPORTED, "model id %d: only the Series, Parallel and Series-Parallel families are implemented",
-              d->model);
+  if (base != BDRT_MODEL_SERIES && base != BDRT_MODEL_SERIES_PARALLEL && base != BDRT_MODEL_PARALLEL &&
+      base != BDRT_MODEL_SERIES_2PARALLEL)
+    BDRT_FAIL(ctx, BDRT_E_MODEL, "unknown model id %d", d->model);
   if (d->model & ~(15 | BDRT_MODEL_POS | BDRT_MODEL_OUTLIERS)) BDRT_FAIL(ctx, BDRT_E_MODEL, "unknown model flags");
-  const int nd = base == BDRT_MODEL_SERIES_PARALLEL ? 2 : 1;
+  const int nd = base == BDRT_MODEL_SERIES_PARALLEL ? 2 : (base == BDRT_MODEL_SERIES_2PARALLEL ? 3 : 1);
   if (base != BDRT_MODEL_SERIES && (d->model & BDRT_MODEL_OUTLIERS))
     BDRT_FAIL(ctx, BDRT_E_UNSUPPORTED,
               "Parallel_outliers / Series-Parallel*_outliers are dimensionally inconsistent as shipped by the reference "
               "and are not implemented");
   if (d->Nf < 2 || d->K < 3 || d->B < 0 || d->Nf > 4096 || d->K > 4096) BDRT_FAIL(ctx, BDRT_E_SIZE, "bad Nf/K/B");
-  if (nd == 2) {
+  if (nd >= 2) {
     if (!d->Ap || !d->Lp) BDRT_FAIL(ctx, BDRT_E_NULL, "bdrt_series_data: null Ap / Lp for a Series-Parallel model");
     if (d->Kp < 3 || d->Kp > 4096) BDRT_FAIL(ctx, BDRT_E_SIZE, "bad Kp");
     if (!(d->x_sum_invscale >= 0) || !(d->xp_scale > 0)) BDRT_FAIL(ctx, BDRT_E_SIZE, "bad x_sum_invscale / xp_scale");
+  }
+  if (nd == 3) {
+    if (!d->Ap2 || !d->Lp2) BDRT_FAIL(ctx, BDRT_E_NULL, "bdrt_series_data: null Ap2 / Lp2 for a Series-2Parallel model");
+    if (d->Kp2 < 3 || d->Kp2 > 4096) BDRT_FAIL(ctx, BDRT_E_SIZE, "bad Kp2");
+    if (!(d->xp2_scale > 0)) BDRT_FAIL(ctx, BDRT_E_SIZE, "bad xp2_scale");
   }
   if (!(d->sigma_min >= 0) || !(d->ups_alpha > 0) || !(d->ups_beta > 0) || !(d->induc_scale > 0))
     BDRT_FAIL(ctx, BDRT_E_SIZE, "model constants must be positive");
@@ -153,9 +160,9 @@ int bdrt_model_prepare(bdrt_ctx* ctx, const bdrt_series_data* d, BdrtModel* m, s
   m->ND = nd;
   m->Nf = d->Nf;
   m->B = d->B;
-  const int Ks[2] = {d->K, d->Kp};
-  const double* As[2] = {d->A, d->Ap};
-  const double* Ls[2] = {d->L, d->Lp};
+  const int Ks[MAXD] = {d->K, d->Kp, d->Kp2};
+  const double* As[MAXD] = {d->A, d->Ap, d->Ap2};
+  const double* Ls[MAXD] = {d->L, d->Lp, d->Lp2};
   for (int i = 0; i < nd; ++i) {
     m->d[i].K = Ks[i];
     m->d[i].A = As[i];
@@ -168,11 +175,16 @@ int bdrt_model_prepare(bdrt_ctx* ctx, const bdrt_series_data* d, BdrtModel* m, s
     m->d[0].par = 1;
     m->flags |= F_POS;
   }
-  if (nd == 2) {
+  if (nd >= 2) {
     m->d[1].par = 1;
     m->d[1].pos = 1;                 // vector<lower=0>[Kp] xp_raw
     m->d[1].ascale = d->xp_scale;    // xp = xp_raw * xp_scale
     m->x_sum_invscale = d->x_sum_invscale;
+  }
+  if (nd == 3) {
+    m->d[2].par = 1;
+    m->d[2].pos = 1;
+    m->d[2].ascale = d->xp2_scale;
   }
   m->freq = d->freq;
   m->f_stride = d->per_spectrum_grid ? d->Nf : 0;
@@ -185,7 +197,7 @@ int bdrt_model_prepare(bdrt_ctx* ctx, const bdrt_series_data* d, BdrtModel* m, s
   m->so_alpha = d->sigma_out_alpha;
   m->so_beta = d->sigma_out_beta;
   // workspace: [info (256 B) | Lb of every distribution | extra]
-  size_t lb_off[2], head = 256;
+  size_t lb_off[MAXD], head = 256;
   for (int i = 0; i < nd; ++i) {
     lb_off[i] = head;
     head += ((size_t)3 * Ks[i] * LBW * sizeof(double) + 255) & ~(size_t)255;
@@ -196,7 +208,7 @@ int bdrt_model_prepare(bdrt_ctx* ctx, const bdrt_series_data* d, BdrtModel* m, s
   // BDRT_FORCE_DENSE=1 keeps the dense-resident A path even for Toeplitz grids (used by the tests to cover both)
   const char* fd = getenv("BDRT_FORCE_DENSE");
   const int try_toep = !(fd && fd[0] == '1');
-  const int init[8] = {0, 1, try_toep, 0, 0, 1, 0, 0};  // per distribution i: info[4i] = bw, info[4i+1] = L Toeplitz
+  const int init[12] = {0, 1, try_toep, 0, 0, 1, 0, 0, 0, 1, 0, 0};  // per distribution i: info[4i] = bw, info[4i+1] = L Toeplitz
   BDRT_CUDA(ctx, cudaMemcpyAsync(info, init, sizeof(init), cudaMemcpyHostToDevice, ctx->stream));
   for (int i = 0; i < nd; ++i) {
     double* Lb = (double*)((char*)ctx->ws + lb_off[i]);
@@ -210,7 +222,7 @@ int bdrt_model_prepare(bdrt_ctx* ctx, const bdrt_series_data* d, BdrtModel* m, s
     }
   }
   BDRT_CUDA(ctx, cudaGetLastError());
-  int hinfo[8];
+  int hinfo[12];
   BDRT_CUDA(ctx, cudaMemcpyAsync(hinfo, info, sizeof(hinfo), cudaMemcpyDeviceToHost, ctx->stream));
   BDRT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   int bw = 0;

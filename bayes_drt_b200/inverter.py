@@ -215,9 +215,13 @@ class Inverter:
             model_type = 'Parallel'
         elif len(ser) == 1 and len(par) == 1:
             model_type = 'Series-Parallel'
+        elif len(ser) == 1 and len(par) == 2:
+            model_type = 'Series-2Parallel'
+            par = sorted(par)  # the reference orders the parallel distributions by name (inversion.py:1963-1968)
+            self.distributions[par[0]]['order'], self.distributions[par[1]]['order'] = 1, 2
         else:
-            raise NotImplementedError("only the 'Series', 'Parallel' (one distribution) and 'Series-Parallel' (one series "
-                                      "+ one parallel distribution) model families are implemented in this build")
+            raise NotImplementedError("the 'MultiDist' model (arbitrary numbers of distributions) is a placeholder in the "
+                                      "reference (its Stan file is not shipped) and is not implemented")
         if model_type != 'Series' and outliers:
             raise NotImplementedError("Parallel_outliers / Series-Parallel*_outliers are dimensionally inconsistent as "
                                       "shipped by the reference (N override vs matrix[N,K] A) and are not implemented")
@@ -303,10 +307,17 @@ class Inverter:
             csp = _MODE_SP[mode]
             Ls = torch.stack([csp['ls'][j] * m[f'L{j}'] for j in range(3)])
             Lp = torch.stack([csp['lp'][j] * mp[f'L{j}'] for j in range(3)])
+            extra = {}
+            x_sum_invscale = csp['x_sum_invscale']
+            if model_type == 'Series-2Parallel':  # inversion.py:1961-2049
+                _, _, mp2 = self._grid(freq, par[1])
+                extra = dict(Ap2=torch.cat((mp2['A_re'], mp2['A_im'])),
+                             Lp2=torch.stack([csp['lp'][j] * mp2[f'L{j}'] for j in range(3)]),
+                             xp2_scale=float(self.distributions[par[1]].get('x_scale', 1)))
+                x_sum_invscale = 0.1 if mode == 'sample' else 0.0
             prob = capi.SeriesProblem(torch.cat((m['A_re'], m['A_im'])), Zst, freq, Ls,
-                                      Ap=torch.cat((mp['A_re'], mp['A_im'])), Lp=Lp,
-                                      x_sum_invscale=csp['x_sum_invscale'],
-                                      xp_scale=float(self.distributions[par[0]].get('x_scale', 1)), **common)
+                                      Ap=torch.cat((mp['A_re'], mp['A_im'])), Lp=Lp, x_sum_invscale=x_sum_invscale,
+                                      xp_scale=float(self.distributions[par[0]].get('x_scale', 1)), **extra, **common)
         self._problem = prob
         B, D, K, Nf = prob.B, prob.D, prob.K, prob.Nf
         nch = 1 if mode == 'optimize' else chains
@@ -372,6 +383,8 @@ class Inverter:
         else:  # series coef * scale, parallel coef / scale
             self.distribution_fits[name] = {'coef': point['xs'] * s[:, None]}
             self.distribution_fits[par[0]] = {'coef': point['xp'] / s[:, None]}
+            if model_type == 'Series-2Parallel':
+                self.distribution_fits[par[1]] = {'coef': point['xp2'] / s[:, None]}
         self.R_inf = point['Rinf'] * s
         self.inductance = point['induc'] * s
         self.error_fit['sigma_min'] = sigma_min * s

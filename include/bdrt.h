@@ -45,6 +45,7 @@ enum { BDRT_BC_TRANSMISSIVE = 0, BDRT_BC_BLOCKING = 1 };
 enum {
   BDRT_MODEL_SERIES = 0,          /* stan_model_files/Series_modelcode.txt */
   BDRT_MODEL_SERIES_PARALLEL = 1, /* stan_model_files/Series-Parallel_modelcode.txt (xp_raw is always lower=0) */
+  BDRT_MODEL_SERIES_2PARALLEL = 3, /* stan_model_files/Series-2Parallel_modelcode.txt: one series + two parallel */
   BDRT_MODEL_PARALLEL = 2,        /* stan_model_files/Parallel_modelcode.txt: one parallel distribution, Z_hat = 1/(A x)
                                      + offsets, vector<lower=0> x (parameter layout of Series_pos) */
   BDRT_MODEL_POS = 16,            /* *_pos_modelcode.txt: vector<lower=0> x */
@@ -121,10 +122,16 @@ typedef struct {
   const double* Ap;   /* [2Nf,Kp] or [B,2Nf,Kp] stacked kernel matrix of the parallel distribution */
   const double* Lp;   /* [3,Kp,Kp] scaled L0p, L1p, L2p */
   double x_sum_invscale, xp_scale;
+  /* BDRT_MODEL_SERIES_2PARALLEL only: the second parallel distribution (the reference orders the parallel
+   * distributions by sorted name, inversion.py:1963) */
+  int Kp2;
+  const double* Ap2;  /* [2Nf,Kp2] or [B,2Nf,Kp2] */
+  const double* Lp2;  /* [3,Kp2,Kp2] */
+  double xp2_scale;
 } bdrt_series_data;
 
 /* number of unconstrained parameters D of the model: Series 2K+9 (+2Nf with outliers);
- * Series-Parallel 2(Ks+Kp)+12 */
+ * Series-Parallel 2(Ks+Kp)+12; Series-2Parallel 2(Ks+Kp1+Kp2)+15 */
 int bdrt_num_params(const bdrt_series_data* data);
 
 /* Test hook == Stan's log_prob + grad_log_prob (what .optimizing / .sampling evaluate internally):

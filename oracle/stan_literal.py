@@ -180,3 +180,76 @@ def logpost_literal_sp(u, d, jacobian=False):
     if jacobian:
         lp = lp + logjac
     return lp
+
+
+def logpost_literal_s2p(u, d, jacobian=False):
+    """Series-2Parallel[_pos]_modelcode.txt, line by line (parameters :39-61, transformed parameters :62-103,
+    model :104-129).  d: dict from oracle.model_sp.prep_series_2parallel."""
+    Ks, Kp1, Kp2, Nf = d['Ks'], d['Kp'], d['Kp2'], d['Nf']
+    t = lambda a: torch.as_tensor(a, dtype=torch.float64)
+    As, Ap1, Ap2, Z, freq = t(d['As']), t(d['Ap']), t(d['Ap2']), t(d['Z']), t(d['freq'])
+    L0s, L1s, L2s = (t(x) for x in d['Ls'])
+    L0p1, L1p1, L2p1 = (t(x) for x in d['Lp'])
+    L0p2, L1p2, L2p2 = (t(x) for x in d['Lp2'])
+    Rinf_vec = torch.cat((torch.ones(Nf, dtype=torch.float64), torch.zeros(Nf, dtype=torch.float64)))
+    induc_vec = torch.cat((torch.zeros(Nf, dtype=torch.float64), 2 * math.pi * freq))
+    pos = 0
+    logjac = torch.zeros((), dtype=torch.float64)
+
+    def take(n, lower0):
+        nonlocal pos, logjac
+        raw = u[pos:pos + n]
+        pos += n
+        if lower0:
+            logjac = logjac + raw.sum()
+            return torch.exp(raw)
+        return raw
+
+    Rinf_raw = take(1, True)[0]
+    induc_raw = take(1, True)[0]
+    xs = take(Ks, d['pos'])
+    xp1_raw = take(Kp1, True)
+    xp2_raw = take(Kp2, True)
+    sigma_res_raw, alpha_prop_raw, alpha_re_raw, alpha_im_raw = (take(1, True)[0] for _ in range(4))
+    ups_s_raw = take(Ks, True)
+    ups_p1_raw = take(Kp1, True)
+    ups_p2_raw = take(Kp2, True)
+    ds_ = [take(1, True)[0] for _ in range(3)]
+    dp1 = [take(1, True)[0] for _ in range(3)]
+    dp2 = [take(1, True)[0] for _ in range(3)]
+    assert pos == u.numel()
+    Rinf = Rinf_raw * 100
+    induc = induc_raw * d['induc_scale']
+    xp1 = xp1_raw * d['xp_scale']
+    xp2 = xp2_raw * d['xp2_scale']
+    q = lambda dd, L0, L1, L2, x: torch.sqrt(dd[0] * (L0 @ x) ** 2 + dd[1] * (L1 @ x) ** 2 + dd[2] * (L2 @ x) ** 2)
+    qs, qp1, qp2 = q(ds_, L0s, L1s, L2s, xs), q(dp1, L0p1, L1p1, L2p1, xp1_raw), q(dp2, L0p2, L1p2, L2p2, xp2_raw)
+    x_sum_raw = xs.sum() + xp1_raw.sum() + xp2_raw.sum()
+    if x_sum_raw.item() < 0:
+        return torch.tensor(-float('inf'), dtype=torch.float64)
+    x_sum = x_sum_raw * d['x_sum_invscale']
+    sigma_res, alpha_prop, alpha_re, alpha_im = (0.05 * v for v in (sigma_res_raw, alpha_prop_raw, alpha_re_raw,
+                                                                    alpha_im_raw))
+
+    def zp(Y):
+        re, im = Y[:Nf], Y[Nf:]
+        return torch.cat((re / (re ** 2 + im ** 2), -im / (re ** 2 + im ** 2)))
+    Z_hat = zp(Ap1 @ xp1) + zp(Ap2 @ xp2) + As @ xs + Rinf * Rinf_vec + induc * induc_vec
+    Z_hat_re = torch.cat((Z_hat[:Nf], Z_hat[:Nf]))
+    Z_hat_im = torch.cat((Z_hat[Nf:], Z_hat[Nf:]))
+    sigma_tot = torch.sqrt(d['sigma_min'] ** 2 + sigma_res ** 2 + (alpha_prop * Z_hat) ** 2
+                           + (alpha_re * Z_hat_re) ** 2 + (alpha_im * Z_hat_im) ** 2)
+    dups = lambda ur: (lambda ups: 0.5 * (ups[1:-1] - 0.5 * (ups[:-2] + ups[2:])) / ups[1:-1])(ur * 0.15)
+    lp = sum(_inv_gamma_lpdf(x, 5.0, 5.0) for x in ds_ + dp1 + dp2)
+    lp = lp + _std_normal_lpdf(x_sum)
+    for ur in (ups_s_raw, ups_p1_raw, ups_p2_raw):
+        lp = lp + _inv_gamma_lpdf(ur, d['ups_alpha'], d['ups_beta']) + _std_normal_lpdf(dups(ur))
+    lp = lp + _std_normal_lpdf(Rinf_raw) + _std_normal_lpdf(induc_raw)
+    lp = lp + _normal_lpdf(qs, 0.0, ups_s_raw * 0.15) + _normal_lpdf(qp1, 0.0, ups_p1_raw * 0.15) \
+        + _normal_lpdf(qp2, 0.0, ups_p2_raw * 0.15)
+    lp = lp + _normal_lpdf(Z, Z_hat, sigma_tot)
+    lp = lp + _std_normal_lpdf(sigma_res_raw) + _std_normal_lpdf(alpha_prop_raw) + _std_normal_lpdf(alpha_re_raw) \
+        + _std_normal_lpdf(alpha_im_raw)
+    if jacobian:
+        lp = lp + logjac
+    return lp

@@ -128,9 +128,11 @@ def test_unsupported_options_are_loud():
         inv.fit(freq[:-1], Z)
     with pytest.raises(ValueError):
         Inverter(basis='Zic')
-    with pytest.raises(NotImplementedError):
-        Inverter(distributions={'DDT': {'kernel': 'DDT', 'dist_type': 'parallel', 'symmetry': 'planar',
-                                        'bc': 'transmissive'}}).fit(freq, Z)
+    two_par = {'kernel': 'DDT', 'dist_type': 'parallel', 'symmetry': 'planar', 'bc': 'transmissive'}
+    with pytest.raises(NotImplementedError):  # MultiDist placeholder of the reference (model file not shipped)
+        Inverter(distributions={'a': dict(two_par), 'b': dict(two_par), 'c': dict(two_par)}).fit(freq, Z)
+    with pytest.raises(NotImplementedError):  # Parallel_outliers is inconsistent as shipped
+        Inverter(distributions={'a': dict(two_par)}).fit(freq, Z, outliers=True)
     with pytest.raises(ValueError):
         inv.coef_percentile('DRT', 50)  # no bayes fit yet
 

@@ -156,3 +156,55 @@ def test_parallel_model_logpost_map_and_inverter(bc, resident_A):
     Zp = inv.predict_Z(freq)
     assert (Zp.cpu() - torch.tensor(np.stack(Zs))).abs().max().item() < 0.03
     assert torch.allclose(inv.R_inf.cpu(), torch.full((2,), 0.3, dtype=torch.float64), atol=0.05)
+
+
+def test_series_2parallel_engine_and_inverter(resident_A):
+    """Stan program 'Series-2Parallel_pos': DRT + transmissive DDT + blocking DDT (three resident operands)."""
+    from bayes_drt_b200 import Inverter, capi
+    rng = np.random.RandomState(12)
+    Nf, K = (61, 61) if resident_A != 'dense' else (33, 29)
+    freq = np.logspace(5, -1, Nf)
+    bf = np.logspace(5, -1, K) if resident_A != 'dense' else np.logspace(5.5, -1.5, K)
+    w = 2 * np.pi * freq
+    Zs = []
+    for k in range(2):
+        Z = 0.5 + 1.0 / (1 + (1j * w * 1e-3) ** 0.8) + 0.7 * np.tanh(np.sqrt(1j * w * 0.3 * (k + 1))) / np.sqrt(1j * w * 0.3 * (k + 1))
+        Zs.append(Z + 0.002 * (rng.standard_normal(Nf) + 1j * rng.standard_normal(Nf)))
+    ser = {'kernel': 'DRT', 'dist_type': 'series', 'basis_freq': bf}
+    p1 = {'kernel': 'DDT', 'dist_type': 'parallel', 'symmetry': 'planar', 'bc': 'transmissive', 'basis_freq': bf, 'x_scale': 0.8}
+    p2 = {'kernel': 'DDT', 'dist_type': 'parallel', 'symmetry': 'planar', 'bc': 'blocking', 'basis_freq': bf}
+    ds = [osp.prep_series_2parallel(freq, Z, ser, p1, p2, mode='sample') for Z in Zs]
+    d0 = ds[0]
+    f = torch.tensor(d0['freq'])
+    tau = torch.tensor(d0['tau_s'])
+    As = capi.build_A(f, tau, d0['eps_s'])
+    A1 = capi.build_A(f, tau, d0['eps_p'], kernel='DDT', dist_type='parallel', symmetry='planar', bc='transmissive')
+    A2 = capi.build_A(f, tau, d0['eps_p2'], kernel='DDT', dist_type='parallel', symmetry='planar', bc='blocking')
+    c = osp.MODE_CONSTANTS_SP['sample']
+    Lb = [capi.build_L(torch.tensor(bf), tau, d0['eps_s'], o) for o in range(3)]
+    Lsp = lambda key: torch.stack([c[key][o] * Lb[o] for o in range(3)])
+    prob = capi.SeriesProblem(torch.cat(As), torch.tensor(np.stack([d['Z'] for d in ds])), f, Lsp('ls'), nonneg=True,
+                              ups_alpha=1.0, ups_beta=0.1, Ap=torch.cat(A1), Lp=Lsp('lp'), x_sum_invscale=0.1,
+                              xp_scale=0.8, Ap2=torch.cat(A2), Lp2=Lsp('lp'), xp2_scale=1.0)
+    assert prob.D == osp.n_params(d0) == 6 * K + 15
+    u = rng.uniform(-1, 1, (9, prob.D))
+    spec = rng.randint(0, 2, 9)
+    for jac in (False, True):
+        lp, grad = prob.logpost_grad(torch.tensor(u), spec=spec, jacobian=jac)
+        for k in range(9):
+            lo, go = osp.logpost(u[k], ds[spec[k]], jacobian=jac)
+            assert abs(lp[k].item() - lo) <= 1e-11 * abs(lo)
+            assert np.max(np.abs(grad[k].cpu().numpy() - go)) <= 1e-9 * np.max(np.abs(go))
+    out = prob.split_outputs(prob.constrain(torch.tensor(u[:1]), spec=spec[:1]))
+    co = osp.constrain(u[0], ds[spec[0]])
+    for nm in ('xs', 'xp1', 'xp2', 'sigma_tot'):
+        assert np.allclose(out[nm][0].cpu().numpy(), co[nm], rtol=1e-10)
+    r = prob.map_lbfgs(torch.tensor(rng.uniform(-2, 2, (2, prob.D))), max_iter=100)
+    assert torch.isfinite(r['lp']).all()
+    # user-facing flow: names sorted -> 'a-TP' is the first parallel distribution, 'b-BP' the second
+    inv = Inverter(distributions={'DRT': dict(ser), 'b-BP': dict(p2), 'a-TP': dict(p1)})
+    inv.fit(freq, torch.tensor(np.stack(Zs)), mode='optimize', nonneg=True, max_iter=3000)
+    assert inv.stan_model_name == 'Series-2Parallel_pos_StanModel.pkl'
+    assert inv.distributions['a-TP']['order'] == 1 and inv.distributions['b-BP']['order'] == 2
+    assert all(tuple(inv.distribution_fits[n]['coef'].shape) == (2, K) for n in ('DRT', 'a-TP', 'b-BP'))
+    assert (inv.predict_Z(freq).cpu() - torch.tensor(np.stack(Zs))).abs().max().item() < 0.05

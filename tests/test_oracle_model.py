@@ -184,3 +184,33 @@ def test_parallel_logpost_matches_literal_autograd(mode, bc):
     Y = d['A'] @ c['x']
     zc = 1 / (Y[:41] + 1j * Y[41:]) + c['Rinf'] + 1j * c['induc'] * 2 * np.pi * d['freq']
     assert np.allclose(c['Z_hat'], np.r_[zc.real, zc.imag], rtol=1e-13)
+
+
+@pytest.mark.parametrize('mode', ['optimize', 'sample'])
+def test_series_2parallel_logpost_matches_literal_autograd(mode):
+    """Series-2Parallel_pos: DRT + transmissive DDT + blocking DDT (the parallel distributions in sorted-name order)."""
+    from oracle import model_sp as osp
+    from oracle.stan_literal import logpost_literal_s2p
+    rng = np.random.RandomState(12)
+    Nf, K = 41, 29
+    freq = np.logspace(5, -1, Nf)
+    bf = np.logspace(5.5, -1.5, K)
+    w = 2 * np.pi * freq
+    Z = 0.5 + 1.0 / (1 + (1j * w * 1e-3) ** 0.8) + 0.7 * np.tanh(np.sqrt(1j * w * 0.3)) / np.sqrt(1j * w * 0.3)
+    Z = Z + 0.002 * (rng.standard_normal(Nf) + 1j * rng.standard_normal(Nf))
+    ser = {'kernel': 'DRT', 'basis_freq': bf}
+    p1 = {'kernel': 'DDT', 'symmetry': 'planar', 'bc': 'transmissive', 'basis_freq': bf, 'x_scale': 0.8}
+    p2 = {'kernel': 'DDT', 'symmetry': 'planar', 'bc': 'blocking', 'basis_freq': bf[:-4]}
+    d = osp.prep_series_2parallel(freq, Z, ser, p1, p2, mode=mode)
+    D = osp.n_params(d)
+    assert D == 2 * (K + K + K - 4) + 15 and d['x_sum_invscale'] == (0.1 if mode == 'sample' else 0.0)
+    for jac in (False, True):
+        u = rng.uniform(-1, 1, D)
+        lp, g = osp.logpost(u, d, jacobian=jac)
+        ut = torch.tensor(u, requires_grad=True)
+        lt = logpost_literal_s2p(ut, d, jacobian=jac)
+        lt.backward()
+        assert abs(lp - lt.item()) <= 1e-12 * abs(lt.item())
+        assert np.max(np.abs(g - ut.grad.numpy())) <= 1e-10 * np.max(np.abs(ut.grad.numpy()))
+    c = osp.constrain(u, d)
+    assert c['xp1'].shape == (K,) and c['xp2'].shape == (K - 4,) and np.isclose(c['xp1'][0], 0.8 * np.exp(u[2 + K]))
