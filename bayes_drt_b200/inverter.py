@@ -590,6 +590,71 @@ class Inverter:
         idx = torch.nonzero(zs > threshold)
         return idx[:, 1].cpu().numpy() if self._single else idx
 
+    # ------------------------------------------------------------------------------------------------------------
+    # saving and loading fits (inversion.py:3980-4064): the same attribute lists, tensors stored as numpy arrays so a
+    # file can be read without a GPU (and by code written against the reference's pickles)
+    # ------------------------------------------------------------------------------------------------------------
+    def get_fit_attributes(self, which='all'):
+        fit_attributes = {
+            'common': {'core': ['distributions', 'distribution_fits', 'f_train', 'Z_train', '_Z_scale', 'fit_type',
+                                'R_inf', 'inductance', '_single'],
+                       'detail': ['distribution_matrices']},
+            'ridge': {'core': [], 'detail': ['_ridge_iters', '_ridge_converged']},
+            'map': {'core': ['stan_model_name', 'error_fit'], 'detail': ['_init_params', '_opt_result']},
+            'bayes': {'core': ['stan_model_name', '_sample_result', 'error_fit'],
+                      'detail': ['_init_params', '_sample_stats']},
+        }
+        if self.fit_type not in fit_attributes:
+            raise ValueError('No fit to save')
+        if which == 'all':
+            return sum(fit_attributes['common'].values(), []) + sum(fit_attributes[self.fit_type].values(), [])
+        if which not in ('core', 'detail'):
+            raise ValueError(f"Invalid which argument {which}. Options are 'core', 'detail', 'all'")
+        return fit_attributes['common'][which] + fit_attributes[self.fit_type][which]
+
+    def save_fit_data(self, filename=None, which='all'):
+        """inversion.py:4004-4036: pickle (or return) the dict of fit attributes; ``which`` in 'core', 'detail', 'all'."""
+        import pickle
+
+        def host(v):
+            if torch.is_tensor(v):
+                return v.detach().cpu().numpy()
+            if isinstance(v, dict):
+                return {k: host(x) for k, x in v.items()}
+            return v
+        fit_data = {att: host(getattr(self, att)) for att in self.get_fit_attributes(which) if hasattr(self, att)}
+        if filename is None:
+            return fit_data
+        with open(filename, 'wb') as f:  # stan_models.save_pickle (stan_models.py:6-9)
+            pickle.dump(fit_data, f, pickle.HIGHEST_PROTOCOL)
+
+    def load_fit_data(self, data):
+        """inversion.py:4038-4064: restore a fit saved by save_fit_data (file name or dict)."""
+        import pickle
+        if isinstance(data, str):
+            with open(data, 'rb') as f:
+                data = pickle.load(f)
+
+        def dev(v):
+            if isinstance(v, np.ndarray) and v.dtype.kind in 'fc':
+                return torch.as_tensor(v, device=self.device)
+            if isinstance(v, dict):
+                return {k: dev(x) for k, x in v.items()}
+            return v
+        for k, v in data.items():
+            if k in ('_Z_scale', 'Z_train', '_sample_result', '_sample_stats', '_opt_result', 'distribution_matrices'):
+                v = dev(v)
+            elif k in ('distribution_fits', 'error_fit', 'R_inf', 'inductance') and not data.get('_single', False):
+                v = dev(v)
+            setattr(self, k, v)
+        if 'distributions' in data:
+            self._distributions = data['distributions']
+        if torch.is_tensor(self._Z_scale) and self._Z_scale.dim() == 0:
+            self._Z_scale = self._Z_scale.reshape(1)
+        if 'distribution_matrices' not in data:
+            self.distribution_matrices = {k: {} for k in self._distributions}  # rebuilt on demand
+        return self
+
     def ridge_fit(self, frequencies, Z, **kw):
         from .ridge import ridge_fit
         return ridge_fit(self, frequencies, Z, **kw)

@@ -173,3 +173,38 @@ def test_init_from_ridge_and_auto_outliers():
     pos = Inverter()
     pos.fit(freq, Z, mode='optimize', nonneg=True, init_from_ridge=True)
     assert np.isfinite(pos.distribution_fits['DRT']['coef']).all() and abs(pos.R_inf - 1.0) < 0.02
+
+
+def test_save_and_load_fit_data(tmp_path):
+    """inversion.py:3980-4064: the attribute dict survives a pickle round trip (numpy inside, no GPU needed to read it)
+    and a fresh Inverter answers the post-fit queries from it."""
+    import pickle
+    from bayes_drt_b200 import Inverter
+    freq, Z = load_spectrum('ZARC_uniform_0.25')
+    Zb = torch.tensor(np.stack([Z, load_spectrum('2ZARC_uniform_0.25')[1]]))
+    inv = Inverter()
+    inv.fit(freq, Zb, mode='sample', chains=2, warmup=60, samples=40)
+    core = inv.save_fit_data(which='core')
+    assert set(core) >= {'distributions', 'distribution_fits', 'f_train', 'Z_train', '_Z_scale', 'fit_type', 'R_inf',
+                         'inductance', 'stan_model_name', '_sample_result', 'error_fit'}
+    assert 'distribution_matrices' not in core and isinstance(core['distribution_fits']['DRT']['coef'], np.ndarray)
+    fn = str(tmp_path / 'fit.pkl')
+    inv.save_fit_data(fn, which='all')
+    with open(fn, 'rb') as f:
+        raw = pickle.load(f)
+    assert 'distribution_matrices' in raw and isinstance(raw['Z_train'], np.ndarray)
+    new = Inverter().load_fit_data(fn)
+    assert new.fit_type == 'bayes' and new.stan_model_name == inv.stan_model_name
+    tau = np.logspace(-6, 1, 50)
+    for kw in (dict(), dict(percentile=97.5)):
+        assert torch.equal(new.predict_distribution('DRT', eval_tau=tau, **kw), inv.predict_distribution('DRT', eval_tau=tau, **kw))
+    assert torch.equal(new.predict_Z(freq), inv.predict_Z(freq))
+    assert torch.equal(new.predict_Rp(percentile=50), inv.predict_Rp(percentile=50))
+    # single-spectrum MAP fit, core only, through a dict
+    one = Inverter()
+    one.fit(freq, Z, mode='optimize', max_iter=500)
+    again = Inverter().load_fit_data(one.save_fit_data(which='core'))
+    assert np.array_equal(again.predict_distribution('DRT', eval_tau=tau), one.predict_distribution('DRT', eval_tau=tau))
+    assert again.predict_Rp() == one.predict_Rp()
+    with pytest.raises(ValueError):
+        Inverter().save_fit_data()
