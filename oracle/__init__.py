@@ -14,7 +14,7 @@ Parity pinning
 --------------
 * ``oracle.matrices`` is pinned against the reference's own ``matrices.py``
   (imported verbatim in the build container by
-  ``scripts/make_golden.py``; outputs committed in ``tests/golden/``).
+  ``scripts/make_golden_matrices.py``; outputs committed in ``tests/golden/matrices.npz``).
 * The Stan programs, Stan's L-BFGS / NUTS and cvxopt's QP are third-party
   natives that are absent from the reference tree and from this image
   (pystan==2.19.1.1, cvxopt).  The reference ships no test or golden vector

@@ -7,7 +7,7 @@ this image.  Restated from the published algorithm (Stan reference manual "Optim
 Wright alg. 3.5/3.6, 7.4) with Stan's defaults as the reference passes them:
 history 5, init_alpha 1e-3, tol_obj 1e-12, tol_rel_obj 1e4, tol_grad 1e-8, tol_rel_grad 1e7, tol_param 1e-8,
 Wolfe c1=1e-4 c2=0.9, minAlpha 1e-12, <=20 line-search iterations.  **Parity unpinned**: no Stan here to diff
-against; the CUDA driver (csrc/map_lbfgs.cu) implements the same statement and is compared with this file.
+against; the CUDA driver (csrc/lbfgs.cu) implements the same statement and is compared with this file.
 
 The objective is f = -log_prob(jacobian=False).
 """

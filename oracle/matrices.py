@@ -12,8 +12,8 @@ Follows ``bayes_drt/matrices.py``:
 
 The reference's Toeplitz shortcut (matrices.py:145-242) only changes *which*
 entries are integrated, not their values, so the oracle always integrates every
-entry.  Pinned against the reference itself through tests/golden/matrices_*.npz
-(made by scripts/make_golden.py, which imports the reference verbatim).
+entry.  Pinned against the reference itself through tests/golden/matrices.npz
+(made by scripts/make_golden_matrices.py, which imports the reference verbatim).
 """
 import numpy as np
 
