@@ -16,7 +16,7 @@ SYMBOLS = [
     'bdrt_version', 'bdrt_ctx_create', 'bdrt_ctx_destroy', 'bdrt_last_error', 'bdrt_launch_count',
     'bdrt_build_A', 'bdrt_build_L', 'bdrt_build_M', 'bdrt_num_params', 'bdrt_num_outputs', 'bdrt_logpost_grad',
     'bdrt_lbfgs_default_opts', 'bdrt_map_lbfgs', 'bdrt_newton_default_opts', 'bdrt_map_newton',
-    'bdrt_nuts_default_opts', 'bdrt_nuts', 'bdrt_constrain', 'bdrt_qp_bound', 'bdrt_ridge_default_opts',
+    'bdrt_nuts_default_opts', 'bdrt_nuts', 'bdrt_constrain', 'bdrt_summarize', 'bdrt_qp_bound', 'bdrt_ridge_default_opts',
     'bdrt_ridge_fit', 'bdrt_peak_fp64',
 ]
 

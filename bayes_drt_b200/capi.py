@@ -221,6 +221,21 @@ class SeriesProblem:
         return d
 
 
+def summarize(draws, percentiles=(), want_mean=True, device=None):
+    """Posterior mean and percentiles (np.percentile semantics, linear interpolation) of draws [G, S, P] over the S axis.
+    Returns (mean [G, P] or None, quant [nq, G, P] or None)."""
+    ctx = context(device)
+    draws = f64(draws, ctx.device)
+    if draws.dim() != 3:
+        raise ValueError('draws must be [G, S, P]')
+    G, S, P = draws.shape
+    probs = (C.c_double * max(len(percentiles), 1))(*[float(p) / 100.0 for p in percentiles])
+    mean = torch.empty((G, P), dtype=torch.float64, device=ctx.device) if want_mean else None
+    quant = torch.empty((len(percentiles), G, P), dtype=torch.float64, device=ctx.device) if len(percentiles) else None
+    ctx.check(ctx.lib.bdrt_summarize(ctx._h, ptr(draws), G, S, P, probs, len(percentiles), ptr(mean), ptr(quant)))
+    return mean, quant
+
+
 def qp_bound(P, q, lb, device=None):
     ctx = context(device)
     P, q, lb = f64(P, ctx.device), f64(q, ctx.device), f64(lb, ctx.device)

@@ -1,0 +1,107 @@
+// On-device posterior summaries of HMC draws: per-parameter mean and percentiles.
+//
+// Replaces the numpy reductions the reference applies to StanFit4Model draws: np.mean(axis=0) in
+// Inverter._extract_parameter (bayes_drt/inversion.py:2514-2519) and np.percentile(axis=0) (default 'linear'
+// interpolation) in coef_percentile / predict_Z / predict_sigma (:2560, :2702, :3096).
+//
+// Layout: draws [G, S, P] (G = spectra, S = merged post-warm-up draws of all chains, P = parameters, row-major).
+// HBM-bound: every draw is read exactly once (S * P * 8 bytes per spectrum; 0.79 MB at S = 400, P = 246).  One CTA
+// takes 32 consecutive parameters of one spectrum: rows are read coalesced (32 x 8 B = 256 B contiguous) and transposed
+// into shared memory, then every warp sorts columns with a bitonic network (S padded to a power of two with +inf) and
+// reads the percentiles off the sorted column; the mean is accumulated in the original order of the draws.
+#include "common.cuh"
+
+#define SUM_COLS 32
+#define SUM_THREADS 256
+
+__global__ void __launch_bounds__(SUM_THREADS)
+summarize_kernel(const double* __restrict__ draws, int G, int S, int P, int S2, const double* __restrict__ probs, int nq,
+                 double* __restrict__ mean, double* __restrict__ quant) {
+  extern __shared__ __align__(16) double sm[];  // [SUM_COLS][S2 + 1]
+  const int ld = S2 + 1;
+  const int tiles = (P + SUM_COLS - 1) / SUM_COLS;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (long long t = blockIdx.x; t < (long long)G * tiles; t += gridDim.x) {
+    const int g = (int)(t / tiles), p0 = (int)(t % tiles) * SUM_COLS;
+    const int pc = lane + p0;
+    const double* base = draws + (long long)g * S * P;
+    __syncthreads();
+    // coalesced load + transpose: warp w reads rows w, w + 8, ...; lane = column
+    for (int s = warp; s < S2; s += SUM_THREADS / 32)
+      sm[lane * ld + s] = (s < S && pc < P) ? base[(long long)s * P + pc] : INFINITY;
+    __syncthreads();
+    // each warp handles columns warp, warp + 8, ...
+    for (int c = warp; c < SUM_COLS; c += SUM_THREADS / 32) {
+      if (p0 + c >= P) continue;  // warp-uniform
+      double* col = sm + c * ld;
+      double acc = 0.0;
+      for (int s = lane; s < S; s += 32) acc += col[s];
+      acc = warp_sum(acc);
+      // bitonic sort of col[0 .. S2)
+      for (int k = 2; k <= S2; k <<= 1) {
+        for (int j = k >> 1; j > 0; j >>= 1) {
+          for (int i = lane; i < S2; i += 32) {
+            const int l = i ^ j;
+            if (l > i) {
+              const double a = col[i], b = col[l];
+              const bool up = (i & k) == 0;
+              if ((a > b) == up) {
+                col[i] = b;
+                col[l] = a;
+              }
+            }
+          }
+          __syncwarp();
+        }
+      }
+      if (lane == 0 && mean) mean[(long long)g * P + p0 + c] = acc / S;
+      // np.percentile(..., interpolation='linear'): virtual index q (S - 1)
+      for (int q = lane; q < nq; q += 32) {
+        const double h = probs[q] * (S - 1);
+        int lo = (int)floor(h);
+        lo = lo < 0 ? 0 : (lo > S - 1 ? S - 1 : lo);
+        const int hi = lo + 1 > S - 1 ? S - 1 : lo + 1;
+        const double fr = h - lo;
+        // numpy's lerp: a + (b - a) * t for t < 0.5, b - (b - a) * (1 - t) otherwise
+        const double a = col[lo], b = col[hi];
+        const double v = fr < 0.5 ? a + (b - a) * fr : b - (b - a) * (1.0 - fr);
+        quant[((long long)q * G + g) * P + p0 + c] = v;
+      }
+      __syncwarp();
+    }
+  }
+}
+
+// draws [G, S, P] (device); probs_host [nq] in [0, 1] (host); mean [G, P] (device, may be NULL); quant [nq, G, P] (device,
+// may be NULL when nq == 0).
+extern "C" int bdrt_summarize(bdrt_ctx* ctx, const double* draws, int G, int S, int P, const double* probs_host, int nq,
+                              double* mean, double* quant) {
+  if (!ctx) return BDRT_E_NULL;
+  if (!draws || (nq > 0 && (!probs_host || !quant))) BDRT_FAIL(ctx, BDRT_E_NULL, "bdrt_summarize: null pointer");
+  if (G < 0 || S < 1 || P < 1 || nq < 0 || nq > 64) BDRT_FAIL(ctx, BDRT_E_SIZE, "bdrt_summarize: bad sizes");
+  for (int q = 0; q < nq; ++q)
+    if (!(probs_host[q] >= 0.0 && probs_host[q] <= 1.0))
+      BDRT_FAIL(ctx, BDRT_E_SIZE, "Percentiles must be in the range [0, 100]");  // numpy's message
+  if (G == 0) return BDRT_OK;
+  int S2 = 1;
+  while (S2 < S) S2 <<= 1;
+  const size_t smem = (size_t)SUM_COLS * (S2 + 1) * sizeof(double);
+  if (smem > (size_t)ctx->smem_optin)
+    BDRT_FAIL(ctx, BDRT_E_SMEM, "bdrt_summarize: %d draws per parameter exceed the shared-memory sort (max %d)", S,
+              (int)(ctx->smem_optin / (SUM_COLS * sizeof(double))) / 2);
+  int rc = bdrt_ws_reserve(ctx, 64 * sizeof(double));
+  if (rc) return rc;
+  double* dprobs = (double*)ctx->ws;
+  if (nq) BDRT_CUDA(ctx, cudaMemcpyAsync(dprobs, probs_host, nq * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+  BDRT_CUDA(ctx, cudaFuncSetAttribute(summarize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const long long tiles = (long long)G * ((P + SUM_COLS - 1) / SUM_COLS);
+  int per_sm = (int)((size_t)ctx->smem_per_sm / (smem + 1024));
+  if (per_sm < 1) per_sm = 1;
+  if (per_sm > 8) per_sm = 8;
+  long long grid = (long long)ctx->sm_count * per_sm;
+  if (grid > tiles) grid = tiles;
+  summarize_kernel<<<(int)grid, SUM_THREADS, smem, ctx->stream>>>(draws, G, S, P, S2, dprobs, nq, mean, quant);
+  ctx->launches++;
+  BDRT_CUDA(ctx, cudaGetLastError());
+  return BDRT_OK;
+}

@@ -353,8 +353,9 @@ class Inverter:
         cons = prob.constrain(r['draws'].reshape(B * chains * samples, D), spec=spec).reshape(
             B, chains * samples, prob.P)
         draws = prob.split_outputs(cons)
-        # posterior mean over the merged chains (Inverter._extract_parameter, inversion.py:2514-2519)
-        point = {k: v.mean(dim=1) for k, v in draws.items()}
+        # posterior mean over the merged chains (Inverter._extract_parameter, inversion.py:2514-2519), reduced on device
+        pm, _ = capi.summarize(cons, device=self.device)
+        point = prob.split_outputs(pm)
         stats = {k: r[k] for k in ('stepsize', 'n_leapfrog', 'n_divergent', 'n_maxdepth', 'accept')}
         return dict(point=point, opt=None, draws=draws if keep_draws else None, stats=stats)
 
@@ -465,12 +466,23 @@ class Inverter:
     # ------------------------------------------------------------------------------------------------------------
     # post-fit queries
     # ------------------------------------------------------------------------------------------------------------
+    def _pct(self, draws, percentile):
+        """np.percentile(draws, percentile, axis=1) of [B, S, P] (or [B, S]) draws, on device (bdrt_summarize)."""
+        d3 = draws if draws.dim() == 3 else draws[:, :, None]
+        q = capi.summarize(d3.contiguous(), percentiles=(percentile,), want_mean=False, device=self.device)[1][0]
+        return q if draws.dim() == 3 else q[:, 0]
+
     def coef_percentile(self, distribution_name, percentile):
         """inversion.py:2547-2566: per-coefficient np.percentile (linear interpolation) of the merged draws."""
         if self.fit_type != 'bayes' or self._sample_result is None:
             raise ValueError('Percentile prediction is only available for bayes_fit')
-        x = self._sample_result['x']
-        q = torch.quantile(x, percentile / 100.0, dim=1, interpolation='linear') * self._Z_scale[:, None]
+        names = list(self.distribution_fits.keys())
+        key = 'x' if len(names) == 1 else ('xs' if self.distributions[distribution_name]['dist_type'] == 'series' else
+                                            ('xp' if 'xp2' not in self._sample_result else
+                                             f"xp{self.distributions[distribution_name].get('order', 1)}"))
+        q = self._pct(self._sample_result[key], percentile)
+        s = self._Z_scale[:, None]
+        q = q / s if self.distributions[distribution_name]['dist_type'] == 'parallel' else q * s
         return self._ret(q)
 
     def predict_distribution(self, name=None, eval_tau=None, percentile=None, time=None):
@@ -518,8 +530,7 @@ class Inverter:
             if include_offsets:
                 Zr = Zr + (self._sample_result['Rinf'][..., None] * s)
                 Zi = Zi + 2 * np.pi * fd * (self._sample_result['induc'][..., None] * s)
-            Zp = torch.complex(torch.quantile(Zr, percentile / 100.0, dim=1),
-                               torch.quantile(Zi, percentile / 100.0, dim=1))
+            Zp = torch.complex(self._pct(Zr, percentile), self._pct(Zi, percentile))
             return self._ret(Zp)
         Zp = None
         for name in names:
@@ -554,7 +565,7 @@ class Inverter:
             if self.fit_type != 'bayes' or self._sample_result is None:
                 raise ValueError('Percentile prediction is only available for bayes_fit results')
             arr = (self._sample_result['x'] * self._Z_scale[:, None, None]).sum(dim=2) * np.pi ** 0.5 / eps
-            rp = torch.quantile(arr, percentile / 100.0, dim=1)
+            rp = self._pct(arr, percentile)
         return float(rp[0]) if self._single else rp
 
     def predict_sigma(self, frequencies=None, percentile=None, times=None):
@@ -567,7 +578,7 @@ class Inverter:
         if percentile is not None:
             if self.fit_type != 'bayes' or self._sample_result is None:
                 raise ValueError('Percentile prediction is only available for bayes_fit')
-            st = torch.quantile(self._sample_result['sigma_tot'], percentile / 100.0, dim=1) * self._Z_scale[:, None]
+            st = self._pct(self._sample_result['sigma_tot'], percentile) * self._Z_scale[:, None]
         else:
             st = torch.as_tensor(self.error_fit['sigma_tot'], device=self.device).reshape(-1, 2 * len(self.f_train))
         nf = len(self.f_train)

@@ -200,6 +200,14 @@ int bdrt_num_outputs(const bdrt_series_data* data);
 int bdrt_constrain(bdrt_ctx* ctx, const bdrt_series_data* data, const double* u, const int* spec, int n,
                    double* out);
 
+/* Posterior summaries of (constrained) draws, on device: replaces np.mean(axis=0) in Inverter._extract_parameter
+ * (inversion.py:2514-2519) and np.percentile(axis=0) (linear interpolation) in coef_percentile / predict_Z /
+ * predict_sigma (inversion.py:2560, :2702, :3096).
+ * draws [G, S, P]: G groups (spectra), S merged draws, P parameters; probs_host [nq] HOST array of probabilities in
+ * [0, 1] (percentile / 100, nq <= 64); outputs mean [G, P] and quant [nq, G, P] (either may be NULL). */
+int bdrt_summarize(bdrt_ctx* ctx, const double* draws, int G, int S, int P, const double* probs_host, int nq,
+                   double* mean, double* quant);
+
 /* ---- hyper-parametric ridge: replaces cvxopt.solvers.qp inside Inverter._convex_opt (inversion.py:1043-1067)
  *      and the hyper-lambda loop of Inverter.ridge_fit (inversion.py:489-753) ---------------------------------- */
 /* Batched bound-constrained strictly convex QP   min 1/2 x'Px + q'x  s.t. x >= lb.

@@ -1,0 +1,41 @@
+"""GPU: on-device posterior summaries (bdrt_summarize) against numpy -- the reductions the reference applies to Stan's
+draws: np.mean(axis=0) (inversion.py:2514-2519) and np.percentile(axis=0), linear interpolation (:2560, :2702, :3096)."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize('G,S,P', [(3, 400, 246), (1, 1, 5), (2, 37, 33), (5, 800, 64), (2, 1000, 7), (4, 512, 32)])
+def test_summarize_matches_numpy(G, S, P):
+    from bayes_drt_b200 import capi
+    rng = np.random.RandomState(G * 1000 + S + P)
+    x = rng.standard_normal((G, S, P)) * np.exp(rng.uniform(-3, 3, (1, 1, P)))
+    x[0, :, 0] = 1.0  # ties
+    pcts = (0, 2.5, 25, 50, 97.5, 99.9, 100)
+    mean, quant = capi.summarize(torch.tensor(x), percentiles=pcts)
+    assert np.allclose(mean.cpu().numpy(), x.mean(axis=1), rtol=1e-12, atol=1e-14)
+    want = np.percentile(x, pcts, axis=1)  # [nq, G, P]
+    assert np.array_equal(quant.cpu().numpy(), want) or np.max(np.abs(quant.cpu().numpy() - want)) <= 1e-15 * np.abs(want).max()
+    m2, q2 = capi.summarize(torch.tensor(x), percentiles=(), want_mean=True)
+    assert q2 is None and torch.equal(m2, mean)
+
+
+def test_summarize_errors_and_large_batch():
+    from bayes_drt_b200 import capi
+    from bayes_drt_b200._lib import BdrtError
+    with pytest.raises(BdrtError, match='range'):
+        capi.summarize(torch.zeros(1, 4, 3, dtype=torch.float64), percentiles=(101,))
+    with pytest.raises(BdrtError, match='shared-memory'):
+        capi.summarize(torch.zeros(1, 5000, 3, dtype=torch.float64), percentiles=(50,))
+    with pytest.raises(ValueError):
+        capi.summarize(torch.zeros(4, 3, dtype=torch.float64))
+    # more tiles than resident CTAs; median of an arithmetic progression per column
+    G, S, P = 600, 400, 40
+    x = torch.arange(S, dtype=torch.float64, device='cuda')[None, :, None] * torch.ones(G, 1, P, dtype=torch.float64, device='cuda')
+    x = x[:, torch.randperm(S, device='cuda'), :] + torch.arange(G, dtype=torch.float64, device='cuda')[:, None, None]
+    mean, quant = capi.summarize(x.contiguous(), percentiles=(50, 100))
+    assert torch.allclose(quant[0], (S - 1) / 2 + torch.arange(G, dtype=torch.float64, device='cuda')[:, None].expand(G, P))
+    assert torch.equal(quant[1][:, 0], S - 1 + torch.arange(G, dtype=torch.float64, device='cuda'))
+    assert torch.allclose(mean, quant[0])
