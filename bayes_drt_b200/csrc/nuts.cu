@@ -82,7 +82,9 @@ nuts_kernel(BdrtModel m, bdrt_nuts_opts o, const double* __restrict__ U0, double
   const double* Zs = m.Z;
   long long n_grad = 0;
 
-  // leapfrog of the active end (V_ZQ, V_ZP, V_ZG); returns lp at the new point
+  // leapfrog of the active end (V_ZQ, V_ZP, V_ZG); returns lp at the new point and the kinetic energy of the new
+  // momentum (accumulated in the second half-step: one pass over the inverse metric less per leaf)
+  double kin_new = 0.0;
   auto leapfrog = [&](double eps) -> double {
     double *q = v[V_ZQ], *p = v[V_ZP], *g = v[V_ZG];
     const double* mi = v[V_MINV];
@@ -94,7 +96,13 @@ nuts_kernel(BdrtModel m, bdrt_nuts_opts o, const double* __restrict__ U0, double
     __syncwarp();
     const double lp = engine_eval<TOEP, ND, FAST>(m, sm, true, q, g, Zs, 1);
     ++n_grad;
-    for (int i = lane; i < D; i += 32) p[i] = fma(0.5 * eps, g[i], p[i]);
+    double ks = 0.0;
+    for (int i = lane; i < D; i += 32) {
+      const double pi = fma(0.5 * eps, g[i], p[i]);
+      p[i] = pi;
+      ks = fma(mi[i] * pi, pi, ks);
+    }
+    kin_new = 0.5 * warp_sum(ks);
     __syncwarp();
     return lp;
   };
@@ -153,7 +161,7 @@ nuts_kernel(BdrtModel m, bdrt_nuts_opts o, const double* __restrict__ U0, double
         __syncwarp();
         const double H0 = -s_lp + kinetic(v[V_ZP]);
         const double lp1 = leapfrog(eps);
-        double h = -lp1 + kinetic(v[V_ZP]);
+        double h = -lp1 + kin_new;
         if (isnan(h)) h = INFINITY;
         const double dH = H0 - h;
         const double thr = log(0.8);
@@ -220,7 +228,7 @@ nuts_kernel(BdrtModel m, bdrt_nuts_opts o, const double* __restrict__ U0, double
         for (int leaf = 0; leaf < n_leaves; ++leaf) {
           z_lp = leapfrog(dir * eps);
           ++n_leap;
-          double h = -z_lp + kinetic(v[V_ZP]);
+          double h = -z_lp + kin_new;
           if (isnan(h)) h = INFINITY;
           if (h - H0 > 1000.0) divergent = true;
           const double w = H0 - h;

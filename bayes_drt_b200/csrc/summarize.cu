@@ -6,7 +6,7 @@
 //
 // Layout: draws [G, S, P] (G = spectra, S = merged post-warm-up draws of all chains, P = parameters, row-major).
 // HBM-bound: every draw is read exactly once (S * P * 8 bytes per spectrum; 0.79 MB at S = 400, P = 246).  One CTA
-// takes 32 consecutive parameters of one spectrum: rows are read coalesced (32 x 8 B = 256 B contiguous) and transposed
+// takes up to 32 consecutive parameters of one spectrum: rows are read coalesced (256 B contiguous) and transposed
 // into shared memory, then every warp sorts columns with a bitonic network (S padded to a power of two with +inf) and
 // reads the percentiles off the sorted column; the mean is accumulated in the original order of the draws.
 #include "common.cuh"
@@ -15,23 +15,24 @@
 #define SUM_THREADS 256
 
 __global__ void __launch_bounds__(SUM_THREADS)
-summarize_kernel(const double* __restrict__ draws, int G, int S, int P, int S2, const double* __restrict__ probs, int nq,
-                 double* __restrict__ mean, double* __restrict__ quant) {
-  extern __shared__ __align__(16) double sm[];  // [SUM_COLS][S2 + 1]
+summarize_kernel(const double* __restrict__ draws, int G, int S, int P, int S2, int cols,
+                 const double* __restrict__ probs, int nq, double* __restrict__ mean, double* __restrict__ quant) {
+  extern __shared__ __align__(16) double sm[];  // [cols][S2 + 1], cols = parameters per tile (power of two <= 32)
   const int ld = S2 + 1;
-  const int tiles = (P + SUM_COLS - 1) / SUM_COLS;
+  const int tiles = (P + cols - 1) / cols;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int lc = threadIdx.x % cols, lr = threadIdx.x / cols, rows_per_pass = SUM_THREADS / cols;
   for (long long t = blockIdx.x; t < (long long)G * tiles; t += gridDim.x) {
-    const int g = (int)(t / tiles), p0 = (int)(t % tiles) * SUM_COLS;
-    const int pc = lane + p0;
+    const int g = (int)(t / tiles), p0 = (int)(t % tiles) * cols;
+    const int pc = lc + p0;
     const double* base = draws + (long long)g * S * P;
     __syncthreads();
-    // coalesced load + transpose: warp w reads rows w, w + 8, ...; lane = column
-    for (int s = warp; s < S2; s += SUM_THREADS / 32)
-      sm[lane * ld + s] = (s < S && pc < P) ? base[(long long)s * P + pc] : INFINITY;
+    // coalesced load + transpose: consecutive threads read consecutive parameters of one draw
+    for (int s = lr; s < S2; s += rows_per_pass)
+      sm[lc * ld + s] = (s < S && pc < P) ? base[(long long)s * P + pc] : INFINITY;
     __syncthreads();
     // each warp handles columns warp, warp + 8, ...
-    for (int c = warp; c < SUM_COLS; c += SUM_THREADS / 32) {
+    for (int c = warp; c < cols; c += SUM_THREADS / 32) {
       if (p0 + c >= P) continue;  // warp-uniform
       double* col = sm + c * ld;
       double acc = 0.0;
@@ -85,22 +86,24 @@ extern "C" int bdrt_summarize(bdrt_ctx* ctx, const double* draws, int G, int S, 
   if (G == 0) return BDRT_OK;
   int S2 = 1;
   while (S2 < S) S2 <<= 1;
-  const size_t smem = (size_t)SUM_COLS * (S2 + 1) * sizeof(double);
+  int cols = SUM_COLS;  // fewer parameters per tile for long chains, so that the columns still fit in shared memory
+  while (cols > 1 && (size_t)cols * (S2 + 1) * sizeof(double) > (size_t)ctx->smem_optin / 2) cols >>= 1;
+  const size_t smem = (size_t)cols * (S2 + 1) * sizeof(double);
   if (smem > (size_t)ctx->smem_optin)
     BDRT_FAIL(ctx, BDRT_E_SMEM, "bdrt_summarize: %d draws per parameter exceed the shared-memory sort (max %d)", S,
-              (int)(ctx->smem_optin / (SUM_COLS * sizeof(double))) / 2);
+              (int)(ctx->smem_optin / sizeof(double)) / 2);
   int rc = bdrt_ws_reserve(ctx, 64 * sizeof(double));
   if (rc) return rc;
   double* dprobs = (double*)ctx->ws;
   if (nq) BDRT_CUDA(ctx, cudaMemcpyAsync(dprobs, probs_host, nq * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
   BDRT_CUDA(ctx, cudaFuncSetAttribute(summarize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  const long long tiles = (long long)G * ((P + SUM_COLS - 1) / SUM_COLS);
+  const long long tiles = (long long)G * ((P + cols - 1) / cols);
   int per_sm = (int)((size_t)ctx->smem_per_sm / (smem + 1024));
   if (per_sm < 1) per_sm = 1;
   if (per_sm > 8) per_sm = 8;
   long long grid = (long long)ctx->sm_count * per_sm;
   if (grid > tiles) grid = tiles;
-  summarize_kernel<<<(int)grid, SUM_THREADS, smem, ctx->stream>>>(draws, G, S, P, S2, dprobs, nq, mean, quant);
+  summarize_kernel<<<(int)grid, SUM_THREADS, smem, ctx->stream>>>(draws, G, S, P, S2, cols, dprobs, nq, mean, quant);
   ctx->launches++;
   BDRT_CUDA(ctx, cudaGetLastError());
   return BDRT_OK;

@@ -7,7 +7,7 @@ import torch
 pytestmark = pytest.mark.gpu
 
 
-@pytest.mark.parametrize('G,S,P', [(3, 400, 246), (1, 1, 5), (2, 37, 33), (5, 800, 64), (2, 1000, 7), (4, 512, 32)])
+@pytest.mark.parametrize('G,S,P', [(3, 400, 246), (1, 1, 5), (2, 37, 33), (5, 800, 64), (2, 1000, 7), (4, 512, 32), (2, 4000, 9)])
 def test_summarize_matches_numpy(G, S, P):
     from bayes_drt_b200 import capi
     rng = np.random.RandomState(G * 1000 + S + P)
@@ -28,7 +28,7 @@ def test_summarize_errors_and_large_batch():
     with pytest.raises(BdrtError, match='range'):
         capi.summarize(torch.zeros(1, 4, 3, dtype=torch.float64), percentiles=(101,))
     with pytest.raises(BdrtError, match='shared-memory'):
-        capi.summarize(torch.zeros(1, 5000, 3, dtype=torch.float64), percentiles=(50,))
+        capi.summarize(torch.zeros(1, 20000, 3, dtype=torch.float64), percentiles=(50,))
     with pytest.raises(ValueError):
         capi.summarize(torch.zeros(4, 3, dtype=torch.float64))
     # more tiles than resident CTAs; median of an arithmetic progression per column
