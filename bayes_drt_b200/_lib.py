@@ -9,7 +9,7 @@ import os
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, 'libbdrt.so')
+LIB_PATH = os.environ.get('BDRT_LIB') or os.path.join(_HERE, 'libbdrt.so')  # BDRT_LIB: A/B timing of library builds
 
 # symbols declared in include/bdrt.h (tests check that every one is exported)
 SYMBOLS = [

@@ -212,10 +212,15 @@ __device__ inline void engine_load(const BdrtModel& m, double* sm, long long spe
 //   nact/snap: optional CTA-wide "slots still working" counter; *snap receives its value at a point where no warp can
 //           be modifying it (between the first and last barrier), so every warp of the CTA reads the same value.
 // Returns lp (non-finite lp or gradient entries must be checked by the caller).
-template <int TOEP, int ND, int FAST>
+// Template parameters: TOEP resident-operand layout; MK model kind (0 Series family, 1 Parallel, 2 Series-Parallel,
+// 3 Series-2Parallel: fixes the number of distributions and which of them are parallel at compile time); FAST
+// register-tiled per-slot phases.
+template <int TOEP, int MK, int FAST>
 __device__ inline double engine_eval(const BdrtModel& m, double* sm, bool active, const double* u, double* grad,
                                      const double* Zs, int jacobian, const volatile int* nact = nullptr,
                                      int* snap = nullptr) {
+  constexpr int ND = MK == 0 ? 1 : MK;
+  auto is_par = [](int dd) { return MK == 1 || dd >= 1; };  // distribution dd contributes Z_p = 1 / (A x)
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int slot = warp;
   const int Nf = m.Nf, bw = m.bw, nfp = m.nfp;
@@ -617,7 +622,7 @@ __device__ inline double engine_eval(const BdrtModel& m, double* sm, bool active
 #pragma unroll
       for (int dd = 0; dd < ND; ++dd) {
         const double* sZd = rowZ(dd);
-        if (m.d[dd].par) {
+        if (is_par(dd)) {
           // Z_p = 1 / (Y' + i Y'')  (Parallel_modelcode.txt:46-50, Series-Parallel :63-66)
           Yr[dd] = sZd[n];
           Yi[dd] = sZd[nfp + n];
@@ -651,7 +656,7 @@ __device__ inline double engine_eval(const BdrtModel& m, double* sm, bool active
 #pragma unroll
       for (int dd = 0; dd < ND; ++dd) {
         double* sVd = rowX(dd);
-        if (m.d[dd].par) {  // d lp / d Y
+        if (is_par(dd)) {  // d lp / d Y
           const double i2 = iM[dd] * iM[dd];
           const double c1 = (Yi[dd] * Yi[dd] - Yr[dd] * Yr[dd]) * i2, c2 = 2.0 * Yr[dd] * Yi[dd] * i2;
           sVd[n] = v_re * c1 + v_im * c2;
@@ -827,8 +832,8 @@ static inline BdrtPlan bdrt_plan(const bdrt_ctx* ctx, const BdrtModel& m, int Dp
   return pl;
 }
 
-// launch KERNEL<TOEP, ND, FAST>: Toeplitz- or dense-resident operands, one (Series) or two (Series-Parallel)
-// distributions, register-tiled or generic per-slot phases (FAST only exists with TOEP)
+// launch KERNEL<TOEP, MK, FAST>: Toeplitz- or dense-resident operands, model kind, register-tiled or generic per-slot
+// phases (FAST only exists with TOEP)
 #define BDRT_LAUNCH_ONE(ctx, KERNEL, T, N, F, grid, smem, ...)                                                       \
   do {                                                                                                               \
     BDRT_CUDA(ctx, cudaFuncSetAttribute(KERNEL<T, N, F>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(smem))); \
@@ -836,7 +841,8 @@ static inline BdrtPlan bdrt_plan(const bdrt_ctx* ctx, const BdrtModel& m, int Dp
   } while (0)
 #define BDRT_LAUNCH_ND(ctx, m, KERNEL, T, F, grid, smem, ...)                                \
   do {                                                                                       \
-    if ((m).ND == 1) BDRT_LAUNCH_ONE(ctx, KERNEL, T, 1, F, grid, smem, __VA_ARGS__);         \
+    if ((m).ND == 1 && !(m).d[0].par) BDRT_LAUNCH_ONE(ctx, KERNEL, T, 0, F, grid, smem, __VA_ARGS__); \
+    else if ((m).ND == 1) BDRT_LAUNCH_ONE(ctx, KERNEL, T, 1, F, grid, smem, __VA_ARGS__);    \
     else if ((m).ND == 2) BDRT_LAUNCH_ONE(ctx, KERNEL, T, 2, F, grid, smem, __VA_ARGS__);    \
     else BDRT_LAUNCH_ONE(ctx, KERNEL, T, 3, F, grid, smem, __VA_ARGS__);                     \
   } while (0)

@@ -141,7 +141,7 @@ __device__ __forceinline__ void two_loop(const double* S, const double* Y, const
 
 }  // namespace
 
-template <int TOEP, int ND, int FAST>
+template <int TOEP, int MK, int FAST>
 __global__ void __launch_bounds__(NTHREADS, TOEP ? 2 : 1)
 lbfgs_kernel(BdrtModel m, bdrt_lbfgs_opts o, double* __restrict__ U, double* lp_out, int* iters_out, int* neval_out,
              int* status_out, int* queue, double* hist, double* gvec, int nvec_smem, int Dpad) {
@@ -178,7 +178,7 @@ lbfgs_kernel(BdrtModel m, bdrt_lbfgs_opts o, double* __restrict__ U, double* lp_
 
   // f(xn) -> f, gn = grad f ; returns false when not finite
   auto feval = [&](double& f) -> bool {
-    const double lp = engine_eval<TOEP, ND, FAST>(m, sm, true, xn, gn, Zs, 0);
+    const double lp = engine_eval<TOEP, MK, FAST>(m, sm, true, xn, gn, Zs, 0);
     ++neval;
     int fin = isfinite(lp);
     for (int i = lane; i < D; i += 32) {
@@ -420,7 +420,7 @@ lbfgs_kernel(BdrtModel m, bdrt_lbfgs_opts o, double* __restrict__ U, double* lp_
       if (lane == 0) atomicSub((int*)n_active, 1);
     }
     do {
-      engine_eval<TOEP, ND, FAST>(m, sm, false, nullptr, nullptr, nullptr, 0, n_active, &snap);
+      engine_eval<TOEP, MK, FAST>(m, sm, false, nullptr, nullptr, nullptr, 0, n_active, &snap);
     } while (snap != 0);
     if (!per_spec) break;
   }

@@ -265,7 +265,7 @@ int bdrt_model_prepare(bdrt_ctx* ctx, const bdrt_series_data* d, BdrtModel* m, s
 // ---------------------------------------------------------------------------------------------------------------------
 // log_prob + gradient test hook
 // ---------------------------------------------------------------------------------------------------------------------
-template <int TOEP, int ND, int FAST>
+template <int TOEP, int MK, int FAST>
 __global__ void __launch_bounds__(NTHREADS, TOEP ? 2 : 1)
 logpost_kernel(BdrtModel m, const double* u, const int* spec, int n_cols, int jacobian, double* lp, double* grad,
                int cta_per_spec) {
@@ -278,7 +278,7 @@ logpost_kernel(BdrtModel m, const double* u, const int* spec, int n_cols, int ja
       const int c = gidx * NSLOT + warp;
       const bool active = c < n_cols;
       const int b = active ? (spec ? spec[c] : c % m.B) : 0;
-      const double v = engine_eval<TOEP, ND, FAST>(m, sm, active, u + (long long)c * m.D, grad + (long long)c * m.D,
+      const double v = engine_eval<TOEP, MK, FAST>(m, sm, active, u + (long long)c * m.D, grad + (long long)c * m.D,
                                    m.Z + (long long)b * m.N2, jacobian);
       if (active && lane == 0) lp[c] = v;
     }
@@ -303,7 +303,7 @@ logpost_kernel(BdrtModel m, const double* u, const int* spec, int n_cols, int ja
         c = nf ? found[nf - 1] : c;
         const bool active = warp < nf;
         const int col = active ? found[warp] : 0;
-        const double v = engine_eval<TOEP, ND, FAST>(m, sm, active, u + (long long)col * m.D, grad + (long long)col * m.D,
+        const double v = engine_eval<TOEP, MK, FAST>(m, sm, active, u + (long long)col * m.D, grad + (long long)col * m.D,
                                      m.Z + (long long)b * m.N2, jacobian);
         if (active && lane == 0) lp[col] = v;
       }

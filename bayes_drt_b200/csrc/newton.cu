@@ -63,7 +63,7 @@ __device__ void chol_solve_packed(double* Hp, int n, double* r, volatile int* fl
 
 }  // namespace
 
-template <int TOEP, int ND, int FAST>
+template <int TOEP, int MK, int FAST>
 __global__ void __launch_bounds__(NTHREADS, 1)
 newton_kernel(BdrtModel m, bdrt_newton_opts o, double* __restrict__ U, double* lp_out, double* gnorm_out, int* iters_out,
               int* neval_out, double* scratch, long long scratch_per_cta, int chol_in_smem, int Dpad) {
@@ -98,7 +98,7 @@ newton_kernel(BdrtModel m, bdrt_newton_opts o, double* __restrict__ U, double* l
     bool stop = false;
     // f, g at u (slot 0 evaluates; the other slots idle through the barriers)
     {
-      const double lp = engine_eval<TOEP, ND, FAST>(m, sm, warp == 0, u, g, Zs, 0);
+      const double lp = engine_eval<TOEP, MK, FAST>(m, sm, warp == 0, u, g, Zs, 0);
       ++neval;
       if (tid == 0) s_val[0] = -lp;
       __syncthreads();
@@ -136,7 +136,7 @@ newton_kernel(BdrtModel m, bdrt_newton_opts o, double* __restrict__ U, double* l
           __syncwarp();
           h = (u[j] + h) - u[j];
         }
-        engine_eval<TOEP, ND, FAST>(m, sm, act, my_u, my_g, Zs, 0);
+        engine_eval<TOEP, MK, FAST>(m, sm, act, my_u, my_g, Zs, 0);
         if (act) {
           const double ih = 1.0 / h;
           for (int i = lane; i < D; i += 32) H[(long long)j * Dpad + i] = (-my_g[i] - g[i]) * ih;
@@ -193,7 +193,7 @@ newton_kernel(BdrtModel m, bdrt_newton_opts o, double* __restrict__ U, double* l
         // remember the jump flags (gtry is about to be overwritten by the gradient)
         for (int i = tid; i < D; i += NTHREADS) step[i] = gtry[i];
         __syncthreads();
-        const double lp = engine_eval<TOEP, ND, FAST>(m, sm, warp == 0, utry, gtry, Zs, 0);
+        const double lp = engine_eval<TOEP, MK, FAST>(m, sm, warp == 0, utry, gtry, Zs, 0);
         ++neval;
         if (tid == 0) s_val[0] = -lp;
         __syncthreads();

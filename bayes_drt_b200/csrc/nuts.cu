@@ -56,7 +56,7 @@ __device__ __forceinline__ double logaddexp(double a, double b) {
 
 }  // namespace
 
-template <int TOEP, int ND, int FAST>
+template <int TOEP, int MK, int FAST>
 __global__ void __launch_bounds__(NTHREADS, TOEP ? 2 : 1)
 nuts_kernel(BdrtModel m, bdrt_nuts_opts o, const double* __restrict__ U0, double* draws, double* stepsize_out,
             long long* nleap_out, int* ndiv_out, int* nmax_out, double* accept_out, int* queue, double* gvec,
@@ -94,7 +94,7 @@ nuts_kernel(BdrtModel m, bdrt_nuts_opts o, const double* __restrict__ U0, double
       q[i] = fma(eps * mi[i], pi, q[i]);
     }
     __syncwarp();
-    const double lp = engine_eval<TOEP, ND, FAST>(m, sm, true, q, g, Zs, 1);
+    const double lp = engine_eval<TOEP, MK, FAST>(m, sm, true, q, g, Zs, 1);
     ++n_grad;
     double ks = 0.0;
     for (int i = lane; i < D; i += 32) {
@@ -131,7 +131,7 @@ nuts_kernel(BdrtModel m, bdrt_nuts_opts o, const double* __restrict__ U0, double
     vcopy(v[V_SQ], U0 + wi * D);
     for (int i = lane; i < D; i += 32) v[V_MINV][i] = 1.0;
     __syncwarp();
-    double s_lp = engine_eval<TOEP, ND, FAST>(m, sm, true, v[V_SQ], v[V_SG], Zs, 1);
+    double s_lp = engine_eval<TOEP, MK, FAST>(m, sm, true, v[V_SQ], v[V_SG], Zs, 1);
     ++n_grad;
     bool bad = !isfinite(s_lp);
 
@@ -403,7 +403,7 @@ nuts_kernel(BdrtModel m, bdrt_nuts_opts o, const double* __restrict__ U0, double
     }
     int snap;
     do {
-      engine_eval<TOEP, ND, FAST>(m, sm, false, nullptr, nullptr, nullptr, 0, n_active, &snap);
+      engine_eval<TOEP, MK, FAST>(m, sm, false, nullptr, nullptr, nullptr, 0, n_active, &snap);
     } while (snap != 0);
     if (!per_spec) break;
   }
