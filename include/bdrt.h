@@ -222,7 +222,7 @@ typedef struct {
   double xtol;      /* 1e-3 */
   double hl_beta;   /* 2.5 */
   double lambda_0;  /* 1e-2 */
-  double reg_ord[3];/* fraction of each derivative order (reg_ord=2 -> {0,0,1}) */
+  double reg_ord[3];/* fraction of each derivative order (reg_ord=2 -> 0, 0, 1) */
   double L1_penalty;/* 0 */
   double epsilon;   /* basis epsilon (only enters the L1 penalty vector) */
   int fit_inductance;

@@ -37,3 +37,30 @@ def test_no_cpu_fallback():
         pytest.skip('GPU present')
     with pytest.raises(_lib.BdrtError):
         _lib.Context()
+
+
+def _struct_fields(hdr, name):
+    """field names of `typedef struct { ... } name;` in declaration order"""
+    body = re.search(r'typedef struct \{([^{}]*)\}\s*' + name + r'\s*;', hdr, re.S).group(1)
+    body = re.sub(r'/\*.*?\*/', '', body, flags=re.S)
+    out = []
+    for stmt in body.split(';'):
+        stmt = stmt.strip()
+        if not stmt:
+            continue
+        # "const double* A" | "double sigma_min, ups_alpha" | "double reg_ord[3]" | "int Nf"
+        names = stmt.split(None, 1)[1] if not stmt.startswith(('const', 'unsigned', 'long long')) else \
+            re.sub(r'^(const\s+\w+(\s+\w+)?\s*\*?|unsigned long long|long long)\s*', '', stmt)
+        for nm in names.split(','):
+            out.append(re.sub(r'[\*\s]|\[.*\]', '', nm))
+    return out
+
+
+def test_ctypes_structs_mirror_the_header():
+    """The ctypes Structures the Python host passes by reference must have the header's fields in the header's order."""
+    from bayes_drt_b200 import _lib
+    hdr = open(os.path.join(ROOT, 'include', 'bdrt.h')).read()
+    for cname, cls in (('bdrt_series_data', _lib.SeriesData), ('bdrt_lbfgs_opts', _lib.LbfgsOpts),
+                       ('bdrt_newton_opts', _lib.NewtonOpts), ('bdrt_nuts_opts', _lib.NutsOpts),
+                       ('bdrt_ridge_opts', _lib.RidgeOpts)):
+        assert _struct_fields(hdr, cname) == [f[0] for f in cls._fields_], cname
