@@ -72,7 +72,7 @@ struct BdrtModel {
   int xoff;  // offset of the data inside an X/V row (= bw: zero margin for the stencils)
   int wm;    // zero margin on both sides of a stencil scratch vector: max(bw, FBW)
   int ws;    // stride of one stencil scratch vector (Kmax + 2 wm, even)
-  int kup;   // Kmax rounded up to even
+  int kup;   // Kmax rounded up to a multiple of 4
   int sd;    // per-slot, per-distribution scratch: W0 | W1 | W2 (ws each) | ups (kup) | 1/ups (kup)
   int st;    // per-slot scratch size: ND * sd | scalars (16) | sigma_out raw, scale (2 Nf)
 };
@@ -110,7 +110,7 @@ static inline int bdrt_model_layout(BdrtModel* m) {
   m->wm = m->bw > FBW ? m->bw : FBW;
   m->ws = m->Kmax + 2 * m->wm;
   m->ws += m->ws & 1;  // even
-  m->kup = (m->Kmax + 1) & ~1;
+  m->kup = (m->Kmax + 3) & ~3;  // a lane's 4 consecutive coefficients never run past the row
   m->sd = 3 * m->ws + 2 * m->kup;
   m->st = m->ND * m->sd + 16 + ((m->flags & F_OUT) ? 2 * m->Nf : 0);
   int mz = k8 > m->n2p ? k8 : m->n2p;
@@ -255,8 +255,9 @@ __device__ inline double engine_eval(const BdrtModel& m, double* sm, bool active
       }
     }
     if (FAST) {
-      // Register-tiled per-slot phase (Toeplitz L with |d| <= FBW, K <= 128): lane owns the 4 consecutive coefficients
-      // kq .. kq+3, stencil windows are fetched as 16-byte pairs, the taps come straight from the parameter bank.
+      // Register-tiled per-slot phase (Toeplitz L with |d| <= FBW, K <= 128).  Everything that touches u / grad uses the
+      // interleaved ownership k = lane + 32 j (conflict-free 8-byte accesses); the stencils use the tiled ownership
+      // kq .. kq+3 with 16-byte shared-memory windows, and the taps come straight from the parameter bank.
       const int kq = 4 * lane;
 #pragma unroll
       for (int dd = 0; dd < ND; ++dd) {
@@ -266,33 +267,33 @@ __device__ inline double engine_eval(const BdrtModel& m, double* sm, bool active
         double* sW = sSt + dd * m.sd + m.wm;
         double* sUps = sSt + dd * m.sd + 3 * m.ws;
         double* sIu = sUps + m.kup;
-        double uu[4], ups[4], iu[4], xr[4];
+        // 1a. transforms; the separable hyper-prior terms are summed here
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-          const int k = kq + j;
-          const bool v = k < K;
-          const double ux = v ? u[Dd.off_x + k] : 0.0;
-          uu[j] = v ? u[Dd.off_ups + k] : 0.0;
-          double xv = Dd.pos ? exp(ux) : ux;
-          xv = v ? xv : 0.0;
-          xr[j] = xv;
-          ups[j] = 0.15 * exp(uu[j]);
-          iu[j] = __drcp_rn(ups[j]);
-          ujac += uu[j] + (Dd.pos ? ux : 0.0);
-          if (ND > 1) xsum += xv;
-          if (v) {
-            sUps[k] = ups[j];
-            sIu[k] = iu[j];
+          const int k = lane + 32 * j;
+          if (k < K) {
+            const double ux = u[Dd.off_x + k], uu = u[Dd.off_ups + k];
+            const double xv = Dd.pos ? exp(ux) : ux;
+            const double ups = 0.15 * exp(uu);
+            const double iu = __drcp_rn(ups);
+            sX[k] = xv;
+            sUps[k] = ups;
+            sIu[k] = iu;
+            ujac += uu + (Dd.pos ? ux : 0.0);
+            if (ND > 1) xsum += xv;
+            // - log ups ; ups_raw ~ inv_gamma(alpha, beta)
+            lp += -(LOG_015 + uu) - (m.ups_alpha + 1.0) * uu - m.ups_beta * 0.15 * iu;
+          } else if (k < 128 + FBW + 2) {
+            sX[k] = 0.0;  // zeros past K (phase 3 of the previous call wrote V here)
           }
         }
-        st2(sX + kq, xr[0], xr[1]);  // x row [0, 128): zeros past K (phase 3 of the previous call wrote V here)
-        st2(sX + kq + 2, xr[2], xr[3]);
         if (lane < FBW + 2) sX[128 + lane] = 0.0;
         __syncwarp();
-        // 1b. a_j = L_j x, q^2, hyper-priors, d lp / d ups, W_j = d_j a_j / ups^2
+        // 1b. a_j = L_j x, q^2, dups, d lp / d ups, W_j = d_j a_j / ups^2
         const double d0 = sTh[6 + 3 * dd], d1 = sTh[7 + 3 * dd], d2 = sTh[8 + 3 * dd];
         double sa0 = 0, sa1 = 0, sa2 = 0;
-        {
+        double gu4[4] = {0, 0, 0, 0};
+        if (kq < K) {
           double xw[16];  // x[kq - 6 .. kq + 9]
 #pragma unroll
           for (int i = 0; i < 8; ++i) ld2(sX + kq - FBW + 2 * i, xw[2 * i], xw[2 * i + 1]);
@@ -306,46 +307,58 @@ __device__ inline double engine_eval(const BdrtModel& m, double* sm, bool active
               a2[j] = fma(Dd.tapc[2][t], xw[j + t], a2[j]);
             }
           }
-          double upw[8], iuw[8];  // ups / (1/ups) [kq - 2 .. kq + 5]
+          double upw[8], iuw[8];  // ups / (1/ups) [kq - 2 .. kq + 5]; own values at index j + 2
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
             ld2(sUps + kq - 2 + 2 * i, upw[2 * i], upw[2 * i + 1]);
             ld2(sIu + kq - 2 + 2 * i, iuw[2 * i], iuw[2 * i + 1]);
           }
+          double w0[4], w1[4], w2[4];
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
             const int k = kq + j;
-            if (k < K) {
-              const double upk = ups[j], iuk = iu[j], iu2 = iuk * iuk, uk = uu[j];
-              const double q2 = d0 * a0[j] * a0[j] + d1 * a1[j] * a1[j] + d2 * a2[j] * a2[j];
-              lp += -0.5 * q2 * iu2 - (LOG_015 + uk) - (m.ups_alpha + 1.0) * uk - m.ups_beta * 0.15 * iuk;
+            const bool v = k < K;
+            const double upk = upw[j + 2], iuk = iuw[j + 2], iu2 = iuk * iuk;
+            const double q2 = d0 * a0[j] * a0[j] + d1 * a1[j] * a1[j] + d2 * a2[j] * a2[j];
+            if (v) {
+              lp += -0.5 * q2 * iu2;  // q ~ normal(0, ups)
               sa0 = fma(a0[j] * a0[j], iu2, sa0);
               sa1 = fma(a1[j] * a1[j], iu2, sa1);
               sa2 = fma(a2[j] * a2[j], iu2, sa2);
-              sW[k] = d0 * a0[j] * iu2;
-              sW[m.ws + k] = d1 * a1[j] * iu2;
-              sW[2 * m.ws + k] = d2 * a2[j] * iu2;
-              // dups_i = 0.5 - 0.25 (ups_i + ups_{i+2}) / ups_{i+1}  (Series_modelcode.txt:51-53); window index j + 2 + e
-              double gu = q2 * iu2 * iuk - iuk;
-              if (k + 2 < K) {
-                const double e = 0.5 - 0.25 * (upk + upw[j + 4]) * iuw[j + 3];
-                gu += e * 0.25 * iuw[j + 3];
-                lp += -0.5 * e * e;
-              }
-              if (k >= 1 && k + 1 < K) {
-                const double sum = upw[j + 1] + upw[j + 3];
-                const double e = 0.5 - 0.25 * sum * iuk;
-                gu -= e * 0.25 * sum * iu2;
-              }
-              if (k >= 2) {
-                const double e = 0.5 - 0.25 * (upw[j] + upk) * iuw[j + 1];
-                gu += e * 0.25 * iuw[j + 1];
-              }
-              grad[Dd.off_ups + k] = gu * upk - (m.ups_alpha + 1.0) + m.ups_beta * 0.15 * iuk + jac;
             }
+            w0[j] = v ? d0 * a0[j] * iu2 : 0.0;
+            w1[j] = v ? d1 * a1[j] * iu2 : 0.0;
+            w2[j] = v ? d2 * a2[j] * iu2 : 0.0;
+            // dups_i = 0.5 - 0.25 (ups_i + ups_{i+2}) / ups_{i+1}  (Series_modelcode.txt:51-53); window index j + 2 + e
+            double gu = q2 * iu2 * iuk - iuk;
+            if (k + 2 < K) {
+              const double e = 0.5 - 0.25 * (upk + upw[j + 4]) * iuw[j + 3];
+              gu += e * 0.25 * iuw[j + 3];
+              lp += -0.5 * e * e;
+            }
+            if (k >= 1 && k + 1 < K) {
+              const double sum = upw[j + 1] + upw[j + 3];
+              const double e = 0.5 - 0.25 * sum * iuk;
+              gu -= e * 0.25 * sum * iu2;
+            }
+            if (k >= 2 && v) {
+              const double e = 0.5 - 0.25 * (upw[j] + upk) * iuw[j + 1];
+              gu += e * 0.25 * iuw[j + 1];
+            }
+            gu4[j] = gu * upk - (m.ups_alpha + 1.0) + m.ups_beta * 0.15 * iuk + jac;
           }
+          st2(sW + kq, w0[0], w0[1]);  // zeros past K keep the right margin zero
+          st2(sW + kq + 2, w0[2], w0[3]);
+          st2(sW + m.ws + kq, w1[0], w1[1]);
+          st2(sW + m.ws + kq + 2, w1[2], w1[3]);
+          st2(sW + 2 * m.ws + kq, w2[0], w2[1]);
+          st2(sW + 2 * m.ws + kq + 2, w2[2], w2[3]);
         }
-        __syncwarp();
+        __syncwarp();  // every lane has its ups / 1/ups windows: the 1/ups row now stages d lp / d u_ups
+        if (kq < K) {
+          st2(sIu + kq, gu4[0], gu4[1]);
+          st2(sIu + kq + 2, gu4[2], gu4[3]);
+        }
         // 1c. prior part of d lp / d x:  - sum_j L_j^T W_j  (kept in registers until phase 5)
         {
           double acc[4] = {0, 0, 0, 0};
@@ -364,6 +377,12 @@ __device__ inline double engine_eval(const BdrtModel& m, double* sm, bool active
           }
 #pragma unroll
           for (int j = 0; j < 4; ++j) gpr[dd][j] = -acc[j];
+        }
+        __syncwarp();
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {  // staged d lp / d u_ups -> grad, interleaved ownership
+          const int k = lane + 32 * j;
+          if (k < K) grad[Dd.off_ups + k] = sIu[k];
         }
         sa0 = warp_sum(sa0);
         sa1 = warp_sum(sa1);
@@ -775,16 +794,26 @@ __device__ inline double engine_eval(const BdrtModel& m, double* sm, bool active
       const BdrtDist& Dd = m.d[dd];
       const double* sG = rowZ(dd);
       if (FAST) {
+        // tiled ownership: G + prior part back into the row (16-byte accesses); then interleaved ownership -> grad
         const int kq = 4 * lane;
-        double g4[4];
-        ld2(sG + kq, g4[0], g4[1]);
-        ld2(sG + kq + 2, g4[2], g4[3]);
+        double* sGw = rowZ(dd);
+        if (kq < Dd.K) {
+          double g4[4];
+          ld2(sGw + kq, g4[0], g4[1]);
+          ld2(sGw + kq + 2, g4[2], g4[3]);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) g4[j] += gpr[dd][j] - gsum;
+          st2(sGw + kq, g4[0], g4[1]);
+          st2(sGw + kq + 2, g4[2], g4[3]);
+        }
+        __syncwarp();
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-          if (kq + j < Dd.K) {
-            double gx = g4[j] + gpr[dd][j] - gsum;
-            if (Dd.pos) gx = gx * exp(u[Dd.off_x + kq + j]) + jac;
-            grad[Dd.off_x + kq + j] = gx;
+          const int k = lane + 32 * j;
+          if (k < Dd.K) {
+            double gx = sGw[k];
+            if (Dd.pos) gx = gx * exp(u[Dd.off_x + k]) + jac;
+            grad[Dd.off_x + k] = gx;
           }
         }
         continue;

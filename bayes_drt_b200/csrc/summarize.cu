@@ -5,10 +5,13 @@
 // interpolation) in coef_percentile / predict_Z / predict_sigma (:2560, :2702, :3096).
 //
 // Layout: draws [G, S, P] (G = spectra, S = merged post-warm-up draws of all chains, P = parameters, row-major).
-// HBM-bound: every draw is read exactly once (S * P * 8 bytes per spectrum; 0.79 MB at S = 400, P = 246).  One CTA
-// takes up to 32 consecutive parameters of one spectrum: rows are read coalesced (256 B contiguous) and transposed
-// into shared memory, then every warp sorts columns with a bitonic network (S padded to a power of two with +inf) and
-// reads the percentiles off the sorted column; the mean is accumulated in the original order of the draws.
+// Every draw is read from HBM exactly once (S * P * 8 bytes per spectrum; 0.79 MB at S = 400, P = 246).  One CTA takes
+// up to 32 consecutive parameters of one spectrum: rows are read coalesced (256 B contiguous) and transposed into
+// shared memory, then every warp sorts columns with a bitonic network (S padded to a power of two with +inf) and reads
+// the percentiles off the sorted column; the mean is accumulated in the original order of the draws.
+// Measured (B200, 4000 x 400 x 246 draws = 3.15 GB): 24.6 ms = 129 GB/s -- bound by the shared-memory sort, not by HBM
+// (2 % of the measured copy bandwidth); it is < 0.1 % of the sampling time that produces the draws, so the sort has
+// not been moved into registers yet.
 #include "common.cuh"
 
 #define SUM_COLS 32
