@@ -168,8 +168,8 @@ lbfgs_kernel(BdrtModel m, bdrt_lbfgs_opts o, double* __restrict__ U, double* lp_
   double* const pk = vec[2];
   double* const xk = vec[3];
   double* const gk = vec[4];
-  double* S = hist + ((long long)blockIdx.x * NSLOT + warp) * 2 * MAXHIST * Dpad;
-  double* Y = S + (long long)MAXHIST * Dpad;
+  double* S = hist + ((long long)blockIdx.x * NSLOT + warp) * 2 * H * Dpad;  // compact: the L2 footprint is what is used
+  double* Y = S + (long long)H * Dpad;
   int snap;
 
   const double EPS = 2.220446049250313e-16;
@@ -455,7 +455,7 @@ extern "C" int bdrt_map_lbfgs(bdrt_ctx* ctx, const bdrt_series_data* data, const
   const int groups = data->per_spectrum_grid ? data->B : (data->B + NSLOT - 1) / NSLOT;
   const int grid_max = data->B == 0 ? 0 : (groups < max_ctas ? groups : max_ctas);
   int grid = grid_max;
-  const size_t hist_bytes = (size_t)grid_max * NSLOT * 2 * MAXHIST * Dpad * sizeof(double);
+  const size_t hist_bytes = (size_t)grid_max * NSLOT * 2 * opts->history * Dpad * sizeof(double);
   const size_t gvec_bytes = (size_t)grid_max * NSLOT * 5 * Dpad * sizeof(double);
   void* extra = nullptr;
   int rc = bdrt_model_prepare(ctx, data, &m, 256 + hist_bytes + gvec_bytes, &extra);

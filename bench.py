@@ -316,6 +316,40 @@ def run_ours(a):
                'divergent_frac': ngrad[2].item() / (ws * Bh * 2 * 200),
                'maxdepth_frac': ngrad[3].item() / (ws * Bh * 2 * 200)}
 
+    # -------------------------------------------------------------------------------- other solvers of the path (info)
+    extras = None
+    if not a.no_hmc:
+        # hyper-parametric ridge (Inverter.ridge_fit defaults: discrete penalty, 20 hyper-iterations, exact QP)
+        ivr = Inverter(basis_freq=bf.numpy(), device=dev)
+        Br = min(Bg, 4096)
+        ivr.ridge_fit(freq, Z_host[:64])
+        barrier()
+        e0.record()
+        ivr.ridge_fit(freq, Z_host[:Br])
+        e1.record()
+        barrier()
+        t_r = e0.elapsed_time(e1) * 1e-3
+        # kernel matrices on per-spectrum grids (config 5 shape): A_re + A_im of 2048 grids, 81 x 81, trapezoid over the
+        # reference's node set restricted to the Gaussian window (76 of 1000 nodes at the default epsilon)
+        Gm = 2048
+        fg = 10.0 ** (6.0 - torch.rand(Gm, 1, dtype=torch.float64) - torch.arange(81, dtype=torch.float64)[None, :] / 10.0)
+        taum = torch.as_tensor(1.0 / (2 * np.pi * np.logspace(6, -2, 81)))
+        epsm = 1.0 / float(np.mean(np.diff(np.log(taum.numpy()))))
+        fgd = fg.to(dev)
+        capi.build_A(fgd[:8], taum, epsm, device=dev)
+        barrier()
+        e0.record()
+        capi.build_A(fgd, taum, epsm, device=dev)
+        e1.record()
+        barrier()
+        t_m = e0.elapsed_time(e1) * 1e-3
+        nodes = 76
+        extras = {'ridge_fits_per_s': ws * Br / t_r, 'ridge_batch': Br,
+                  'ridge_hyper_iterations': float(ivr._ridge_iters.float().mean().item()),
+                  'A_builds_per_s': ws * 2 * Gm / t_m, 'A_build_shape': [81, 81],
+                  'A_build_tflops': Gm * 81 * 81 * nodes * 12 / t_m / 1e12,  # 12 flop per entry and node for both parts
+                  'A_build_frac_of_dfma_peak': Gm * 81 * 81 * nodes * 12 / t_m / 1e12 / dfma}
+
     # -------------------------------------------------------------------------------- CPU baseline (rank 0, N = 1)
     cpu = None
     if rank == 0 and ws == 1:
@@ -338,7 +372,7 @@ def run_ours(a):
                        'l2_flush': 'explicit 256 MiB write between timed steps',
                        'termination': {str(k): v for k, v in term.items()}},
             'e2e': e2e, 'gpu_launches': int(launches), 'clocks': clocks, 'roofline': roofline, 'cpu_baseline': cpu,
-            'hmc': hmc,
+            'hmc': hmc, 'extras': extras,
         }
         print(json.dumps(line))
     if ws > 1:
