@@ -9,14 +9,62 @@
 // up to 32 consecutive parameters of one spectrum: rows are read coalesced (256 B contiguous) and transposed into
 // shared memory, then every warp sorts columns with a bitonic network (S padded to a power of two with +inf) and reads
 // the percentiles off the sorted column; the mean is accumulated in the original order of the draws.
-// Measured (B200, 4000 x 400 x 246 draws = 3.15 GB): 24.6 ms = 129 GB/s -- bound by the shared-memory sort, not by HBM
-// (2 % of the measured copy bandwidth); it is < 0.1 % of the sampling time that produces the draws, so the sort has
-// not been moved into registers yet.
+// The sort runs in registers (warp_sort: shuffles between lanes, compare-exchanges inside a lane) for columns of up to
+// 1024 draws.  The first version sorted in shared memory: 24.6 ms for 4000 x 400 x 246 draws (3.15 GB) = 129 GB/s.
 #include "common.cuh"
 
 #define SUM_COLS 32
 #define SUM_THREADS 256
 
+// Bitonic sort of 32 * E values held by one warp, E per lane, entirely in registers: lane owns the sorted positions
+// lane * E .. lane * E + E - 1 at the end.  Stages that pair positions inside a lane are register compare-exchanges,
+// stages that pair lanes are one shuffle per element.
+template <int E>
+__device__ __forceinline__ void warp_sort(double (&v)[E], int lane) {
+#pragma unroll
+  for (int k = 2; k <= 32 * E; k <<= 1) {
+#pragma unroll
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      if (j >= E) {  // partner position is in lane ^ (j / E), same register
+        const int dl = j / E;
+        const bool up = ((lane * E) & k) == 0;            // k >= 2E here: the direction is uniform over the lane
+        const bool keep_min = ((lane & dl) == 0) == up;
+#pragma unroll
+        for (int r = 0; r < E; ++r) {
+          const double o = __shfl_xor_sync(0xffffffffu, v[r], dl);
+          v[r] = keep_min ? fmin(v[r], o) : fmax(v[r], o);
+        }
+      } else {  // both positions in this lane
+#pragma unroll
+        for (int r = 0; r < E; ++r) {
+          const int l = r ^ j;
+          if (l > r) {
+            const bool up = (((lane * E) + r) & k) == 0;
+            const double a = v[r], b = v[l];
+            const double lo = fmin(a, b), hi = fmax(a, b);
+            v[r] = up ? lo : hi;
+            v[l] = up ? hi : lo;
+          }
+        }
+      }
+    }
+  }
+}
+
+template <int E>
+__device__ __forceinline__ void sort_column(double* col, int lane) {
+  double v[E];
+#pragma unroll
+  for (int r = 0; r < E; ++r) v[r] = col[r * 32 + lane];  // any input order will do: conflict-free interleaved read
+  warp_sort<E>(v, lane);
+  __syncwarp();
+#pragma unroll
+  for (int r = 0; r < E; ++r) col[lane * E + r] = v[r];
+  __syncwarp();
+}
+
+// E = S2 / 32 values per lane for the register sort (0: shared-memory sort for longer columns)
+template <int E>
 __global__ void __launch_bounds__(SUM_THREADS)
 summarize_kernel(const double* __restrict__ draws, int G, int S, int P, int S2, int cols,
                  const double* __restrict__ probs, int nq, double* __restrict__ mean, double* __restrict__ quant) {
@@ -41,21 +89,25 @@ summarize_kernel(const double* __restrict__ draws, int G, int S, int P, int S2, 
       double acc = 0.0;
       for (int s = lane; s < S; s += 32) acc += col[s];
       acc = warp_sum(acc);
-      // bitonic sort of col[0 .. S2)
-      for (int k = 2; k <= S2; k <<= 1) {
-        for (int j = k >> 1; j > 0; j >>= 1) {
-          for (int i = lane; i < S2; i += 32) {
-            const int l = i ^ j;
-            if (l > i) {
-              const double a = col[i], b = col[l];
-              const bool up = (i & k) == 0;
-              if ((a > b) == up) {
-                col[i] = b;
-                col[l] = a;
+      // sort col[0 .. S2): in registers when the column fits (S2 <= 1024), else with a shared-memory bitonic network
+      __syncwarp();
+      if (E > 0) sort_column<(E > 0 ? E : 1)>(col, lane);
+      else {
+        for (int k = 2; k <= S2; k <<= 1) {
+          for (int j = k >> 1; j > 0; j >>= 1) {
+            for (int i = lane; i < S2; i += 32) {
+              const int l = i ^ j;
+              if (l > i) {
+                const double a = col[i], b = col[l];
+                const bool up = (i & k) == 0;
+                if ((a > b) == up) {
+                  col[i] = b;
+                  col[l] = a;
+                }
               }
             }
+            __syncwarp();
           }
-          __syncwarp();
         }
       }
       if (lane == 0 && mean) mean[(long long)g * P + p0 + c] = acc / S;
@@ -87,7 +139,7 @@ extern "C" int bdrt_summarize(bdrt_ctx* ctx, const double* draws, int G, int S, 
     if (!(probs_host[q] >= 0.0 && probs_host[q] <= 1.0))
       BDRT_FAIL(ctx, BDRT_E_SIZE, "Percentiles must be in the range [0, 100]");  // numpy's message
   if (G == 0) return BDRT_OK;
-  int S2 = 1;
+  int S2 = 32;  // at least one value per lane
   while (S2 < S) S2 <<= 1;
   int cols = SUM_COLS;  // fewer parameters per tile for long chains, so that the columns still fit in shared memory
   while (cols > 1 && (size_t)cols * (S2 + 1) * sizeof(double) > (size_t)ctx->smem_optin / 2) cols >>= 1;
@@ -99,14 +151,26 @@ extern "C" int bdrt_summarize(bdrt_ctx* ctx, const double* draws, int G, int S, 
   if (rc) return rc;
   double* dprobs = (double*)ctx->ws;
   if (nq) BDRT_CUDA(ctx, cudaMemcpyAsync(dprobs, probs_host, nq * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
-  BDRT_CUDA(ctx, cudaFuncSetAttribute(summarize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+#define SUM_LAUNCH(EE)                                                                                          \
+  do {                                                                                                         \
+    BDRT_CUDA(ctx, cudaFuncSetAttribute(summarize_kernel<EE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+    summarize_kernel<EE><<<(int)grid, SUM_THREADS, smem, ctx->stream>>>(draws, G, S, P, S2, cols, dprobs, nq, mean, quant); \
+  } while (0)
   const long long tiles = (long long)G * ((P + cols - 1) / cols);
   int per_sm = (int)((size_t)ctx->smem_per_sm / (smem + 1024));
   if (per_sm < 1) per_sm = 1;
   if (per_sm > 8) per_sm = 8;
   long long grid = (long long)ctx->sm_count * per_sm;
   if (grid > tiles) grid = tiles;
-  summarize_kernel<<<(int)grid, SUM_THREADS, smem, ctx->stream>>>(draws, G, S, P, S2, cols, dprobs, nq, mean, quant);
+  switch (S2) {
+    case 32: SUM_LAUNCH(1); break;
+    case 64: SUM_LAUNCH(2); break;
+    case 128: SUM_LAUNCH(4); break;
+    case 256: SUM_LAUNCH(8); break;
+    case 512: SUM_LAUNCH(16); break;
+    case 1024: SUM_LAUNCH(32); break;
+    default: SUM_LAUNCH(0); break;
+  }
   ctx->launches++;
   BDRT_CUDA(ctx, cudaGetLastError());
   return BDRT_OK;
