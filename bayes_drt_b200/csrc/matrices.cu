@@ -200,7 +200,7 @@ extern "C" int bdrt_build_A(bdrt_ctx* ctx, const double* freq, int n_grids, int 
                             double k_ct, double* A_re, double* A_im) {
   if (!ctx) return BDRT_E_NULL;
   if (!freq || !tau || (!A_re && !A_im)) BDRT_FAIL(ctx, BDRT_E_NULL, "bdrt_build_A: null pointer");
-  if (n_grids < 0 || Nf <= 0 || K <= 0 || n_grids > 65535) BDRT_FAIL(ctx, BDRT_E_SIZE, "bdrt_build_A: bad sizes");
+  if (n_grids < 0 || Nf <= 0 || K <= 0) BDRT_FAIL(ctx, BDRT_E_SIZE, "bdrt_build_A: bad sizes");
   if (!(epsilon > 0.0)) BDRT_FAIL(ctx, BDRT_E_SIZE, "bdrt_build_A: epsilon must be > 0");
   if (kernel != BDRT_KERNEL_DRT && kernel != BDRT_KERNEL_DDT) BDRT_FAIL(ctx, BDRT_E_MODEL, "bdrt_build_A: bad kernel id");
   if (kernel == BDRT_KERNEL_DRT && dist_type != BDRT_DIST_SERIES)
@@ -211,12 +211,16 @@ extern "C" int bdrt_build_A(bdrt_ctx* ctx, const double* freq, int n_grids, int 
     if (bc != BDRT_BC_TRANSMISSIVE && bc != BDRT_BC_BLOCKING) BDRT_FAIL(ctx, BDRT_E_MODEL, "bad bc");
   }
   if (n_grids == 0) return BDRT_OK;
-  ABuildArgs p{freq, tau, tau_per_grid ? (long long)K : 0LL, Nf, K, epsilon, kernel, dist_type, symmetry, bc, ct, k_ct,
-               A_re, A_im};
   dim3 block(TILE_M, TILE_N);
-  dim3 grid((K + TILE_M - 1) / TILE_M, (Nf + TILE_N - 1) / TILE_N, n_grids);
-  build_A_kernel<<<grid, block, 0, ctx->stream>>>(p);
-  ctx->launches++;
+  for (int g0 = 0; g0 < n_grids; g0 += 65535) {  // gridDim.z <= 65535: large batches of grids go in several launches
+    const int ng = n_grids - g0 < 65535 ? n_grids - g0 : 65535;
+    ABuildArgs p{freq + (long long)g0 * Nf, tau + (tau_per_grid ? (long long)g0 * K : 0LL), tau_per_grid ? (long long)K : 0LL,
+                 Nf, K, epsilon, kernel, dist_type, symmetry, bc, ct, k_ct,
+                 A_re ? A_re + (long long)g0 * Nf * K : nullptr, A_im ? A_im + (long long)g0 * Nf * K : nullptr};
+    dim3 grid((K + TILE_M - 1) / TILE_M, (Nf + TILE_N - 1) / TILE_N, ng);
+    build_A_kernel<<<grid, block, 0, ctx->stream>>>(p);
+    ctx->launches++;
+  }
   BDRT_CUDA(ctx, cudaGetLastError());
   return BDRT_OK;
 }
@@ -225,12 +229,17 @@ extern "C" int bdrt_build_L(bdrt_ctx* ctx, const double* freq, int n_grids, int 
                             int tau_per_grid, double epsilon, int order, double* L) {
   if (!ctx) return BDRT_E_NULL;
   if (!freq || !tau || !L) BDRT_FAIL(ctx, BDRT_E_NULL, "bdrt_build_L: null pointer");
-  if (n_grids < 0 || N <= 0 || K <= 0 || N > 65535 || n_grids > 65535) BDRT_FAIL(ctx, BDRT_E_SIZE, "bdrt_build_L: bad sizes");
+  if (n_grids < 0 || N <= 0 || K <= 0 || N > 65535) BDRT_FAIL(ctx, BDRT_E_SIZE, "bdrt_build_L: bad sizes");
   if (order < 0 || order > 3) BDRT_FAIL(ctx, BDRT_E_SIZE, "Order must be between 0 and 3");  // matrices.py:315-316
   if (n_grids == 0) return BDRT_OK;
-  dim3 grid((K + 127) / 128, N, n_grids);
-  build_L_kernel<<<grid, 128, 0, ctx->stream>>>(freq, tau, tau_per_grid ? (long long)K : 0LL, N, K, epsilon, order, L);
-  ctx->launches++;
+  for (int g0 = 0; g0 < n_grids; g0 += 65535) {
+    const int ng = n_grids - g0 < 65535 ? n_grids - g0 : 65535;
+    dim3 grid((K + 127) / 128, N, ng);
+    build_L_kernel<<<grid, 128, 0, ctx->stream>>>(freq + (long long)g0 * N, tau + (tau_per_grid ? (long long)g0 * K : 0LL),
+                                                  tau_per_grid ? (long long)K : 0LL, N, K, epsilon, order,
+                                                  L + (long long)g0 * N * K);
+    ctx->launches++;
+  }
   BDRT_CUDA(ctx, cudaGetLastError());
   return BDRT_OK;
 }
@@ -239,12 +248,16 @@ extern "C" int bdrt_build_M(bdrt_ctx* ctx, const double* freq, int n_grids, int 
                             int toeplitz, double* M) {
   if (!ctx) return BDRT_E_NULL;
   if (!freq || !M) BDRT_FAIL(ctx, BDRT_E_NULL, "bdrt_build_M: null pointer");
-  if (n_grids < 0 || K <= 0 || K > 65535 || n_grids > 65535) BDRT_FAIL(ctx, BDRT_E_SIZE, "bdrt_build_M: bad sizes");
+  if (n_grids < 0 || K <= 0 || K > 65535) BDRT_FAIL(ctx, BDRT_E_SIZE, "bdrt_build_M: bad sizes");
   if (order < 0 || order > 2) BDRT_FAIL(ctx, BDRT_E_SIZE, "Invalid order");  // matrices.py:361-362
   if (n_grids == 0) return BDRT_OK;
-  dim3 grid((K + 127) / 128, K, n_grids);
-  build_M_kernel<<<grid, 128, 0, ctx->stream>>>(freq, K, epsilon, order, toeplitz, M);
-  ctx->launches++;
+  for (int g0 = 0; g0 < n_grids; g0 += 65535) {
+    const int ng = n_grids - g0 < 65535 ? n_grids - g0 : 65535;
+    dim3 grid((K + 127) / 128, K, ng);
+    build_M_kernel<<<grid, 128, 0, ctx->stream>>>(freq + (long long)g0 * K, K, epsilon, order, toeplitz,
+                                                  M + (long long)g0 * K * K);
+    ctx->launches++;
+  }
   BDRT_CUDA(ctx, cudaGetLastError());
   return BDRT_OK;
 }

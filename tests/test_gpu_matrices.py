@@ -71,3 +71,19 @@ def test_build_A_errors():
         capi.build_A(f, t, 1.0, kernel='DDT', dist_type='parallel', bc='blocking', ct=True)  # matrices.py:42-43
     with pytest.raises(BdrtError):
         capi.build_L(f, t, 1.0, 4)
+
+
+def test_build_A_more_grids_than_one_launch():
+    """> 65535 grids (gridDim.z limit) go in several launches; every grid equals the single-grid result."""
+    from bayes_drt_b200 import capi
+    G = 70000
+    rng = np.random.RandomState(0)
+    f = torch.tensor(10 ** (3 - rng.uniform(0, 1, (G, 1)) - np.arange(9)[None, :] / 3))
+    tau = torch.tensor(np.logspace(-4, 0, 7))
+    A_re, A_im = capi.build_A(f, tau, 1.7)
+    assert tuple(A_re.shape) == (G, 9, 7)
+    for g in (0, 65534, 65535, 69999):
+        a, b = capi.build_A(f[g], tau, 1.7)
+        assert torch.equal(a, A_re[g]) and torch.equal(b, A_im[g])
+    L = capi.build_L(f, tau, 1.7, 1)
+    assert torch.equal(capi.build_L(f[69999], tau, 1.7, 1), L[69999])
