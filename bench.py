@@ -104,7 +104,7 @@ def run_reference(a):
         'e2e': {'value': value, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
         'gpu_launches': 0,
     }
-    print(json.dumps(line))
+    _emit(line)
 
 
 # ----------------------------------------------------------------------------------------------------------------------
@@ -374,12 +374,21 @@ def run_ours(a):
             'e2e': e2e, 'gpu_launches': int(launches), 'clocks': clocks, 'roofline': roofline, 'cpu_baseline': cpu,
             'hmc': hmc, 'extras': extras,
         }
-        print(json.dumps(line))
+        _emit(line)
     if ws > 1:
         dist.destroy_process_group()
 
 
+def _emit(line):
+    """The JSON line is the only thing that goes to the real stdout (libraries such as NCCL print banners to fd 1)."""
+    os.write(_REAL_STDOUT, (json.dumps(line) + '\n').encode())
+
+
 if __name__ == '__main__':
+    # everything else that is written to stdout (NCCL version banner, warnings of child processes) goes to stderr
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     args = parse()
     if args.impl == 'reference':
         run_reference(args)
