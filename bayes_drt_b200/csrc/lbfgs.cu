@@ -99,8 +99,9 @@ __device__ __forceinline__ void two_loop(const double* S, const double* Y, const
     }
   };
   auto hidx = [&](int j) { return head - 1 - j + (head - 1 - j < 0 ? H : 0); };  // j < nh <= H
-  // (prefetching the next entry into a second register buffer was measured slower: it spills under the 128-register
-  // cap of the two-CTAs-per-SM kernels, 52.9 M vs 70.6 M gradients/s)
+  // (prefetching the next entry, or just the next entry's first vector, into another register buffer was measured
+  // slower: it spills under the 128-register cap of the two-CTAs-per-SM kernels -- 52.9 M resp. 61 M vs 72 M
+  // gradients/s)
   double sa[NCC], ya[NCC];
   auto first = [&](int h, const double (&sv)[NCC], const double (&yv)[NCC]) {  // newest -> oldest
     double d = 0.0;
