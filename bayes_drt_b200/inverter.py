@@ -127,9 +127,16 @@ class Inverter:
         self._single = Zt.dim() == 1
         if self._single:
             Zt = Zt[None, :]
+        if f.dim() == 2:
+            # one grid per spectrum ([B, Nf]): every row sorted on its own
+            if self._single or tuple(f.shape) != tuple(Zt.shape):
+                raise ValueError('Length of frequencies and Z must be equal')  # inversion.py:2128-2129
+            idx = torch.argsort(f, dim=1, descending=True)
+            f = torch.gather(f, 1, idx).contiguous()
+            Zt = torch.gather(Zt.to(self.device), 1, idx.to(self.device)).contiguous()
+            return f, Zt
         if f.dim() != 1:
-            raise NotImplementedError('per-spectrum frequency grids are not implemented in Inverter yet '
-                                      '(use capi.build_A for batched grids)')
+            raise ValueError('frequencies must be [Nf] (shared grid) or [B, Nf] (one grid per spectrum)')
         if f.shape[0] != Zt.shape[1]:
             raise ValueError('Length of frequencies and Z must be equal')  # inversion.py:2128-2129
         # sort by descending frequency (inversion.py:2138-2141)
@@ -158,7 +165,17 @@ class Inverter:
         info = self.distributions[name]
         bf = info.get('basis_freq', self.basis_freq)
         fn = freq.numpy()
-        if bf is None:
+        if bf is None and fn.ndim == 2:
+            # default basis of every spectrum (inversion.py:2191-2199 applied row by row).  The penalty matrices are
+            # shared by the batch, so the rows' bases must be log-shifts of one another (same K, same spacing).
+            tmin = np.log10(1 / (2 * np.pi * fn.max(axis=1))) - 1
+            tmax = np.log10(1 / (2 * np.pi * fn.min(axis=1))) + 1
+            Ks = (10 * (tmax - tmin) + 1).astype(int)
+            if np.any(Ks != Ks[0]) or np.ptp(tmax - tmin) > 1e-9 * abs(tmax[0] - tmin[0]):
+                raise NotImplementedError('per-spectrum grids with default bases must span the same number of '
+                                          'decades (pass a shared basis_freq otherwise)')
+            tau = np.stack([np.logspace(a, b, int(Ks[0])) for a, b in zip(tmin, tmax)])
+        elif bf is None:
             tmin = np.log10(1 / (2 * np.pi * np.max(fn))) - 1
             tmax = np.log10(1 / (2 * np.pi * np.min(fn))) + 1
             tau = np.logspace(tmin, tmax, int(10 * (tmax - tmin) + 1))
@@ -166,7 +183,7 @@ class Inverter:
             tau = 1 / (2 * np.pi * np.asarray(torch.as_tensor(bf).cpu(), dtype=np.float64))
         eps = info.get('epsilon', self.epsilon)
         if eps is None:
-            eps = 1 / np.mean(np.diff(np.log(tau)))
+            eps = 1 / np.mean(np.diff(np.log(tau[0] if tau.ndim == 2 else tau)))
         info['tau'], info['epsilon'] = tau, float(eps)
         key = (name, fn.tobytes(), tau.tobytes(), float(eps), info['kernel'], info['dist_type'],
                info.get('symmetry'), info.get('bc'), info.get('ct', False), info.get('k_ct'))
@@ -176,7 +193,9 @@ class Inverter:
             A_re, A_im = capi.build_A(freq, t, eps, kernel=info['kernel'], dist_type=info['dist_type'],
                                       symmetry=info.get('symmetry') or 'planar', bc=info.get('bc') or 'transmissive',
                                       ct=info.get('ct', False), k_ct=info.get('k_ct'), device=self.device)
-            bft = torch.as_tensor(1 / (2 * np.pi * tau))
+            if tau.ndim == 2:  # L depends on ratios of the basis time constants only: the first row stands for all
+                t = t[0]
+            bft = 1 / (2 * np.pi * t)
             m.clear()
             m.update(_key=key, A_re=A_re, A_im=A_im,
                      L0=capi.build_L(bft, t, eps, 0, device=self.device),
@@ -235,6 +254,9 @@ class Inverter:
         freq, Zb = self._to_batch(frequencies, Z)
         single = self._single
         B = Zb.shape[0]
+        if freq.dim() == 2 and (init_from_ridge or outliers == 'auto'):
+            raise NotImplementedError("init_from_ridge / outliers='auto' need the ridge solver, which takes one "
+                                      "frequency grid per batch")
         ids = torch.arange(spectrum_offset, spectrum_offset + B, dtype=torch.int64, device=self.device)
         # ---- ridge initialisation and automatic outlier detection (inversion.py:1154-1187)
         ridge_init, flags = None, None
@@ -298,7 +320,7 @@ class Inverter:
                       induc_scale=float(inductance_scale), device=self.device)
         if model_type in ('Series', 'Parallel'):  # same constants (inversion.py:1714-1754)
             L = torch.stack([c['l'][0] * m['L0'], c['l'][1] * m['L1'], c['l'][2] * m['L2']])
-            prob = capi.SeriesProblem(torch.cat((m['A_re'], m['A_im'])), Zst, freq, L, outliers=bool(outliers),
+            prob = capi.SeriesProblem(torch.cat((m['A_re'], m['A_im']), dim=-2), Zst, freq, L, outliers=bool(outliers),
                                       parallel=model_type == 'Parallel',
                                       sigma_out_lambda=10.0 if outlier_lambda is None else float(outlier_lambda),
                                       sigma_out_alpha=c['sigma_out_alpha'], sigma_out_beta=1.0, **common)
@@ -311,12 +333,12 @@ class Inverter:
             x_sum_invscale = csp['x_sum_invscale']
             if model_type == 'Series-2Parallel':  # inversion.py:1961-2049
                 _, _, mp2 = self._grid(freq, par[1])
-                extra = dict(Ap2=torch.cat((mp2['A_re'], mp2['A_im'])),
+                extra = dict(Ap2=torch.cat((mp2['A_re'], mp2['A_im']), dim=-2),
                              Lp2=torch.stack([csp['lp'][j] * mp2[f'L{j}'] for j in range(3)]),
                              xp2_scale=float(self.distributions[par[1]].get('x_scale', 1)))
                 x_sum_invscale = 0.1 if mode == 'sample' else 0.0
-            prob = capi.SeriesProblem(torch.cat((m['A_re'], m['A_im'])), Zst, freq, Ls,
-                                      Ap=torch.cat((mp['A_re'], mp['A_im'])), Lp=Lp, x_sum_invscale=x_sum_invscale,
+            prob = capi.SeriesProblem(torch.cat((m['A_re'], m['A_im']), dim=-2), Zst, freq, Ls,
+                                      Ap=torch.cat((mp['A_re'], mp['A_im']), dim=-2), Lp=Lp, x_sum_invscale=x_sum_invscale,
                                       xp_scale=float(self.distributions[par[0]].get('x_scale', 1)), **extra, **common)
         self._problem = prob
         B, D, K, Nf = prob.B, prob.D, prob.K, prob.Nf
@@ -495,13 +517,30 @@ class Inverter:
         basis_tau = torch.as_tensor(info['tau'], dtype=torch.float64, device=self.device)
         et = basis_tau if eval_tau is None else torch.as_tensor(eval_tau, dtype=torch.float64, device=self.device)
         coef = self._coef_batch(name) if percentile is None else \
-            torch.as_tensor(self.coef_percentile(name, percentile), device=self.device).reshape(-1, len(basis_tau))
+            torch.as_tensor(self.coef_percentile(name, percentile), device=self.device).reshape(-1, basis_tau.shape[-1])
+        if basis_tau.dim() == 2:  # one basis per spectrum: eval_tau [T] (shared) or [B, T]
+            nb = basis_tau.shape[0]
+            coef = coef.reshape(nb, -1)
+            et = et if et.dim() == 2 else et[None, :].expand(nb, -1)
+            phi = torch.exp(-(info['epsilon'] * torch.log(et[:, :, None] / basis_tau[:, None, :])) ** 2)
+            return self._ret(self._apply(phi, coef))
         phi = torch.exp(-(info['epsilon'] * torch.log(et[:, None] / basis_tau[None, :])) ** 2)
         return self._ret(coef @ phi.T)
 
+    @staticmethod
+    def _apply(A, coef):
+        """A @ coef for coefficients [B, K] or draws [B, S, K]; A [Nf, K] (shared grid) or [B, Nf, K]."""
+        At = A.transpose(-1, -2)
+        if A.dim() == 3 and coef.dim() == 2:
+            return torch.bmm(coef[:, None, :], At)[:, 0, :]
+        return coef @ At
+
     def _pred_matrices(self, f, name):
         info = self.distributions[name]
-        return capi.build_A(f, torch.as_tensor(info['tau']), info['epsilon'], kernel=info['kernel'],
+        tau = torch.as_tensor(info['tau'])
+        if tau.dim() == 2 and f.dim() == 1:  # per-spectrum bases, one set of evaluation frequencies for all
+            f = f[None, :].expand(tau.shape[0], -1).contiguous()
+        return capi.build_A(f, tau, info['epsilon'], kernel=info['kernel'],
                             dist_type=info['dist_type'], symmetry=info.get('symmetry') or 'planar',
                             bc=info.get('bc') or 'transmissive', ct=info.get('ct', False), k_ct=info.get('k_ct'),
                             device=self.device)
@@ -525,18 +564,19 @@ class Inverter:
             A_re, A_im = self._pred_matrices(f, names[0])
             s = self._Z_scale[:, None, None]
             x = self._sample_result['x'] * s
-            Zr = x @ A_re.T
-            Zi = x @ A_im.T
+            Zr = self._apply(A_re, x)
+            Zi = self._apply(A_im, x)
             if include_offsets:
                 Zr = Zr + (self._sample_result['Rinf'][..., None] * s)
-                Zi = Zi + 2 * np.pi * fd * (self._sample_result['induc'][..., None] * s)
+                Zi = Zi + 2 * np.pi * (fd[:, None, :] if fd.dim() == 2 else fd) * \
+                    (self._sample_result['induc'][..., None] * s)
             Zp = torch.complex(self._pct(Zr, percentile), self._pct(Zi, percentile))
             return self._ret(Zp)
         Zp = None
         for name in names:
             A_re, A_im = self._pred_matrices(f, name)
             coef = self._coef_batch(name)
-            z = torch.complex(coef @ A_re.T, coef @ A_im.T)
+            z = torch.complex(self._apply(A_re, coef), self._apply(A_im, coef))
             if self.distributions[name]['dist_type'] == 'parallel':
                 z = 1.0 / z
             Zp = z if Zp is None else Zp + z
@@ -572,31 +612,56 @@ class Inverter:
         """inversion.py:3089 for the training frequencies: the fitted sigma_tot split into real / imaginary parts."""
         if self.fit_type not in ('map', 'bayes'):
             raise ValueError('Error scale prediction only available for bayes_fit and map_fit')
-        if frequencies is not None and not np.array_equal(mat.rel_round(np.asarray(frequencies), 10),
-                                                           mat.rel_round(self.f_train, 10)):
+        if frequencies is not None and not (
+                np.shape(frequencies) == np.shape(self.f_train) and
+                np.array_equal(mat.rel_round(np.ravel(frequencies), 10), mat.rel_round(np.ravel(self.f_train), 10))):
             raise NotImplementedError('predict_sigma at frequencies other than the training grid is not implemented')
         if percentile is not None:
             if self.fit_type != 'bayes' or self._sample_result is None:
                 raise ValueError('Percentile prediction is only available for bayes_fit')
             st = self._pct(self._sample_result['sigma_tot'], percentile) * self._Z_scale[:, None]
         else:
-            st = torch.as_tensor(self.error_fit['sigma_tot'], device=self.device).reshape(-1, 2 * len(self.f_train))
-        nf = len(self.f_train)
+            st = torch.as_tensor(self.error_fit['sigma_tot'], device=self.device).reshape(-1, 2 * self.f_train.shape[-1])
+        nf = self.f_train.shape[-1]
         return self._ret(st[:, :nf]), self._ret(st[:, nf:])
 
     def check_outliers(self, frequencies=None, Z=None, threshold=3.5, use_existing_fit=True, **ridge_kw):
-        """inversion.py:3313-3376, existing MAP / HMC fit branch: combined z-score of the residuals under the fitted
-        error model.  Returns indices ([n] for one spectrum, [n, 2] (spectrum, frequency) for a batch)."""
-        if self.fit_type not in ('map', 'bayes'):
-            raise NotImplementedError('check_outliers from a ridge fit needs ridge_fit (not wired up in this build)')
+        """inversion.py:3313-3376.  An existing MAP / HMC fit of the same data: combined z-score of the residuals under
+        the fitted error model.  Otherwise (no fit of this data yet, or ``use_existing_fit=False``, or a ridge fit):
+        ridge fit (``preset='Huang'`` unless one exists) and the inter-quartile rule on the residuals relative to |Z|.
+        ``frequencies`` / ``Z`` default to the training data.  Returns indices ([n] for one spectrum, [n, 2]
+        (spectrum, frequency) for a batch)."""
+        fit_exists = self.fit_type in ('ridge', 'map', 'bayes') and not self._recalc_mat
+        if frequencies is not None and Z is not None and fit_exists:
+            f_in = np.asarray(torch.as_tensor(frequencies).cpu(), dtype=np.float64)
+            Z_in = torch.as_tensor(np.asarray(Z) if not torch.is_tensor(Z) else Z).to(torch.complex128)
+            if f_in.ndim == 1 and f_in.shape == np.shape(self.f_train):  # the training data are stored sorted
+                o = np.argsort(-f_in)
+                f_in, Z_in = f_in[o], Z_in[..., torch.as_tensor(o.copy())]
+            fit_exists = f_in.shape == np.shape(self.f_train) and np.array_equal(f_in, self.f_train) and \
+                tuple(Z_in.reshape(-1).shape) == tuple(self.Z_train.reshape(-1).shape) and \
+                bool(torch.equal(Z_in.reshape(-1).to(self.device), self.Z_train.reshape(-1)))
+        elif frequencies is None or Z is None:
+            if self.fit_type not in ('ridge', 'map', 'bayes'):
+                raise ValueError('frequencies and Z must be given if the Inverter has not been fitted')
+            frequencies, Z, fit_exists = self.f_train, self.Z_train, True
+        if not (use_existing_fit and fit_exists) or self.fit_type == 'ridge':
+            if np.ndim(frequencies) != 1:
+                raise NotImplementedError('the ridge solver takes one frequency grid per batch')
+            single = torch.as_tensor(np.asarray(Z) if not torch.is_tensor(Z) else Z).dim() == 1
+            freq, Zb = self._to_batch(frequencies, Z)
+            flags = self._ridge_outlier_flags(freq, Zb, threshold, use_existing_fit and fit_exists, **ridge_kw)
+            self._single = single
+            idx = torch.nonzero(flags)
+            return idx[:, 1].cpu().numpy() if single else idx
         single = self._single
         self._single = False
         Zp = self.predict_Z(self.f_train)
         self._single = single
         err_re = Zp.real - self.Z_train.real
         err_im = Zp.imag - self.Z_train.imag
-        st = torch.as_tensor(self.error_fit['sigma_tot'], device=self.device).reshape(-1, 2 * len(self.f_train))
-        nf = len(self.f_train)
+        nf = self.f_train.shape[-1]
+        st = torch.as_tensor(self.error_fit['sigma_tot'], device=self.device).reshape(-1, 2 * nf)
         zs = torch.sqrt(((err_re / st[:, :nf]) ** 2 + (err_im / st[:, nf:]) ** 2) / 2)
         idx = torch.nonzero(zs > threshold)
         return idx[:, 1].cpu().numpy() if self._single else idx

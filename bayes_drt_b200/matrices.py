@@ -57,13 +57,26 @@ def construct_A(frequencies, part, tau=None, basis='gaussian', fit_inductance=Fa
 def construct_L(frequencies, tau=None, basis='gaussian', epsilon=1, order=1):
     if basis != 'gaussian':
         raise ValueError(f'Invalid basis {basis}. Options are gaussian')
-    if not (isinstance(order, (int, np.integer)) and 0 <= order <= 3):
-        if isinstance(order, (int, float)) and not (0 <= order <= 3):
-            raise ValueError('Order must be between 0 and 3')  # matrices.py:315-316
-        raise NotImplementedError('fractional / mixed derivative orders are not implemented')
     f = torch.as_tensor(frequencies, dtype=torch.float64)
     t = 1.0 / (2 * np.pi * f) if tau is None else torch.as_tensor(tau, dtype=torch.float64)
-    return capi.build_L(f, t, epsilon, int(order))
+    # matrices.py:278-316: a list [f0, f1, f2] mixes the 0th/1st/2nd derivative, a fractional order interpolates
+    # linearly between its two neighbouring integer orders; the integer orders come from the kernel
+    if isinstance(order, list):
+        f0, f1, f2 = order
+        mix = ((0, f0), (1, f1), (2, f2))
+    elif order in (0, 1, 2, 3):
+        return capi.build_L(f, t, epsilon, int(order))
+    elif 0 < order < 1:
+        mix = ((0, 1 - order), (1, order))
+    elif 1 < order < 2:
+        mix = ((1, 2 - order), (2, order - 1))
+    else:
+        raise ValueError('Order must be between 0 and 3')  # matrices.py:315-316
+    L = None
+    for o, w in mix:
+        Lo = capi.build_L(f, t, epsilon, o) * float(w)
+        L = Lo if L is None else L + Lo
+    return L
 
 
 def construct_M(frequencies, basis='gaussian', order=1, epsilon=1):

@@ -70,6 +70,8 @@ def ridge_fit(inv, frequencies, Z, part='both', penalty='discrete', reg_ord=2, L
 
     dev = inv.device
     freq, Zb = inv._to_batch(frequencies, Z)
+    if freq.dim() == 2:
+        raise NotImplementedError('ridge_fit takes one frequency grid per batch (per-spectrum grids: Inverter.fit)')
     inv.f_train, inv.Z_train = freq.numpy(), Zb
     Zs = inv._scale_Z(Zb, scale_Z)
     tau, eps, m = inv._grid(freq, name)

@@ -45,6 +45,9 @@ def add_case(name, freq, tau, eps, kernel='DRT', dist_type='series', symmetry='p
         for o in (0, 1, 2):
             out[f'{name}/L{o}'] = ref.construct_L(bf, tau=tau, basis='gaussian', epsilon=eps, order=o)  # inversion.py:2301-2307
             out[f'{name}/M{o}'] = ref.construct_M(bf, basis='gaussian', order=o, epsilon=eps)  # inversion.py:2296-2299
+        # third derivative, fractional and list-mixed orders (matrices.py:278-316)
+        for key, o in (('L3', 3), ('Lf0.5', 0.5), ('Lf1.25', 1.25), ('Lmix', [0.2, 0.3, 0.5])):
+            out[f'{name}/{key}'] = ref.construct_L(bf, tau=tau, basis='gaussian', epsilon=eps, order=o)
     print(name, out[f'{name}/A_re'].shape)
 
 

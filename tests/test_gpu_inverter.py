@@ -208,3 +208,82 @@ def test_save_and_load_fit_data(tmp_path):
     assert again.predict_Rp() == one.predict_Rp()
     with pytest.raises(ValueError):
         Inverter().save_fit_data()
+
+
+def _zarc_batch(deltas, seed=3):
+    """ZARC spectra on per-spectrum grids freq_b = 10**(6 - delta_b - arange(81)/10) (SURVEY 8d config 5 grids)."""
+    rng = np.random.RandomState(seed)
+    freq = 10.0 ** (6 - np.asarray(deltas)[:, None] - np.arange(81)[None, :] / 10)
+    B = len(deltas)
+    R0, R1 = rng.uniform(0.5, 2, B), rng.uniform(0.5, 2, B)
+    tau0, n = 10.0 ** rng.uniform(-4, 0, B), rng.uniform(0.6, 1.0, B)
+    Z = R0[:, None] + R1[:, None] / (1 + (2j * np.pi * freq * tau0[:, None]) ** n[:, None])
+    Z = Z + 0.0025 * R1[:, None] * (rng.randn(B, 81) + 1j * rng.randn(B, 81))
+    return freq, Z
+
+
+def test_fit_per_spectrum_frequency_grids():
+    """frequencies [B, Nf]: every spectrum on its own grid (matrices built per spectrum on the GPU) gives what the
+    spectrum gives when fitted alone on its grid through the shared-grid path."""
+    from bayes_drt_b200 import Inverter
+    freq, Z = _zarc_batch([0.0, 0.13, 0.37, 0.5, 0.82])
+    inv = Inverter()
+    inv.fit(freq, Z, mode='optimize', polish=True)
+    coef = inv.distribution_fits['DRT']['coef']
+    assert tuple(coef.shape) == (5, 101) and inv.f_train.shape == (5, 81)
+    assert tuple(np.shape(inv.distributions['DRT']['tau'])) == (5, 101)
+    # (the random start of global spectrum 0 ends in a poor local mode that the Newton polish cannot leave -- on both
+    # paths alike, which is what this test compares)
+    assert int((inv._opt_result['gnorm'] < 1e-6).sum()) >= 4
+    Zp = inv.predict_Z(inv.f_train)
+    assert tuple(Zp.shape) == (5, 81) and float((Zp.cpu() - torch.tensor(Z))[1:].abs().max()) < 0.03
+    gam = inv.predict_distribution()
+    assert tuple(gam.shape) == (5, 101)
+    rp = inv.predict_Rp()
+    s_re, s_im = inv.predict_sigma(inv.f_train)
+    assert tuple(s_re.shape) == (5, 81) and (s_re > 0).all() and (s_im > 0).all()
+    assert inv.check_outliers(threshold=3.5).shape[1] == 2
+    for b in (0, 1, 4):
+        one = Inverter()
+        one.fit(freq[b], Z[b], mode='optimize', polish=True, spectrum_offset=b)  # same global index -> same init
+        c1 = one.distribution_fits['DRT']['coef']
+        assert np.allclose(one.distributions['DRT']['tau'], inv.distributions['DRT']['tau'][b], rtol=1e-14)
+        assert np.max(np.abs(c1 - coef[b].cpu().numpy())) <= 1e-5 * np.abs(c1).max(), b
+        assert abs(one.R_inf - float(inv.R_inf[b])) <= 1e-5 * abs(one.R_inf)
+        assert abs(one.predict_Rp() - float(rp[b])) <= 1e-5 * abs(one.predict_Rp())
+        assert np.allclose(one.predict_distribution(), gam[b].cpu().numpy(), rtol=0, atol=1e-5 * np.abs(c1).max())
+    # a shared basis for shifted grids, HMC started at the MAP estimates, percentiles
+    inv2 = Inverter(basis_freq=np.logspace(7, -3, 101))
+    u0 = inv._opt_result['u'][1:3, None, :].expand(-1, 2, -1).contiguous()
+    inv2.fit(freq[1:3], Z[1:3], mode='sample', warmup=60, samples=40, chains=2, init=u0)
+    assert inv2.fit_type == 'bayes' and tuple(inv2.distribution_fits['DRT']['coef'].shape) == (2, 101)
+    lo, hi = inv2.coef_percentile('DRT', 2.5), inv2.coef_percentile('DRT', 97.5)
+    assert (lo <= hi).all()
+    Zq = inv2.predict_Z(inv2.f_train, percentile=50)
+    assert tuple(Zq.shape) == (2, 81) and float((Zq.cpu() - torch.tensor(Z[1:3])).abs().max()) < 0.05
+    with pytest.raises(NotImplementedError):
+        inv2.fit(freq[:2], Z[:2], init_from_ridge=True)
+    with pytest.raises(ValueError):
+        inv2.fit(freq[:2], Z[0])
+
+
+def test_check_outliers_ridge_branch():
+    """check_outliers without a Stan fit: ridge fit (preset 'Huang') + inter-quartile rule (inversion.py:3351-3367)."""
+    from bayes_drt_b200 import Inverter
+    freq, Z = load_spectrum('ZARC_uniform_0.25')
+    Zo = Z.copy()
+    Zo[30] += 0.2 + 0.2j
+    inv = Inverter()
+    idx = inv.check_outliers(freq, Zo, threshold=4, use_existing_fit=True)
+    assert inv.fit_type == 'ridge' and 30 in idx and len(idx) <= 3
+    # an existing ridge fit of the same data is reused; batch form returns (spectrum, frequency) pairs
+    assert np.array_equal(inv.check_outliers(freq, Zo, threshold=4, use_existing_fit=True), idx)
+    pairs = inv.check_outliers(freq, np.stack([Z, Zo]), threshold=4, use_existing_fit=False)
+    assert pairs.shape[1] == 2 and [1, 30] in pairs.cpu().tolist() and [0, 30] not in pairs.cpu().tolist()
+    # after a MAP fit of the same data the fitted error model is used; a new data set falls back to ridge
+    inv.fit(freq, Zo, mode='optimize', outliers=True)
+    assert inv.fit_type == 'map'
+    zs = inv.check_outliers(freq, Zo, threshold=3.5, use_existing_fit=True)
+    assert inv.fit_type == 'map' and isinstance(zs, np.ndarray)
+    inv.check_outliers(freq, Z, threshold=4, use_existing_fit=True)
+    assert inv.fit_type == 'ridge'

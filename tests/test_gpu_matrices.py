@@ -87,3 +87,18 @@ def test_build_A_more_grids_than_one_launch():
         assert torch.equal(a, A_re[g]) and torch.equal(b, A_im[g])
     L = capi.build_L(f, tau, 1.7, 1)
     assert torch.equal(capi.build_L(f[69999], tau, 1.7, 1), L[69999])
+
+
+@pytest.mark.parametrize('name', [c for c in CASES if c + '/L3' in G.files])
+def test_construct_L_fractional_and_mixed_orders(name):
+    """matrices.construct_L: third derivative, fractional and list-mixed orders (matrices.py:278-316)"""
+    from bayes_drt_b200 import matrices
+    from test_oracle_matrices import L_ORDERS
+    t, e = G[name + '/tau'], float(G[name + '/eps'])
+    bf = 1 / (2 * np.pi * t)
+    for key, o in L_ORDERS:
+        L = matrices.construct_L(bf, tau=t, epsilon=e, order=o).cpu().numpy()
+        RL = G[f'{name}/{key}']
+        assert np.max(np.abs(L - RL)) <= 1e-10 * np.abs(RL).max(), key
+    with pytest.raises(ValueError, match='Order must be between 0 and 3'):
+        matrices.construct_L(bf, tau=t, epsilon=e, order=3.5)

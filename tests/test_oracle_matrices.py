@@ -48,3 +48,17 @@ def test_construct_L_M(name):
         RL, RM = G[f'{name}/L{o}'], G[f'{name}/M{o}']
         assert np.max(np.abs(L - RL)) <= 1e-12 * np.abs(RL).max()
         assert np.max(np.abs(M - RM)) <= 1e-12 * np.abs(RM).max()
+
+
+L_ORDERS = (('L3', 3), ('Lf0.5', 0.5), ('Lf1.25', 1.25), ('Lmix', [0.2, 0.3, 0.5]))
+
+
+@pytest.mark.parametrize('name', [c for c in CASES if c + '/L3' in G.files])
+def test_construct_L_fractional_and_mixed_orders(name):
+    """third derivative, fractional and list-mixed orders (matrices.py:278-316)"""
+    t, e = G[name + '/tau'], float(G[name + '/eps'])
+    bf = 1 / (2 * np.pi * t)
+    for key, o in L_ORDERS:
+        L = om.construct_L(bf, tau=t, epsilon=e, order=o)
+        RL = G[f'{name}/{key}']
+        assert np.max(np.abs(L - RL)) <= 1e-12 * np.abs(RL).max(), key
