@@ -61,7 +61,8 @@ class NutsOpts(C.Structure):
 class RidgeOpts(C.Structure):
     _fields_ = [('penalty', C.c_int), ('nonneg', C.c_int), ('max_iter', C.c_int), ('xtol', C.c_double),
                 ('hl_beta', C.c_double), ('lambda_0', C.c_double), ('reg_ord', C.c_double * 3),
-                ('L1_penalty', C.c_double), ('epsilon', C.c_double), ('fit_inductance', C.c_int)]
+                ('L1_penalty', C.c_double), ('epsilon', C.c_double), ('fit_inductance', C.c_int),
+                ('hl_fbeta', C.c_double)]
 
 
 class BdrtError(RuntimeError):

@@ -249,7 +249,7 @@ def qp_bound(P, q, lb, device=None):
 
 def ridge_fit(WA_re, WA_im, WZ_re, WZ_im, Pen, Lmat, penalty='discrete', nonneg=True, max_iter=20, xtol=1e-3,
               hl_beta=2.5, lambda_0=1e-2, reg_ord=(0.0, 0.0, 1.0), L1_penalty=0.0, epsilon=1.0, fit_inductance=True,
-              device=None):
+              hl_fbeta=None, device=None):
     ctx = context(device)
     dev = ctx.device
     WA_re, WA_im = f64(WA_re, dev), f64(WA_im, dev)
@@ -265,6 +265,7 @@ def ridge_fit(WA_re, WA_im, WZ_re, WZ_im, Pen, Lmat, penalty='discrete', nonneg=
     for i in range(3):
         o.reg_ord[i] = float(reg_ord[i])
     o.L1_penalty, o.epsilon, o.fit_inductance = float(L1_penalty), float(epsilon), int(fit_inductance)
+    o.hl_fbeta = 0.0 if hl_fbeta is None else float(hl_fbeta)
     coef = torch.empty((B, n), dtype=torch.float64, device=dev)
     lam = torch.empty((B, 3, n), dtype=torch.float64, device=dev)
     iters = torch.empty(B, dtype=torch.int32, device=dev)

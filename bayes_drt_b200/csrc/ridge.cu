@@ -165,7 +165,18 @@ __global__ void __launch_bounds__(RT) ridge_kernel(RidgeArgs a) {
             double s = 0.0;
             for (int j = l; j < n; j += 32) s = fma(Lo[(long long)k * n + j], prev[j], s);
             s = warp_sum(s);
-            if (l == 0) lam[o * n + 2 + k] = 1.0 / (s * s / (a.o.hl_beta - 1.0) + 1.0 / a.o.lambda_0);
+            if (l == 0) {
+              if (a.o.hl_fbeta > 0.0) y[2 + k] = s * s;  // second pass below needs max_k (L c)_k^2
+              else lam[o * n + 2 + k] = 1.0 / (s * s / (a.o.hl_beta - 1.0) + 1.0 / a.o.lambda_0);
+            }
+          }
+          if (a.o.hl_fbeta > 0.0) {
+            // lam_k = lambda_0 / ((L_o c)_k^2 / (max_k (L_o c)_k^2 * hl_fbeta) + 1)   (inversion.py:956-964)
+            __syncthreads();
+            double mx = 0.0;
+            for (int k = tid; k < K; k += RT) mx = fmax(mx, y[2 + k]);
+            mx = block_max(mx, red);
+            for (int k = tid; k < K; k += RT) lam[o * n + 2 + k] = a.o.lambda_0 / (y[2 + k] / (mx * a.o.hl_fbeta) + 1.0);
           }
           if (tid < 2) lam[o * n + tid] = 1.0;
         } else {
@@ -400,6 +411,7 @@ extern "C" void bdrt_ridge_default_opts(bdrt_ridge_opts* o) {
   o->L1_penalty = 0.0;
   o->epsilon = 1.0;
   o->fit_inductance = 1;
+  o->hl_fbeta = 0.0;  // off: the hl_beta rule
 }
 
 static size_t ridge_smem(int n, int ld) { return ((size_t)n * ld + 9 * n + 32) * sizeof(double) + ((size_t)n + 8) * sizeof(int); }

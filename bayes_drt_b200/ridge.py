@@ -37,7 +37,7 @@ def ridge_fit(inv, frequencies, Z, part='both', penalty='discrete', reg_ord=2, L
     if preset is not None:
         if preset not in presets:
             raise ValueError('Invalid preset {}. Options are {}'.format(preset, presets))
-        if preset == 'Ciucci':
+        if preset == 'Ciucci':  # inversion.py:274-277
             penalty, lambda_0, hl_fbeta = 'discrete', 'cv', 0.1
         else:  # inversion.py:278-282
             penalty, hl_beta, lambda_0, weights = 'integral', 2.5, 1e-2, 'modulus'
@@ -55,12 +55,16 @@ def ridge_fit(inv, frequencies, Z, part='both', penalty='discrete', reg_ord=2, L
         raise ValueError('ridge_fit cannot be used to fit multiple distributions')
     if correct_phase_offset and IERange is None:
         raise ValueError('IERange must be provided if correct_phase_offset==True')
+    if part not in ('both', 'real', 'imag'):
+        raise ValueError(f"Invalid part {part}. Options are 'both', 'real', 'imag'")
+    cv = isinstance(lambda_0, str) and lambda_0 == 'cv'
     # options outside the hot path: loud, never a silent fallback
-    for flag, nm in ((penalty == 'cholesky', "penalty='cholesky'"), (lambda_0 == 'cv', "lambda_0='cv' (Re-Im CV)"),
-                     (hl_fbeta is not None, 'hl_fbeta'), (hl_solution != 'analytic', "hl_solution='lm'"),
+    for flag, nm in ((penalty == 'cholesky', "penalty='cholesky'"),
+                     (hl_fbeta is not None and (penalty != 'discrete' or not hyper_lambda),
+                      "hl_fbeta without the discrete hyper-lambda penalty"),
+                     (hl_solution != 'analytic', "hl_solution='lm'"),
                      (hyper_weights, 'hyper_weights'), (hyper_a or hyper_b, 'hyper_a / hyper_b'),
-                     (correct_phase_offset, 'correct_phase_offset'), (dZ, 'dZ'), (x0 is not None, 'x0'),
-                     (part != 'both', "part != 'both'")):
+                     (correct_phase_offset, 'correct_phase_offset'), (dZ, 'dZ'), (x0 is not None, 'x0')):
         if flag:
             raise NotImplementedError(f'ridge_fit option {nm} is not implemented in this build')
     name = list(inv.distributions.keys())[0]
@@ -110,28 +114,89 @@ def ridge_fit(inv, frequencies, Z, part='both', penalty='discrete', reg_ord=2, L
         for o in range(3):
             Lmat[o, :, 2:] = m[f'L{o}']
             Pen[o] = Lmat[o].T @ Lmat[o]
-    if hyper_lambda:
-        r = capi.ridge_fit(WA_re, WA_im, WZ_re, WZ_im, Pen, Lmat, penalty=penalty, nonneg=nonneg, max_iter=max_iter,
-                           xtol=xtol, hl_beta=float(hl_beta), lambda_0=float(lambda_0), reg_ord=frac,
-                           L1_penalty=L1_penalty, epsilon=eps, fit_inductance=inv.fit_inductance, device=dev)
-        coef, lam = r['coef'], r['lam']
-        inv._ridge_iters, inv._ridge_converged = r['iters'], r['converged']
-        if inv._single and not bool(r['converged'][0]):
-            warnings.warn(f'Hyperparametric solution did not converge within {max_iter} iterations')
+
+    def core(lam0, part_, sel=None):
+        """One ridge fit of the (sub-)batch ``sel`` on one part of the data -> scaled coefficients [b, n], lambda
+        vectors, hyper-iterations, convergence flags.  A part that is left out enters with zero rows (_convex_opt,
+        inversion.py:1047-1052); the parameter it alone determines is then set by least squares (:855-873)."""
+        pick = (lambda t: t) if sel is None else (lambda t: t[sel])
+        war, wai = (WA_re, WA_im) if shared_w else (pick(WA_re), pick(WA_im))
+        wzr, wzi, zs = pick(WZ_re), pick(WZ_im), pick(Zs)
+        if part_ == 'real':
+            wai, wzi = torch.zeros_like(wai), torch.zeros_like(wzi)
+        elif part_ == 'imag':
+            war, wzr = torch.zeros_like(war), torch.zeros_like(wzr)
+        b = zs.shape[0]
+        if hyper_lambda:
+            r = capi.ridge_fit(war, wai, wzr, wzi, Pen, Lmat, penalty=penalty, nonneg=nonneg, max_iter=max_iter,
+                               xtol=xtol, hl_beta=float(hl_beta), lambda_0=float(lam0), reg_ord=frac,
+                               L1_penalty=L1_penalty, epsilon=eps,
+                               fit_inductance=inv.fit_inductance and part_ != 'real', hl_fbeta=hl_fbeta, device=dev)
+            coef, lam, iters, conv = r['coef'], r['lam'], r['iters'], r['converged']
+        else:
+            # ordinary ridge: one QP with lambda = lambda_0 (inversion.py:835-850)
+            G0 = (war.transpose(-1, -2) @ war + wai.transpose(-1, -2) @ wai)
+            P = G0 + sum(frac[o] * float(lam0) * Pen[o] for o in range(3))
+            P = P.expand(b, n, n).contiguous()
+            L1_vec = torch.full((n,), np.pi ** 0.5 / eps * L1_penalty, dtype=torch.float64, device=dev)
+            L1_vec[:2] = 0
+            q = -(war.transpose(-1, -2) @ wzr[:, :, None])[..., 0] - (wai.transpose(-1, -2) @ wzi[:, :, None])[..., 0] \
+                + L1_vec
+            lb = torch.zeros(n, dtype=torch.float64, device=dev)
+            if not nonneg:
+                lb[2:] = -10.0
+            coef, _, _ = capi.qp_bound(P, q.contiguous(), lb, device=dev)
+            lam = torch.full((b, 3, n), float(lam0), dtype=torch.float64, device=dev)
+            iters = torch.ones(b, dtype=torch.int32, device=dev)
+            conv = torch.ones(b, dtype=torch.int32, device=dev)
+        if part_ == 'imag':  # R_inf from the real part: the least-squares fit of a constant is the mean
+            coef[:, 0] = (zs.real - coef[:, 2:] @ A_re[:, 2:].T).mean(dim=1)
+        elif part_ == 'real' and inv.fit_inductance:  # inductance from the imaginary part
+            a_l = A_im[:, 1]
+            coef[:, 1] = ((zs.imag - coef[:, 2:] @ A_im[:, 2:].T) @ a_l) / (a_l @ a_l)
+        return coef, lam, iters, conv
+
+    if cv:
+        # Re-Im cross-validation of lambda_0 (Inverter.ridge_ReImCV, inversion.py:902-944): fit the real part and score
+        # it on the imaginary part and vice versa, for every lambda_0 of the grid; each spectrum takes its own optimum.
+        lambdas = np.logspace(-10, 5, 31) if cv_lambdas is None else np.asarray(cv_lambdas, dtype=np.float64)
+        recv = torch.zeros((B, len(lambdas)), dtype=torch.float64, device=dev)
+        imcv = torch.zeros_like(recv)
+        for i, lam_i in enumerate(lambdas):
+            c = core(lam_i, 'real')[0]
+            imcv[:, i] = ((Zs.imag - c @ A_im.T) ** 2).sum(dim=1)
+            c = core(lam_i, 'imag')[0]
+            recv[:, i] = ((Zs.real - c @ A_re.T) ** 2).sum(dim=1)
+        s2 = (inv._Z_scale ** 2)[:, None]  # the reference scores in unscaled units
+        recv, imcv = recv * s2, imcv * s2
+        totcv = recv + imcv
+        best = torch.argmin(torch.nan_to_num(totcv, nan=float('inf')), dim=1).cpu().numpy()
+        lam_b = lambdas[best]
+        if inv._single:
+            if best[0] in (int(np.argmin(lambdas)), int(np.argmax(lambdas))):
+                warnings.warn('Optimal lambda_0 {} determined by Re-Im CV is at the boundary of the evaluated range. '
+                              'Re-run with an expanded lambda_0 range to obtain an accurate estimate of the optimal '
+                              'lambda_0.'.format(lam_b[0]))
+            import pandas as pd
+            inv.cv_result = pd.DataFrame(np.stack([lambdas, recv[0].cpu().numpy(), imcv[0].cpu().numpy(),
+                                                   totcv[0].cpu().numpy()]).T,
+                                         columns=['lambda', 'recv', 'imcv', 'totcv'])
+        else:
+            inv.cv_result = {'lambda': lambdas, 'recv': recv, 'imcv': imcv, 'totcv': totcv}
+        inv._cv_lambda_0 = lam_b
+        coef = torch.empty((B, n), dtype=torch.float64, device=dev)
+        lam = torch.empty((B, 3, n), dtype=torch.float64, device=dev)
+        iters = torch.empty(B, dtype=torch.int32, device=dev)
+        conv = torch.empty(B, dtype=torch.int32, device=dev)
+        for lv in np.unique(lam_b):  # one launch per selected lambda_0
+            sel = torch.as_tensor(np.nonzero(lam_b == lv)[0], device=dev)
+            coef[sel], lam[sel], iters[sel], conv[sel] = core(lv, part, sel)
     else:
-        # ordinary ridge: one QP with lambda = lambda_0 (inversion.py:835-850)
-        G0 = (WA_re.transpose(-1, -2) @ WA_re + WA_im.transpose(-1, -2) @ WA_im)
-        P = G0 + sum(frac[o] * lambda_0 * Pen[o] for o in range(3))
-        P = P.expand(B, n, n).contiguous()
-        L1_vec = torch.full((n,), np.pi ** 0.5 / eps * L1_penalty, dtype=torch.float64, device=dev)
-        L1_vec[:2] = 0
-        q = -(WA_re.transpose(-1, -2) @ WZ_re[:, :, None])[..., 0] - (WA_im.transpose(-1, -2) @ WZ_im[:, :, None])[..., 0] \
-            + L1_vec
-        lb = torch.zeros(n, dtype=torch.float64, device=dev)
-        if not nonneg:
-            lb[2:] = -10.0
-        coef, _, _ = capi.qp_bound(P, q.contiguous(), lb, device=dev)
-        lam = torch.full((B, 3, n), float(lambda_0), dtype=torch.float64, device=dev)
+        coef, lam, iters, conv = core(lambda_0, part)
+    if hyper_lambda:
+        inv._ridge_iters, inv._ridge_converged = iters, conv
+        if inv._single and not bool(conv[0]):
+            warnings.warn(f'Hyperparametric solution did not converge within {max_iter} iterations')
     # rescale (inversion.py:875-898)
     s = inv._Z_scale
     out = coef * s[:, None]

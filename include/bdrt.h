@@ -226,6 +226,8 @@ typedef struct {
   double L1_penalty;/* 0 */
   double epsilon;   /* basis epsilon (only enters the L1 penalty vector) */
   int fit_inductance;
+  double hl_fbeta;  /* > 0: lambda_k = lambda_0 / ((L c)_k^2 / (max_k (L c)_k^2 hl_fbeta) + 1) instead of the hl_beta rule
+                     * (discrete penalty, _hyper_lambda_fbeta inversion.py:956-964; preset 'Ciucci' uses 0.1); 0: off */
 } bdrt_ridge_opts;
 void bdrt_ridge_default_opts(bdrt_ridge_opts* o);
 

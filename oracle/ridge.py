@@ -23,7 +23,7 @@ from . import matrices as om
 from .model import default_epsilon, default_tau, z_scale
 
 
-def qp_bound(P, q, lb, F0=None, max_iter=500):
+def qp_bound(P, q, lb, F0=None, max_iter=500, strict=True):
     """argmin 1/2 x'Px + q'x  s.t. x >= lb, by block principal pivoting (Judice & Pires 1994; Kim & Park 2011).
     Returns (x, y, F, iters) with y = Px + q the multipliers (y >= 0 on the bound set, 0 on the free set F)."""
     n = len(q)
@@ -53,7 +53,9 @@ def qp_bound(P, q, lb, F0=None, max_iter=500):
         else:
             i = np.max(np.nonzero(V)[0])  # backup rule: only the largest infeasible index
             F[i] = ~F[i]
-    raise RuntimeError('block principal pivoting did not terminate')
+    if strict:
+        raise RuntimeError('block principal pivoting did not terminate')
+    return x, y, F, max_iter  # numerically singular P (e.g. lambda_0 = 1e-10 on one part of the data): last iterate
 
 
 def format_weights(Z, weights):
@@ -73,6 +75,13 @@ def format_weights(Z, weights):
 def hyper_lambda_discrete(L, coef, hl_beta, lambda_0):
     Lx2 = (L @ coef) ** 2
     lam = 1 / (Lx2 / (hl_beta - 1) + 1 / lambda_0)
+    return np.hstack(([1, 1], lam))
+
+
+def hyper_lambda_fbeta(L, coef, hl_fbeta, lambda_0):
+    """_hyper_lambda_fbeta (inversion.py:956-964)"""
+    Lx2 = (L @ coef) ** 2
+    lam = lambda_0 / (Lx2 / (np.max(Lx2) * hl_fbeta) + 1)
     return np.hstack(([1, 1], lam))
 
 
@@ -114,19 +123,47 @@ def prep(freq, Z, basis_freq=None, epsilon=None, penalty='discrete', weights=Non
         else:
             Lmat[o, :, 2:] = om.construct_L(bf, tau=tau, epsilon=eps, order=o)
             Pen[o] = Lmat[o].T @ Lmat[o]
-    return dict(freq=freq, tau=tau, epsilon=eps, Z_scale=zs, WA_re=w.real[:, None] * A_re, WA_im=w.imag[:, None] * A_im,
+    return dict(freq=freq, tau=tau, epsilon=eps, Z_scale=zs, Zs=Zs, A_re=A_re, A_im=A_im, w=w,
+                WA_re=w.real[:, None] * A_re, WA_im=w.imag[:, None] * A_im,
                 WZ_re=w.real * Zs.real, WZ_im=w.imag * Zs.imag, Pen=Pen, Lmat=Lmat, K=K)
+
+
+def ridge_ReImCV(freq, Z, lambdas=None, **kw):
+    """Re-Im cross-validation of lambda_0 (Inverter.ridge_ReImCV, inversion.py:902-944): the real part is fitted and
+    scored on the imaginary part and vice versa; returns (lambda_0 with the smallest total error, table
+    [n_lambda, 4] = lambda, recv, imcv, totcv).  Errors are taken in the scaled units of the fit (one factor Z_scale^2
+    against the reference's, which does not move the minimum)."""
+    lambdas = np.logspace(-10, 5, 31) if lambdas is None else np.asarray(lambdas, dtype=np.float64)
+    recv, imcv = np.zeros_like(lambdas), np.zeros_like(lambdas)
+    for i, lam in enumerate(lambdas):
+        r = ridge_fit(freq, Z, part='real', lambda_0=lam, **kw)
+        p = r['prep']
+        zs = p['Zs']
+        imcv[i] = np.sum((zs.imag - p['A_im'] @ r['scaled_coef']) ** 2)
+        r = ridge_fit(freq, Z, part='imag', lambda_0=lam, **kw)
+        recv[i] = np.sum((zs.real - p['A_re'] @ r['scaled_coef']) ** 2)
+    tot = recv + imcv
+    return lambdas[np.argmin(tot)], np.stack([lambdas, recv, imcv, tot], axis=1)
 
 
 def ridge_fit(freq, Z, basis_freq=None, epsilon=None, penalty='discrete', reg_ord=2, L1_penalty=0.0, scale_Z=True,
               nonneg=True, weights=None, hl_beta=2.5, lambda_0=1e-2, xtol=1e-3, max_iter=20, fit_inductance=True,
-              preset=None, x0=None, return_history=False):
-    """Default hyper-lambda path of Inverter.ridge_fit.  Returns dict(coef [K], R_inf, inductance, scaled_coef [K+2],
-    lam [3, K+2], iters, converged)."""
+              preset=None, x0=None, return_history=False, part='both', hl_fbeta=None, cv_lambdas=None):
+    """Hyper-lambda path of Inverter.ridge_fit.  Returns dict(coef [K], R_inf, inductance, scaled_coef [K+2],
+    lam [3, K+2], iters, converged).  ``part`` 'real' / 'imag' fits one part only (_convex_opt :1047-1052) and then
+    sets the parameter that part cannot see by least squares on the other part (:855-873)."""
     if preset == 'Huang':  # inversion.py:278-282
         penalty, hl_beta, lambda_0, weights = 'integral', 2.5, 1e-2, 'modulus'
+    elif preset == 'Ciucci':  # inversion.py:274-277
+        penalty, lambda_0, hl_fbeta = 'discrete', 'cv', 0.1
     elif preset is not None:
         raise NotImplementedError(preset)
+    cv_table = None
+    if isinstance(lambda_0, str) and lambda_0 == 'cv':  # inversion.py:344-352
+        lambda_0, cv_table = ridge_ReImCV(freq, Z, lambdas=cv_lambdas, basis_freq=basis_freq, epsilon=epsilon,
+                                          penalty=penalty, reg_ord=reg_ord, L1_penalty=L1_penalty, scale_Z=scale_Z,
+                                          nonneg=nonneg, weights=weights, hl_beta=hl_beta, xtol=xtol,
+                                          max_iter=max_iter, fit_inductance=fit_inductance, x0=x0, hl_fbeta=hl_fbeta)
     p = prep(freq, Z, basis_freq, epsilon, penalty, weights, scale_Z, fit_inductance)
     n = p['K'] + 2
     frac = np.zeros(3)
@@ -134,10 +171,13 @@ def ridge_fit(freq, Z, basis_freq=None, epsilon=None, penalty='discrete', reg_or
         frac[reg_ord] = 1
     else:
         frac[:] = reg_ord
-    G0 = p['WA_re'].T @ p['WA_re'] + p['WA_im'].T @ p['WA_im']
+    if part not in ('both', 'real', 'imag'):
+        raise ValueError(f"Invalid part {part}. Options are 'both', 'real', 'imag'")
+    use_re, use_im = float(part != 'imag'), float(part != 'real')
+    G0 = use_re * (p['WA_re'].T @ p['WA_re']) + use_im * (p['WA_im'].T @ p['WA_im'])
     L1_vec = np.ones(n) * np.pi ** 0.5 / p['epsilon'] * L1_penalty
     L1_vec[0:2] = 0
-    q = -p['WA_re'].T @ p['WZ_re'] - p['WA_im'].T @ p['WZ_im'] + L1_vec
+    q = -use_re * (p['WA_re'].T @ p['WZ_re']) - use_im * (p['WA_im'].T @ p['WZ_im']) + L1_vec
     lb = np.zeros(n) if nonneg else np.r_[0.0, 0.0, -10.0 * np.ones(n - 2)]
     coef = np.zeros(n) + 1e-6 if x0 is None else np.asarray(x0, dtype=np.float64).copy()
     lam = np.ones((3, n)) * lambda_0
@@ -149,7 +189,9 @@ def ridge_fit(freq, Z, basis_freq=None, epsilon=None, penalty='discrete', reg_or
         prev = coef.copy()
         for o in range(3):
             if frac[o] > 0:
-                if penalty == 'discrete':
+                if penalty == 'discrete' and hl_fbeta is not None:
+                    lam[o] = hyper_lambda_fbeta(p['Lmat'][o][:, 2:], prev[2:], hl_fbeta, lambda_0)
+                elif penalty == 'discrete':
                     lam[o] = hyper_lambda_discrete(p['Lmat'][o][:, 2:], prev[2:], hl_beta, lambda_0)
                 else:
                     factor = (100.0, 10.0, 1.0)[o]
@@ -161,7 +203,7 @@ def ridge_fit(freq, Z, basis_freq=None, epsilon=None, penalty='discrete', reg_or
             if frac[o] > 0:
                 s = np.sqrt(lam[o])
                 Pm += frac[o] * (s[:, None] * p['Pen'][o] * s[None, :])
-        coef, y, F, nit = qp_bound(Pm, q, lb, F0=F)
+        coef, y, F, nit = qp_bound(Pm, q, lb, F0=F, strict=False)
         hist.append(coef.copy())
         with np.errstate(all='ignore'):
             delta = (coef - prev) / prev
@@ -172,12 +214,18 @@ def ridge_fit(freq, Z, basis_freq=None, epsilon=None, penalty='discrete', reg_or
                 break
         it += 1
     iters = len(hist)
+    coef = coef.copy()
+    if part == 'imag':  # R_inf from the real part (inversion.py:855-863; a constant's least-squares fit is the mean)
+        coef[0] = np.mean(p['Zs'].real - p['A_re'][:, 2:] @ coef[2:])
+    elif part == 'real' and fit_inductance:  # inductance from the imaginary part (:865-873)
+        a_l = 2 * np.pi * p['freq'] * 1e-4
+        coef[1] = a_l @ (p['Zs'].imag - p['A_im'][:, 2:] @ coef[2:]) / (a_l @ a_l)
     out_coef = coef * p['Z_scale']
     out_coef[1] *= 1e-4
     if not fit_inductance:
         out_coef[1] = 0
     res = dict(coef=out_coef[2:], R_inf=out_coef[0], inductance=out_coef[1], scaled_coef=coef, lam=lam, iters=iters,
-               converged=converged, Z_scale=p['Z_scale'], prep=p)
+               converged=converged, Z_scale=p['Z_scale'], prep=p, lambda_0=lambda_0, cv_result=cv_table)
     if return_history:
         res['history'] = hist
     return res

@@ -31,7 +31,9 @@ def test_qp_bound_random_problems():
 
 @pytest.mark.parametrize('kw', [dict(), dict(preset='Huang'),
                                 dict(penalty='integral', lambda_0=1, hl_beta=5, weights='modulus'),
-                                dict(nonneg=False), dict(reg_ord=[0.2, 0.3, 0.5], L1_penalty=0.01)])
+                                dict(nonneg=False), dict(reg_ord=[0.2, 0.3, 0.5], L1_penalty=0.01),
+                                dict(part='real'), dict(part='imag', weights='modulus'), dict(hl_fbeta=0.1),
+                                dict(part='real', hl_fbeta=0.3, lambda_0=1e-3)])
 def test_ridge_fit_matches_oracle(kw):
     from bayes_drt_b200 import Inverter
     freq = load_spectrum(NAMES[0])[0]
@@ -73,11 +75,46 @@ def test_ridge_unsupported_options_are_loud():
     from bayes_drt_b200 import Inverter
     freq, Z = load_spectrum('ZARC_uniform_0.25')
     inv = Inverter()
-    for kw in (dict(preset='Ciucci'), dict(hyper_weights=True, hyper_lambda=False), dict(hl_solution='lm'),
-               dict(dZ=True), dict(penalty='cholesky')):
+    for kw in (dict(hl_fbeta=0.1, penalty='integral', hl_beta=2.5), dict(hyper_weights=True, hyper_lambda=False),
+               dict(hl_solution='lm'), dict(dZ=True), dict(penalty='cholesky')):
         with pytest.raises(NotImplementedError):
             inv.ridge_fit(freq, Z, **kw)
     with pytest.raises(ValueError):
         inv.ridge_fit(freq, Z, hl_beta=0.5)
     with pytest.raises(ValueError):
         inv.ridge_fit(freq, Z, preset='nope')
+    with pytest.raises(ValueError):
+        inv.ridge_fit(freq, Z, part='modulus')
+
+
+def test_ridge_reim_cross_validation_and_ciucci_preset():
+    """lambda_0='cv' (Inverter.ridge_ReImCV, inversion.py:902-944) and preset 'Ciucci' against the oracle: the
+    cross-validation table, the selected lambda_0 of every spectrum of a batch, and the final fit."""
+    import warnings
+    from bayes_drt_b200 import Inverter
+    freq = load_spectrum(NAMES[0])[0]
+    Z = np.stack([load_spectrum(n)[1] for n in NAMES[:3]])
+    grid = np.logspace(-6, 0, 7)
+    inv = Inverter()
+    inv.ridge_fit(freq, Z, lambda_0='cv', cv_lambdas=grid)
+    coef = inv.distribution_fits['DRT']['coef'].cpu().numpy()
+    for b in range(3):
+        o = oridge.ridge_fit(freq, Z[b], lambda_0='cv', cv_lambdas=grid)
+        assert inv._cv_lambda_0[b] == o['lambda_0']
+        tab = o['cv_result']
+        zs2 = o['Z_scale'] ** 2
+        for j, key in ((1, 'recv'), (2, 'imcv'), (3, 'totcv')):
+            assert np.allclose(inv.cv_result[key][b].cpu().numpy(), tab[:, j] * zs2, rtol=1e-5), key
+        assert np.max(np.abs(coef[b] - o['coef'])) <= 1e-6 * np.max(np.abs(o['coef']))
+        assert abs(inv.R_inf[b].item() - o['R_inf']) <= 1e-6 * abs(o['R_inf'])
+    # single spectrum, full default grid, preset 'Ciucci' (discrete penalty, hl_fbeta = 0.1)
+    one = Inverter()
+    with warnings.catch_warnings():
+        warnings.simplefilter('ignore')
+        one.ridge_fit(freq, Z[0], preset='Ciucci')
+    o = oridge.ridge_fit(freq, Z[0], preset='Ciucci')
+    assert list(one.cv_result.columns) == ['lambda', 'recv', 'imcv', 'totcv'] and len(one.cv_result) == 31
+    assert one._cv_lambda_0[0] == o['lambda_0']
+    c1 = one.distribution_fits['DRT']['coef']
+    assert np.max(np.abs(c1 - o['coef'])) <= 1e-6 * np.max(np.abs(o['coef']))
+    assert abs(one.predict_Rp() - 1.0) < 0.05
