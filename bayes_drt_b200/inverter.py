@@ -609,21 +609,85 @@ class Inverter:
         return float(rp[0]) if self._single else rp
 
     def predict_sigma(self, frequencies=None, percentile=None, times=None):
-        """inversion.py:3089 for the training frequencies: the fitted sigma_tot split into real / imaginary parts."""
+        """inversion.py:3089-3139.  At the training frequencies: the fitted sigma_tot split into real / imaginary parts.
+        Elsewhere: rebuilt from the error-model parameters and the predicted impedance (baseline outlier level
+        min(sigma_out), as the reference does -- it notes that this does not match sigma_tot exactly)."""
+        if times is not None:
+            raise NotImplementedError('drift fits are out of scope')
         if self.fit_type not in ('map', 'bayes'):
             raise ValueError('Error scale prediction only available for bayes_fit and map_fit')
-        if frequencies is not None and not (
+        if percentile is not None and (self.fit_type != 'bayes' or self._sample_result is None):
+            raise ValueError('Percentile prediction is only available for bayes_fit')
+        nf = self.f_train.shape[-1]
+        s = self._Z_scale
+        if frequencies is None or (
                 np.shape(frequencies) == np.shape(self.f_train) and
                 np.array_equal(mat.rel_round(np.ravel(frequencies), 10), mat.rel_round(np.ravel(self.f_train), 10))):
-            raise NotImplementedError('predict_sigma at frequencies other than the training grid is not implemented')
+            if percentile is not None:
+                st = self._pct(self._sample_result['sigma_tot'], percentile) * s[:, None]
+            else:
+                st = torch.as_tensor(self.error_fit['sigma_tot'], device=self.device).reshape(-1, 2 * nf)
+            return self._ret(st[:, :nf]), self._ret(st[:, nf:])
+        dev = self.device
+
+        def col(v):  # [B, 1]
+            return torch.as_tensor(v, dtype=torch.float64, device=dev).reshape(-1, 1)
         if percentile is not None:
-            if self.fit_type != 'bayes' or self._sample_result is None:
-                raise ValueError('Percentile prediction is only available for bayes_fit')
-            st = self._pct(self._sample_result['sigma_tot'], percentile) * self._Z_scale[:, None]
+            r = self._sample_result
+
+            def pct_all(d):  # np.percentile over every draw (and entry) of a spectrum -> [B, 1]
+                return self._pct(d.reshape(d.shape[0], -1).contiguous(), percentile).reshape(-1, 1)
+            sigma_res = pct_all(r['sigma_res']) * s[:, None]
+            a_prop, a_re, a_im = pct_all(r['alpha_prop']), pct_all(r['alpha_re']), pct_all(r['alpha_im'])
+            so = r.get('sigma_out')
+            so_min = torch.zeros_like(sigma_res) if so is None or not bool(torch.isfinite(so).all()) else \
+                (self._pct(so, percentile) * s[:, None]).min(dim=1, keepdim=True).values
         else:
-            st = torch.as_tensor(self.error_fit['sigma_tot'], device=self.device).reshape(-1, 2 * self.f_train.shape[-1])
-        nf = self.f_train.shape[-1]
-        return self._ret(st[:, :nf]), self._ret(st[:, nf:])
+            e = self.error_fit
+            sigma_res, a_prop, a_re, a_im = col(e['sigma_res']), col(e['alpha_prop']), col(e['alpha_re']), col(e['alpha_im'])
+            so = e.get('sigma_out')
+            if so is None:
+                so_min = torch.zeros_like(sigma_res)
+            else:
+                so = torch.as_tensor(so, dtype=torch.float64, device=dev).reshape(sigma_res.shape[0], -1)
+                so_min = torch.nan_to_num(so, nan=0.0).min(dim=1, keepdim=True).values
+        single = self._single
+        self._single = False
+        Zp = self.predict_Z(frequencies, percentile=percentile)
+        self._single = single
+        base2 = sigma_res ** 2 + so_min ** 2 + col(self.error_fit['sigma_min']) ** 2
+        common = (a_re * Zp.real) ** 2 + (a_im * Zp.imag) ** 2
+        sigma_re = torch.sqrt(base2 + (a_prop * Zp.real) ** 2 + common)
+        sigma_im = torch.sqrt(base2 + (a_prop * Zp.imag) ** 2 + common)
+        return self._ret(sigma_re), self._ret(sigma_im)
+
+    def score(self, frequencies, Z, metric='chi_sq', weights=None, part='both', times=None):
+        """inversion.py:3141-3160: weighted chi^2 per frequency or r^2 (utils.r2_score) of the predicted impedance.
+        Returns a float for one spectrum, a tensor [B] for a batch."""
+        from .ridge import _weights
+        if part not in ('both', 'real', 'imag'):
+            raise ValueError(f"Invalid part {part}. Options are 'both', 'real', or 'imag'")
+        if metric not in ('chi_sq', 'r2'):
+            raise ValueError(f"Invalid metric {metric}. Options are 'chi_sq', 'r2'")
+        single = self._single
+        self._single = False
+        Zp = self.predict_Z(frequencies, times=times)
+        self._single = single
+        Zt = torch.as_tensor(np.asarray(Z) if not torch.is_tensor(Z) else Z).to(torch.complex128).to(self.device)
+        Zt = Zt.reshape(Zp.shape)
+        w_re, w_im = _weights(Zt, weights)
+        if part == 'both':
+            zp, zt, w = torch.cat((Zp.real, Zp.imag), 1), torch.cat((Zt.real, Zt.imag), 1), torch.cat((w_re, w_im), 1)
+        elif part == 'real':
+            zp, zt, w = Zp.real, Zt.real, w_re
+        else:
+            zp, zt, w = Zp.imag, Zt.imag, w_im
+        if metric == 'chi_sq':
+            out = (((zp - zt) * w) ** 2).sum(dim=1) / Zp.shape[1]
+        else:
+            avg = (w * zt).sum(dim=1, keepdim=True) / w.sum(dim=1, keepdim=True)
+            out = 1 - (w * (zp - zt) ** 2).sum(dim=1) / (w * (zt - avg) ** 2).sum(dim=1)
+        return float(out[0]) if self._single else out
 
     def check_outliers(self, frequencies=None, Z=None, threshold=3.5, use_existing_fit=True, **ridge_kw):
         """inversion.py:3313-3376.  An existing MAP / HMC fit of the same data: combined z-score of the residuals under

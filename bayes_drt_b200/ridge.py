@@ -10,7 +10,8 @@ from . import matrices as mat
 
 
 def _weights(Zs, weights):
-    """Inverter._format_weights for part='both' (inversion.py:2338-2395) -> (w_re, w_im) [B, Nf]."""
+    """Inverter._format_weights (inversion.py:2338-2395) on a batch -> (w_re, w_im) [B, Nf]: named schemes, a real or
+    complex constant, or an array ([Nf] or [B, Nf]; real: both parts, complex: real part weights Z', imaginary Z'')."""
     if weights is None or (isinstance(weights, str) and weights == 'unity'):
         w = torch.ones_like(Zs.real)
         return w, w.clone()
@@ -23,9 +24,23 @@ def _weights(Zs, weights):
             return w, w.clone()
         if weights == 'proportional':
             return 1.0 / Zs.real.abs(), 1.0 / Zs.imag.abs()
+        if weights == 'prop_adj':  # 25th percentile of |Z|^2, as the reference has it
+            p25 = torch.quantile(Zs.abs() ** 2, 0.25, dim=1, keepdim=True)
+            return 1.0 / (Zs.real.abs() + p25), 1.0 / (Zs.imag.abs() + p25)
         raise ValueError(f"Invalid weights argument {weights}. String options are 'unity', 'modulus', 'proportional', "
                          f"and 'prop_adj'")
-    raise NotImplementedError('array / scalar weights are not implemented in this build')
+    one = torch.ones_like(Zs.real)
+    if isinstance(weights, (float, int)):
+        return one * float(weights), one * float(weights)
+    if isinstance(weights, complex):
+        return one * weights.real, one * weights.imag
+    w = torch.as_tensor(np.asarray(weights) if not torch.is_tensor(weights) else weights).to(Zs.device)
+    if w.shape[-1] != Zs.shape[1] or w.dim() > 2 or (w.dim() == 2 and w.shape[0] != Zs.shape[0]):
+        raise ValueError('Weights array must match length of data')  # inversion.py:2373-2374
+    if w.is_complex():
+        return (one * w.real.to(torch.float64)).contiguous(), (one * w.imag.to(torch.float64)).contiguous()
+    w = (one * w.to(torch.float64)).contiguous()
+    return w, w.clone()
 
 
 def ridge_fit(inv, frequencies, Z, part='both', penalty='discrete', reg_ord=2, L1_penalty=0, scale_Z=True, nonneg=True,

@@ -287,3 +287,50 @@ def test_check_outliers_ridge_branch():
     assert inv.fit_type == 'map' and isinstance(zs, np.ndarray)
     inv.check_outliers(freq, Z, threshold=4, use_existing_fit=True)
     assert inv.fit_type == 'ridge'
+
+
+def test_predict_sigma_off_grid_score_and_weight_forms():
+    """predict_sigma away from the training grid (inversion.py:3104-3137), score (:3141-3160), array / scalar /
+    'prop_adj' weights of ridge_fit (_format_weights :2338-2395)."""
+    from bayes_drt_b200 import Inverter
+    freq, Z = load_spectrum('ZARC_uniform_0.25')
+    inv = Inverter()
+    inv.fit(freq, Z, mode='optimize')
+    s_re, s_im = inv.predict_sigma(freq)
+    # the same error model rebuilt from its parameters at (almost) the training frequencies
+    t_re, t_im = inv.predict_sigma(freq * (1 + 1e-6))
+    assert t_re.shape == (81,) and np.allclose(t_re, s_re, rtol=1e-4) and np.allclose(t_im, s_im, rtol=1e-4)
+    f2 = np.logspace(5.5, -1.5, 33)
+    u_re, u_im = inv.predict_sigma(f2)
+    assert u_re.shape == (33,) and (u_re > 0).all() and (u_im > 0).all()
+    Zp = inv.predict_Z(freq)
+    chi = inv.score(freq, Z)
+    ref = np.sum(np.concatenate(((Zp - Z).real, (Zp - Z).imag)) ** 2) / 81
+    assert isinstance(chi, float) and abs(chi - ref) <= 1e-12 * ref
+    w = 1 / np.abs(Z)
+    chi_w = inv.score(freq, Z, weights='modulus', part='imag')
+    assert abs(chi_w - np.sum(((Zp - Z).imag * w) ** 2) / 81) <= 1e-12 * chi_w
+    assert 0.999 < inv.score(freq, Z, metric='r2') <= 1.0
+    with pytest.raises(ValueError):
+        inv.score(freq, Z, metric='mse')
+    # HMC fit: percentile version off the grid, batch shapes
+    Zb = np.stack([Z, load_spectrum('ZARC-RL_uniform_0.25')[1]])
+    hm = Inverter()
+    hm.fit(freq, Zb, mode='sample', warmup=60, samples=40, chains=2, init_from_ridge=True)
+    lo_re, lo_im = hm.predict_sigma(f2, percentile=10)
+    hi_re, hi_im = hm.predict_sigma(f2, percentile=90)
+    assert tuple(lo_re.shape) == (2, 33) and bool((lo_re > 0).all()) and bool((hi_im > 0).all())
+    assert tuple(hm.score(freq, Zb).shape) == (2,)
+    # ridge weights: an array equal to the 'modulus' weights of the scaled data reproduces weights='modulus'
+    r1 = Inverter()
+    r1.ridge_fit(freq, Z, weights='modulus')
+    c1 = r1.distribution_fits['DRT']['coef'].copy()
+    r1.ridge_fit(freq, Z, weights=1 / np.abs(Z / float(r1._Z_scale[0])))
+    assert np.max(np.abs(r1.distribution_fits['DRT']['coef'] - c1)) <= 1e-9 * np.abs(c1).max()
+    r1.ridge_fit(freq, Z, weights=(1 + 1j) / np.abs(Z / float(r1._Z_scale[0])))
+    assert np.max(np.abs(r1.distribution_fits['DRT']['coef'] - c1)) <= 1e-9 * np.abs(c1).max()
+    for wt in (2.0, 'prop_adj', 1 + 2j):
+        r1.ridge_fit(freq, Z, weights=wt)
+        assert np.isfinite(r1.distribution_fits['DRT']['coef']).all() and abs(r1.predict_Rp() - 1.0) < 0.1
+    with pytest.raises(ValueError):
+        r1.ridge_fit(freq, Z, weights=np.ones(5))
