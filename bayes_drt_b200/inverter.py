@@ -114,6 +114,41 @@ class Inverter:
 
     basis = property(lambda self: self._basis, set_basis)
 
+    def get_distributions(self):
+        return self._distributions
+
+    def get_basis(self):
+        return self._basis
+
+    def get_basis_freq(self):
+        return self._basis_freq
+
+    def set_basis_freq(self, basis_freq):
+        self._basis_freq = basis_freq
+        self._recalc_mat = True
+
+    basis_freq = property(get_basis_freq, set_basis_freq)
+
+    def get_epsilon(self):
+        return self._epsilon
+
+    def set_epsilon(self, epsilon, override_distributions=False):
+        self._epsilon = epsilon
+        self._recalc_mat = True
+        if override_distributions:  # inversion.py:4095-4097
+            for name in self.distributions.keys():
+                self.distributions[name]['epsilon'] = epsilon
+
+    epsilon = property(get_epsilon, set_epsilon)
+
+    def get_fit_inductance(self):
+        return self._fit_inductance_
+
+    def set_fit_inductance(self, fit_inductance):
+        self._fit_inductance_ = fit_inductance
+
+    fit_inductance = property(get_fit_inductance, set_fit_inductance)
+
     # ------------------------------------------------------------------------------------------------------------
     # preprocessing (Inverter._prep_matrices, inversion.py:2127-2336; _scale_Z :2411-2443)
     # ------------------------------------------------------------------------------------------------------------
@@ -494,15 +529,19 @@ class Inverter:
         q = capi.summarize(d3.contiguous(), percentiles=(percentile,), want_mean=False, device=self.device)[1][0]
         return q if draws.dim() == 3 else q[:, 0]
 
+    def _draw_key(self, name):
+        """name of a distribution's coefficient block among the draws (Inverter._get_stan_coef_name)"""
+        if len(self.distribution_fits) == 1:
+            return 'x'
+        if self.distributions[name]['dist_type'] == 'series':
+            return 'xs'
+        return 'xp' if 'xp2' not in self._sample_result else f"xp{self.distributions[name].get('order', 1)}"
+
     def coef_percentile(self, distribution_name, percentile):
         """inversion.py:2547-2566: per-coefficient np.percentile (linear interpolation) of the merged draws."""
         if self.fit_type != 'bayes' or self._sample_result is None:
             raise ValueError('Percentile prediction is only available for bayes_fit')
-        names = list(self.distribution_fits.keys())
-        key = 'x' if len(names) == 1 else ('xs' if self.distributions[distribution_name]['dist_type'] == 'series' else
-                                            ('xp' if 'xp2' not in self._sample_result else
-                                             f"xp{self.distributions[distribution_name].get('order', 1)}"))
-        q = self._pct(self._sample_result[key], percentile)
+        q = self._pct(self._sample_result[self._draw_key(distribution_name)], percentile)
         s = self._Z_scale[:, None]
         q = q / s if self.distributions[distribution_name]['dist_type'] == 'parallel' else q * s
         return self._ret(q)
@@ -585,6 +624,40 @@ class Inverter:
             ind = torch.as_tensor(self.inductance, dtype=torch.float64, device=self.device).reshape(-1, 1)
             Zp = Zp + torch.complex(Rinf.expand_as(Zp.real), (2 * np.pi * fd * ind).expand_as(Zp.real))
         return self._ret(Zp)
+
+    def predict_Z_distribution(self, frequencies, distributions=None, include_offsets=True):
+        """inversion.py:2963-3031: the impedance of every posterior draw, [B, chains * samples, Nf] complex
+        ([chains * samples, Nf] for one spectrum)."""
+        if self.fit_type != 'bayes' or self._sample_result is None:
+            raise ValueError('predict_Z_distribution is only available for bayes_fit results')
+        names = list(self.distribution_fits.keys()) if distributions is None else (
+            [distributions] if isinstance(distributions, str) else list(distributions))
+        if len(names) != len(self.distributions) or not include_offsets:
+            warnings.warn('All distributions and offsets should be included for meaningful results from '
+                          'predict_Z_distribution')
+        f = torch.as_tensor(np.asarray(frequencies, dtype=np.float64))
+        fd = f.to(self.device)
+        s = self._Z_scale[:, None, None]
+        Zm = None
+        for name in names:
+            A_re, A_im = self._pred_matrices(f, name)
+            par = self.distributions[name]['dist_type'] == 'parallel'
+            x = self._sample_result[self._draw_key(name)]
+            x = x / s if par else x * s
+            z = torch.complex(self._apply(A_re, x), self._apply(A_im, x))
+            z = 1.0 / z if par else z
+            Zm = z if Zm is None else Zm + z
+        if include_offsets:
+            Zr = (self._sample_result['Rinf'][..., None] * s).expand_as(Zm.real)
+            Zi = 2 * np.pi * (fd[:, None, :] if fd.dim() == 2 else fd) * (self._sample_result['induc'][..., None] * s)
+            Zm = Zm + torch.complex(Zr, Zi.expand_as(Zm.real))
+        return Zm[0].cpu().numpy() if self._single else Zm
+
+    def ridge_ReImCV(self, frequencies, Z, lambdas=None, **kw):
+        """inversion.py:902-944: Re-Im cross-validation of lambda_0.  Returns the optimum (one value per spectrum of a
+        batch); the table is in ``cv_result``.  The instance is left fitted at that lambda_0."""
+        self.ridge_fit(frequencies, Z, lambda_0='cv', cv_lambdas=lambdas, **kw)
+        return float(self._cv_lambda_0[0]) if self._single else self._cv_lambda_0
 
     def predict_Rp(self, distributions=None, percentile=None, time=None):
         """inversion.py:3033: area under the DRT, sum(coef) sqrt(pi) / epsilon."""

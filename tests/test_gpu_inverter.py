@@ -321,6 +321,18 @@ def test_predict_sigma_off_grid_score_and_weight_forms():
     hi_re, hi_im = hm.predict_sigma(f2, percentile=90)
     assert tuple(lo_re.shape) == (2, 33) and bool((lo_re > 0).all()) and bool((hi_im > 0).all())
     assert tuple(hm.score(freq, Zb).shape) == (2,)
+    # every draw's impedance; its per-frequency median is what predict_Z(percentile=50) reports
+    Zd = hm.predict_Z_distribution(f2)
+    assert tuple(Zd.shape) == (2, 80, 33)
+    med = hm.predict_Z(f2, percentile=50)
+    assert torch.allclose(torch.quantile(Zd.real, 0.5, dim=1), med.real, rtol=0, atol=1e-12)
+    assert torch.allclose(torch.quantile(Zd.imag, 0.5, dim=1), med.imag, rtol=0, atol=1e-12)
+    # accessors of the reference (inversion.py:133, :4069-4110)
+    assert hm.get_distributions() is hm.distributions and hm.get_basis() == 'gaussian' and hm.get_fit_inductance()
+    hm.set_epsilon(3.0, override_distributions=True)
+    assert hm.get_epsilon() == 3.0 and hm.distributions['DRT']['epsilon'] == 3.0 and hm.get_basis_freq() is None
+    lam = Inverter().ridge_ReImCV(freq, Z, lambdas=np.logspace(-5, -1, 5))
+    assert isinstance(lam, float) and 1e-5 <= lam <= 1e-1
     # ridge weights: an array equal to the 'modulus' weights of the scaled data reproduces weights='modulus'
     r1 = Inverter()
     r1.ridge_fit(freq, Z, weights='modulus')
