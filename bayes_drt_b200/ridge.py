@@ -74,8 +74,7 @@ def ridge_fit(inv, frequencies, Z, part='both', penalty='discrete', reg_ord=2, L
         raise ValueError(f"Invalid part {part}. Options are 'both', 'real', 'imag'")
     cv = isinstance(lambda_0, str) and lambda_0 == 'cv'
     # options outside the hot path: loud, never a silent fallback
-    for flag, nm in ((penalty == 'cholesky', "penalty='cholesky'"),
-                     (hl_fbeta is not None and (penalty != 'discrete' or not hyper_lambda),
+    for flag, nm in ((hl_fbeta is not None and (penalty == 'integral' or not hyper_lambda),
                       "hl_fbeta without the discrete hyper-lambda penalty"),
                      (hl_solution != 'analytic', "hl_solution='lm'"),
                      (hyper_weights, 'hyper_weights'), (hyper_a or hyper_b, 'hyper_a / hyper_b'),
@@ -119,11 +118,15 @@ def ridge_fit(inv, frequencies, Z, part='both', penalty='discrete', reg_ord=2, L
     bft = torch.as_tensor(1 / (2 * np.pi * tau))
     Pen = torch.zeros((3, n, n), dtype=torch.float64, device=dev)
     Lmat = None
-    if penalty == 'integral':
+    if penalty in ('integral', 'cholesky'):
         toep = mat.is_loguniform(bft)
         for o in range(3):
             Pen[o, 2:, 2:] = capi.build_M(bft, eps, o, toep, device=dev)
             m[f'M{o}'] = Pen[o, 2:, 2:]
+        if penalty == 'cholesky':  # inversion.py:2309-2321: M in the objective, L = chol(M) (upper) in the lambda rule
+            Lmat = torch.zeros((3, K, n), dtype=torch.float64, device=dev)
+            for o in range(3):
+                Lmat[o, :, 2:] = torch.linalg.cholesky(Pen[o, 2:, 2:], upper=True)
     else:
         Lmat = torch.zeros((3, K, n), dtype=torch.float64, device=dev)
         for o in range(3):
@@ -143,7 +146,8 @@ def ridge_fit(inv, frequencies, Z, part='both', penalty='discrete', reg_ord=2, L
             war, wzr = torch.zeros_like(war), torch.zeros_like(wzr)
         b = zs.shape[0]
         if hyper_lambda:
-            r = capi.ridge_fit(war, wai, wzr, wzi, Pen, Lmat, penalty=penalty, nonneg=nonneg, max_iter=max_iter,
+            r = capi.ridge_fit(war, wai, wzr, wzi, Pen, Lmat, nonneg=nonneg, max_iter=max_iter,
+                               penalty='integral' if penalty == 'integral' else 'discrete',  # 'cholesky': discrete rule
                                xtol=xtol, hl_beta=float(hl_beta), lambda_0=float(lam0), reg_ord=frac,
                                L1_penalty=L1_penalty, epsilon=eps,
                                fit_inductance=inv.fit_inductance and part_ != 'real', hl_fbeta=hl_fbeta, device=dev)

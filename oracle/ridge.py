@@ -120,6 +120,10 @@ def prep(freq, Z, basis_freq=None, epsilon=None, penalty='discrete', weights=Non
     for o in range(3):
         if penalty == 'integral':
             Pen[o, 2:, 2:] = om.construct_M(bf, order=o, epsilon=eps)
+        elif penalty == 'cholesky':  # inversion.py:2309-2321: M in the objective, L = chol(M) (upper) in the lambda rule
+            from scipy.linalg import cholesky
+            Pen[o, 2:, 2:] = om.construct_M(bf, order=o, epsilon=eps)
+            Lmat[o, :, 2:] = cholesky(Pen[o, 2:, 2:])
         else:
             Lmat[o, :, 2:] = om.construct_L(bf, tau=tau, epsilon=eps, order=o)
             Pen[o] = Lmat[o].T @ Lmat[o]
@@ -189,9 +193,9 @@ def ridge_fit(freq, Z, basis_freq=None, epsilon=None, penalty='discrete', reg_or
         prev = coef.copy()
         for o in range(3):
             if frac[o] > 0:
-                if penalty == 'discrete' and hl_fbeta is not None:
+                if penalty in ('discrete', 'cholesky') and hl_fbeta is not None:
                     lam[o] = hyper_lambda_fbeta(p['Lmat'][o][:, 2:], prev[2:], hl_fbeta, lambda_0)
-                elif penalty == 'discrete':
+                elif penalty in ('discrete', 'cholesky'):
                     lam[o] = hyper_lambda_discrete(p['Lmat'][o][:, 2:], prev[2:], hl_beta, lambda_0)
                 else:
                     factor = (100.0, 10.0, 1.0)[o]
