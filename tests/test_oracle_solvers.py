@@ -77,6 +77,46 @@ def test_ridge_loop_on_reference_spectrum():
     assert np.array_equal(r3['coef'], r4['coef'])
 
 
+def test_ridge_parts_cross_validation_and_penalty_variants():
+    """part='real'/'imag' (_convex_opt :1047-1052 + the least-squares offsets :855-873), Re-Im CV (:902-944), the
+    hl_fbeta rule (:956-964), penalty='cholesky' (:2309-2321) and preset 'Ciucci' (:274-277) of the oracle."""
+    freq, Z = load_spectrum('ZARC_uniform_0.25')
+    both = oridge.ridge_fit(freq, Z)
+    re = oridge.ridge_fit(freq, Z, part='real')
+    im = oridge.ridge_fit(freq, Z, part='imag')
+    eps = both['prep']['epsilon']
+    rp = lambda r: r['coef'].sum() * np.sqrt(np.pi) / eps
+    # either part alone recovers the spectrum (Kramers-Kronig): offsets and polarisation resistance agree to ~1 %
+    assert abs(re['R_inf'] - both['R_inf']) < 0.02 and abs(im['R_inf'] - both['R_inf']) < 0.02
+    assert abs(rp(re) - rp(both)) < 0.03 and abs(rp(im) - rp(both)) < 0.03
+    p = both['prep']
+    # the real-part fit never saw Z'': its inductance is the least-squares value on the imaginary residual
+    a_l = 2 * np.pi * p['freq'] * 1e-4
+    resid = p['Zs'].imag - p['A_im'][:, 2:] @ re['scaled_coef'][2:]
+    assert abs(re['scaled_coef'][1] - a_l @ resid / (a_l @ a_l)) < 1e-15
+    assert abs(im['scaled_coef'][0] - np.mean(p['Zs'].real - p['A_re'][:, 2:] @ im['scaled_coef'][2:])) < 1e-15
+    # hl_fbeta rule by hand
+    L = p['Lmat'][2][:, 2:]
+    c = np.linspace(0.1, 1.0, L.shape[1])
+    lam = oridge.hyper_lambda_fbeta(L, c, 0.1, 1e-2)
+    Lx2 = (L @ c) ** 2
+    assert np.allclose(lam[2:], 1e-2 / (Lx2 / (Lx2.max() * 0.1) + 1)) and lam[0] == lam[1] == 1
+    # cholesky penalty: L'L reproduces M
+    pc = oridge.prep(freq, Z, penalty='cholesky')
+    for o in range(3):
+        Lc = pc['Lmat'][o][:, 2:]
+        assert np.allclose(Lc.T @ Lc, pc['Pen'][o][2:, 2:], rtol=1e-12, atol=1e-12) and np.allclose(Lc, np.triu(Lc))
+    # cross-validation on a coarse grid: an interior optimum, and the fit is the plain fit at that lambda_0
+    grid = np.logspace(-6, 0, 7)
+    cv = oridge.ridge_fit(freq, Z, lambda_0='cv', cv_lambdas=grid)
+    assert cv['lambda_0'] in grid[1:-1] and cv['cv_result'].shape == (7, 4)
+    assert np.allclose(cv['cv_result'][:, 3], cv['cv_result'][:, 1] + cv['cv_result'][:, 2])
+    assert np.array_equal(cv['coef'], oridge.ridge_fit(freq, Z, lambda_0=cv['lambda_0'])['coef'])
+    ci = oridge.ridge_fit(freq, Z, preset='Ciucci', cv_lambdas=grid)
+    assert np.array_equal(ci['coef'], oridge.ridge_fit(freq, Z, lambda_0=ci['lambda_0'], hl_fbeta=0.1)['coef'])
+    assert abs(rp(ci) - 1.0) < 0.05
+
+
 def test_nuts_restatement_on_gaussian():
     sd = np.array([0.1, 1.0, 3.0, 10.0, 0.5])
     mu = np.array([1.0, -2.0, 0.0, 5.0, 0.3])
