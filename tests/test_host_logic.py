@@ -88,3 +88,38 @@ def test_reference_interface_errors_without_gpu():
     r = m.rel_round(np.array([123456.789012345, 0.00123456789012345]), 10)
     # utils.py:113-131: round(x, precision - floor(log10 x)) decimals
     assert r[0] == 123456.78901 and r[1] == round(0.00123456789012345, 13)
+
+
+def test_ridge_weight_forms_match_the_oracle():
+    """ridge._weights (Inverter._format_weights, inversion.py:2338-2395) on CPU tensors: named schemes against the
+    oracle's restatement, constants and arrays by their definition."""
+    import numpy as np
+    import torch
+    from bayes_drt_b200.ridge import _weights
+    from oracle import ridge as oridge
+    rng = np.random.RandomState(0)
+    Z = rng.randn(3, 11) + 1j * rng.randn(3, 11)
+    Zt = torch.tensor(Z)
+    for scheme in (None, 'unity', 'modulus', 'Orazem', 'proportional'):
+        w_re, w_im = _weights(Zt, scheme)
+        for b in range(3):
+            w = oridge.format_weights(Z[b], scheme)
+            assert np.allclose(w_re[b].numpy(), w.real, rtol=1e-15) and np.allclose(w_im[b].numpy(), w.imag, rtol=1e-15)
+    w_re, w_im = _weights(Zt, 'prop_adj')
+    p25 = np.percentile(np.abs(Z) ** 2, 25, axis=1)[:, None]
+    assert np.allclose(w_re.numpy(), 1 / (np.abs(Z.real) + p25)) and np.allclose(w_im.numpy(), 1 / (np.abs(Z.imag) + p25))
+    w_re, w_im = _weights(Zt, 2.5)
+    assert bool((w_re == 2.5).all()) and bool((w_im == 2.5).all())
+    w_re, w_im = _weights(Zt, 1 + 3j)
+    assert bool((w_re == 1).all()) and bool((w_im == 3).all())
+    a = rng.rand(11)
+    w_re, w_im = _weights(Zt, a)
+    assert tuple(w_re.shape) == (3, 11) and np.array_equal(w_re[2].numpy(), a) and np.array_equal(w_im[0].numpy(), a)
+    ac = rng.rand(3, 11) + 1j * rng.rand(3, 11)
+    w_re, w_im = _weights(Zt, ac)
+    assert np.array_equal(w_re.numpy(), ac.real) and np.array_equal(w_im.numpy(), ac.imag)
+    import pytest
+    with pytest.raises(ValueError):
+        _weights(Zt, 'nope')
+    with pytest.raises(ValueError):
+        _weights(Zt, np.ones(5))
