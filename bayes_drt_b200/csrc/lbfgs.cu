@@ -52,7 +52,7 @@ __device__ double cubic_interp(double df0, double x1, double f1, double df1, dou
 // of an entry are fetched together, so each entry costs one L2 round trip instead of two and no shared-memory
 // traffic; the summation order is that of vdot(), so the result is bitwise that of the generic path (NC == 0).
 template <int NC>
-__device__ __forceinline__ void two_loop(const double* S, const double* Y, const double* rho, double* al,
+__device__ __forceinline__ double two_loop(const double* S, const double* Y, const double* rho, double* al,
                                          const double* gk, double* pk, int D, int Dpad, int nh, int head, int H,
                                          double gamma, int lane) {
   if (NC == 0) {
@@ -78,7 +78,7 @@ __device__ __forceinline__ void two_loop(const double* S, const double* Y, const
       for (int i = lane; i < D; i += 32) pk[i] = fma(c, Sh[i], pk[i]);
       __syncwarp();
     }
-    return;
+    return vdot(gk, pk, D, lane);
   }
   constexpr int NCC = NC > 0 ? NC : 1;
   double pr[NCC];
@@ -132,12 +132,17 @@ __device__ __forceinline__ void two_loop(const double* S, const double* Y, const
       second(hidx(j), sa, ya);
     }
   }
+  double gp = 0.0;  // gk . pk in vdot's summation order
 #pragma unroll
   for (int c = 0; c < NCC; ++c) {
     const int i = lane + 32 * c;
-    if (i < D) pk[i] = pr[c];
+    if (i < D) {
+      pk[i] = pr[c];
+      gp = fma(gk[i], pr[c], gp);
+    }
   }
   __syncwarp();
+  return warp_sum(gp);
 }
 
 }  // namespace
@@ -178,15 +183,19 @@ lbfgs_kernel(BdrtModel m, bdrt_lbfgs_opts o, double* __restrict__ U, double* lp_
   const double* Zs = m.Z;
 
   // f(xn) -> f, gn = grad f ; returns false when not finite
-  auto feval = [&](double& f) -> bool {
+  // also returns the slope gn . pk along the current direction (same summation order as vdot): one pass instead of two
+  auto feval = [&](double& f, double& slope) -> bool {
     const double lp = engine_eval<TOEP, MK, FAST>(m, sm, true, xn, gn, Zs, 0);
     ++neval;
     int fin = isfinite(lp);
+    double d = 0.0;
     for (int i = lane; i < D; i += 32) {
       const double v = -gn[i];
       gn[i] = v;
       fin &= isfinite(v);
+      d = fma(v, pk[i], d);
     }
+    slope = warp_sum(d);
     __syncwarp();
     f = -lp;
     return warp_and(fin);
@@ -199,12 +208,13 @@ lbfgs_kernel(BdrtModel m, bdrt_lbfgs_opts o, double* __restrict__ U, double* lp_
   auto run_spectrum = [&](int b) {
     Zs = m.Z + (long long)b * m.N2;
     double* ub = U + (long long)b * D;
-    for (int i = lane; i < D; i += 32) xn[i] = ub[i];
+    for (int i = lane; i < D; i += 32) { xn[i] = ub[i]; pk[i] = 0.0; }  // pk: read (unused) by the first evaluation
     __syncwarp();
     neval = 0;
     double fk = nan("");
     int code = BDRT_TERM_RUNNING, it = 0;
-    if (!feval(fk)) {
+    double slope_ev = 0.0;
+    if (!feval(fk, slope_ev)) {
       code = BDRT_TERM_BADINIT;
     } else {
       for (int i = lane; i < D; i += 32) {
@@ -263,7 +273,7 @@ lbfgs_kernel(BdrtModel m, bdrt_lbfgs_opts o, double* __restrict__ U, double* lp_
               }
             }
             step_to(alpha);
-            const bool okev = feval(f1);
+            const bool okev = feval(f1, slope_ev);
             if (!zoom) {
               if (!okev) {
                 if (restarts >= 10) { ret = 1; break; }
@@ -272,7 +282,7 @@ lbfgs_kernel(BdrtModel m, bdrt_lbfgs_opts o, double* __restrict__ U, double* lp_
                 continue;
               }
               restarts = 0;
-              newDFp = vdot(gn, pk, D, lane);
+              newDFp = slope_ev;
               if (f1 > fk + alpha * c1dfp || (f1 >= prevF && nits > 0)) {
                 alo = alpha0; aloF = prevF; aloDFp = prevDFp; ahi = alpha; ahiF = f1; ahiDFp = newDFp;
                 zoom = true;
@@ -295,7 +305,7 @@ lbfgs_kernel(BdrtModel m, bdrt_lbfgs_opts o, double* __restrict__ U, double* lp_
                 continue;
               }
               retry = false;
-              newDFp = vdot(gn, pk, D, lane);
+              newDFp = slope_ev;
               if (f1 > (fk + alpha * c1dfp) || f1 >= aloF) {
                 ahi = alpha; ahiF = f1; ahiDFp = newDFp;
               } else {
@@ -356,15 +366,15 @@ lbfgs_kernel(BdrtModel m, bdrt_lbfgs_opts o, double* __restrict__ U, double* lp_
         __syncwarp();
         __threadfence_block();
         // ---------------- two-loop recursion -> pk
+        double gp;
         if (D <= 32 * 7)
-          two_loop<7>(S, Y, rho, al, gn, pk, D, Dpad, nh, head, H, gamma, lane);
+          gp = two_loop<7>(S, Y, rho, al, gn, pk, D, Dpad, nh, head, H, gamma, lane);
         else if (D <= 32 * 12)
-          two_loop<12>(S, Y, rho, al, gn, pk, D, Dpad, nh, head, H, gamma, lane);
+          gp = two_loop<12>(S, Y, rho, al, gn, pk, D, Dpad, nh, head, H, gamma, lane);
         else
-          two_loop<0>(S, Y, rho, al, gn, pk, D, Dpad, nh, head, H, gamma, lane);
+          gp = two_loop<0>(S, Y, rho, al, gn, pk, D, Dpad, nh, head, H, gamma, lane);
         // ---------------- convergence tests, Stan's order
         const double df = fabs(fk_1 - fk);
-        const double gp = vdot(gn, pk, D, lane);
         gp_prev = gp;
         if (df < o.tol_obj)
           code = BDRT_TERM_ABSF;
