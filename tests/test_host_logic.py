@@ -123,3 +123,24 @@ def test_ridge_weight_forms_match_the_oracle():
         _weights(Zt, 'nope')
     with pytest.raises(ValueError):
         _weights(Zt, np.ones(5))
+
+
+def test_bench_reference_arm_prints_one_contract_line():
+    """`bench.py --impl reference` (the CPU arm the driver runs beside ours): exactly one JSON line on stdout with the
+    contract's keys, timed on a bounded sample of the workload."""
+    import json
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, os.path.join(root, 'bench.py'), '--impl', 'reference', '--steps', '1', '--warmup',
+                        '0', '--cpu-sample', '2'], capture_output=True, text=True, timeout=600, cwd=root)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [ln for ln in r.stdout.splitlines() if ln.strip()]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d['impl'] == 'reference' and d['metric'] == 'spectra/sec (MAP)' and d['unit'] == 'spectra/s'
+    assert d['higher_is_better'] is True and d['value'] > 0 and d['steps'] == 1
+    assert d['cpu_baseline']['kind'] == 'port' and d['cpu_baseline']['cores'] >= 1 and d['cpu_baseline']['value'] == d['value']
+    assert d['e2e']['value'] == d['value'] and d['e2e']['h2d_bytes_per_step'] == 0 and d['e2e']['d2h_bytes_per_step'] == 0
+    assert 'workload' in d['config']
