@@ -144,3 +144,31 @@ def test_bench_reference_arm_prints_one_contract_line():
     assert d['cpu_baseline']['kind'] == 'port' and d['cpu_baseline']['cores'] >= 1 and d['cpu_baseline']['value'] == d['value']
     assert d['e2e']['value'] == d['value'] and d['e2e']['h2d_bytes_per_step'] == 0 and d['e2e']['d2h_bytes_per_step'] == 0
     assert 'workload' in d['config']
+
+
+def test_numeric_helpers_against_reference_vectors():
+    """tests/golden/utils.npz holds outputs of the reference's utils.py (rel_round, is_loguniform, get_outlier_thresh,
+    r2_score; generated by scripts/make_golden_utils.py).  The host mirrors and the torch expressions Inverter uses for
+    the inter-quartile rule (check_outliers) and r^2 (score) reproduce them."""
+    import os
+    import numpy as np
+    import torch
+    from bayes_drt_b200 import matrices as m
+    from oracle import matrices as om
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden', 'utils.npz'))
+    for prec in (3, 10):
+        assert np.array_equal(m.rel_round(g['rr/x'], prec), g[f'rr/p{prec}'])
+    i = 0
+    while f'lu/g{i}' in g.files:
+        assert m.is_loguniform(g[f'lu/g{i}']) == bool(g[f'lu/r{i}']) == om.is_loguniform(g[f'lu/g{i}']), i
+        i += 1
+    assert i == 7
+    y = torch.tensor(g['ot/y'])[None, :]
+    for f in (1.5, 3.5, 4.0):  # Inverter._ridge_outlier_flags: q75 + f * (q75 - q25), utils.py:143-146
+        q = torch.quantile(y, torch.tensor([0.25, 0.75], dtype=torch.float64), dim=1)
+        assert abs(float(q[1] + f * (q[1] - q[0])) - float(g[f'ot/t{f}'])) <= 1e-12 * float(g[f'ot/t{f}'])
+    yt, yh, w = (torch.tensor(g[k])[None, :] for k in ('r2/y', 'r2/yhat', 'r2/w'))
+    for wt, key in ((torch.ones_like(w), 'r2/plain'), (w, 'r2/weighted')):  # Inverter.score, utils.py:149-165
+        avg = (wt * yt).sum(dim=1, keepdim=True) / wt.sum(dim=1, keepdim=True)
+        r2 = 1 - (wt * (yh - yt) ** 2).sum(dim=1) / (wt * (yt - avg) ** 2).sum(dim=1)
+        assert abs(float(r2) - float(g[key])) <= 1e-13
