@@ -7,7 +7,12 @@ Follows Inverter.ridge_fit (inversion.py:142-900; default hyper-lambda path :489
 _prep_matrices (:2127-2336) and the result rescaling (:875-898).  SURVEY appendix B has the same iteration in
 pseudo-code.
 
-The QP itself is cvxopt.solvers.qp in the reference (third-party, absent here: **parity unpinned**).  Each QP is
+Pinned against the reference's own code: tests/golden/ridge_reference.npz holds outputs of the unmodified
+Inverter.ridge_fit (imported from the reference, scripts/make_golden_ridge_reference.py) for eleven option sets
+(defaults, presets 'Huang' / 'Ciucci', integral / discrete / cholesky penalties, free sign, mixed orders, one-part fits,
+hl_fbeta, Re-Im cross-validation) and this restatement reproduces them to 1e-9 (1e-6 for the max-normalised hl_fbeta
+rule) -- tests/test_oracle_solvers.py.  The one substitution in that run is the QP solver: cvxopt.solvers.qp
+(third-party, absent here: its own arithmetic stays **unpinned**) is replaced by the exact solver below.  Each QP is
 strictly convex with simple bounds, so its solution is unique; the oracle solves it *exactly* by block principal
 pivoting (active-set with exact Cholesky solves, KKT residual ~1e-13), which is what cvxopt's interior-point iterates
 converge to within its own tolerances (abstol 1e-7, reltol 1e-6).

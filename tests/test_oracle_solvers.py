@@ -2,6 +2,7 @@
 bound-constrained QP (vs scipy's NNLS / bounded least squares), the hyper-lambda ridge loop (vs the survey's measured
 values on the reference's simulated spectrum), and the NUTS restatement on a Gaussian with known moments."""
 import numpy as np
+import pytest
 from scipy.optimize import lsq_linear, nnls
 
 from helpers import load_spectrum
@@ -137,3 +138,36 @@ def test_nuts_restatement_on_gaussian():
         m, s = x[:, :, i].mean(), x[:, :, i].std(ddof=1)
         assert abs(m - mu[i]) < 5 * sd[i] / np.sqrt(ess)
         assert abs(np.log(s / sd[i])) < 0.15
+
+
+RIDGE_REFERENCE_CASES = {
+    'default': dict(), 'huang': dict(preset='Huang'),
+    'init_from_ridge': dict(penalty='integral', lambda_0=1, hl_beta=5, weights='modulus'),
+    'free_sign': dict(nonneg=False), 'mixed_orders': dict(reg_ord=[0.2, 0.3, 0.5], L1_penalty=0.01),
+    'real_part': dict(part='real'), 'imag_part': dict(part='imag', weights='modulus'), 'fbeta': dict(hl_fbeta=0.1),
+    'cholesky': dict(penalty='cholesky'), 'cv': dict(lambda_0='cv', cv_lambdas=np.logspace(-6, 0, 7)),
+    'ciucci': dict(preset='Ciucci', cv_lambdas=np.logspace(-6, 0, 7)),
+}
+
+
+@pytest.mark.parametrize('case', sorted(RIDGE_REFERENCE_CASES))
+def test_ridge_oracle_against_the_reference_ridge_fit(case):
+    """tests/golden/ridge_reference.npz: outputs of the reference's own Inverter.ridge_fit (inversion.py:142-900,
+    imported unmodified; scripts/make_golden_ridge_reference.py) with cvxopt.solvers.qp replaced by an exact solver
+    of the same QP.  The oracle's restatement of everything around the QP -- scaling, weights, matrices, the
+    hyper-lambda rules, the stop test, one-part fits, Re-Im cross-validation, presets, rescaling -- reproduces them."""
+    import os
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden', 'ridge_reference.npz'))
+    for name in ('ZARC_uniform_0.25', '2ZARC_uniform_0.25'):
+        freq, Z = load_spectrum(name)
+        o = oridge.ridge_fit(freq, Z, **RIDGE_REFERENCE_CASES[case])
+        key = f'{name}/{case}'
+        ref = g[key + '/coef']
+        tol = 1e-6 if case in ('fbeta', 'ciucci') else 1e-9  # the max-normalised rule amplifies rounding
+        assert np.max(np.abs(o['coef'] - ref)) <= tol * np.abs(ref).max(), key
+        assert abs(o['R_inf'] - float(g[key + '/R_inf'])) <= tol * abs(float(g[key + '/R_inf']))
+        assert abs(o['inductance'] - float(g[key + '/inductance'])) <= tol * max(abs(float(g[key + '/inductance'])), 1e-9)
+        if key + '/cv_result' in g.files:
+            tab = g[key + '/cv_result']
+            assert o['lambda_0'] == tab[np.argmin(tab[:, 3]), 0]
+            assert np.allclose(o['cv_result'][:, 1:] * o['Z_scale'] ** 2, tab[:, 1:], rtol=1e-6)
