@@ -12,10 +12,13 @@ Follows
   * Stan transforms / densities  [Stan-upstream 2.19.1]: real<lower=0> theta = exp(u), Jacobian +u (sampling only);
                                  '~' statements drop constant terms.
 
-The Stan / pystan natives are not in the reference tree nor in this image: this part of the oracle is *parity
-unpinned* (no reference-side golden vector exists); it is anchored on the model files line by line and checked
-against (a) an independent literal transcription differentiated by torch autograd (tests/test_oracle_model.py) and
-(b) the paper's MAP outputs code_EchemActa/map_results/*.csv (loose, ~1 % of peak).
+Pinning.  Data preparation: against the Stan input the reference's own Inverter.fit builds (tests/golden/stan_data.npz,
+tests/test_oracle_stan_data.py).  Log-density and gradient: against a mechanical evaluation of the reference's Stan
+source text (scripts/stan_subset_interpreter.py reads the *_modelcode.txt files in place; tests/golden/
+stan_logdensity.npz, tests/test_oracle_stan_source.py), against an independent literal transcription differentiated by
+torch autograd (tests/test_oracle_model.py) and, loosely (~1 % of peak), against the paper's MAP outputs
+code_EchemActa/map_results/*.csv.  The Stan / pystan natives themselves are neither in the reference tree nor in this
+image, so Stan's own floating-point evaluation is not reproduced bit for bit.
 """
 import numpy as np
 
