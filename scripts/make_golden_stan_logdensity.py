@@ -95,6 +95,12 @@ for key, (name, dat, meta) in CASES.items():
             lps.append(float(lp))
         out[key + f'/lp_jac{int(jac)}'] = np.array(lps)
         out[key + f'/grad_jac{int(jac)}'] = np.array(grads)
+    env = {}
+    prog.log_prob(dat, torch.tensor(U[0]), False, env_out=env)  # what Stan reports for the first point
+    for nm in ('x', 'xs', 'xp', 'xp1', 'xp2', 'Rinf', 'induc', 'sigma_res', 'alpha_prop', 'alpha_re', 'alpha_im',
+               'sigma_tot', 'sigma_out', 'Z_hat'):
+        if nm in env:
+            out[key + '/tp/' + nm] = env[nm]
     print(key, 'D', D, 'lp', out[key + '/lp_jac0'])
 dst = os.path.join(ROOT, 'tests', 'golden', 'stan_logdensity.npz')
 np.savez_compressed(dst, **out)

@@ -233,8 +233,9 @@ class Program:
             types[name] = typ
         return out, types
 
-    def log_prob(self, data, u, jacobian):
-        """log density at the unconstrained point u (torch float64 vector, Stan's declaration order)."""
+    def log_prob(self, data, u, jacobian, env_out=None):
+        """log density at the unconstrained point u (torch float64 vector, Stan's declaration order).  ``env_out``: a
+        dict that receives every parameter and transformed parameter by name (what Stan reports back)."""
         env = self._data_env(data)
         params, types = self._params(env)
         lp = torch.zeros((), dtype=torch.float64)
@@ -251,6 +252,8 @@ class Program:
         check = []
         for stmt in _statements(self.blocks.get('transformed parameters', '')):
             self._run(stmt, env, check)
+        if env_out is not None:
+            env_out.update({k: v.t.detach().numpy().copy() for k, v in env.items() if isinstance(v, V)})
         for name in check:  # Stan validates the declared bounds at the end of the block and rejects the point
             if bool((env[name].t < 0).any()):
                 return torch.tensor(-math.inf, dtype=torch.float64)

@@ -53,3 +53,17 @@ def test_logpost_matches_the_stan_source(program, mode):
         for i in ok:
             g = res[i][1]
             assert np.max(np.abs(g - ref_g[i])) <= 1e-10 * np.max(np.abs(ref_g[i])), (key, jac, i)
+
+
+@pytest.mark.parametrize('mode', ['optimize', 'sample'])
+@pytest.mark.parametrize('program', PROGRAMS)
+def test_constrain_matches_the_stan_source(program, mode):
+    """The parameters and transformed parameters Stan reports (what the reference reads back, inversion.py:1229-1276)."""
+    mod, d = _oracle(program, mode)
+    key = f'{program}/{mode}'
+    out = mod.constrain(G[key + '/U'][0], d)
+    names = [k[len(key + '/tp/'):] for k in G.files if k.startswith(key + '/tp/')]
+    assert {'Rinf', 'induc', 'sigma_tot', 'sigma_res', 'alpha_prop', 'alpha_re', 'alpha_im'} <= set(names)
+    for nm in names:
+        ref = G[key + '/tp/' + nm]
+        assert np.max(np.abs(np.asarray(out[nm]) - ref)) <= 1e-12 * np.max(np.abs(ref)), (key, nm)
