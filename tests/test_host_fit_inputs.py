@@ -1,0 +1,191 @@
+"""CPU: what the shipped host code of bayes_drt_b200.Inverter.fit hands to the CUDA solvers, against what the
+reference's own Inverter.fit hands to Stan (tests/golden/stan_data.npz, scripts/make_golden_stan_data.py).
+
+The device library is replaced here by a recorder: kernel matrices come from the oracle (their CUDA builders are
+tested against the same reference matrices on the GPU), capi.SeriesProblem captures its arguments and aborts the fit.
+Everything between the user's call and that point -- sorting, scaling, default grids, model choice, constants of each
+mode, stacking, the parallel families -- is the shipped code, running on CPU tensors."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import matrices as om
+
+G = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden', 'stan_data.npz'))
+FREQ, Z = G['freq'], G['Z']
+BF = np.logspace(6, -2, 81)
+TP = {'kernel': 'DDT', 'symmetry': 'planar', 'bc': 'transmissive', 'dist_type': 'parallel', 'basis_freq': BF}
+BP = {'kernel': 'DDT', 'symmetry': 'planar', 'bc': 'blocking', 'dist_type': 'parallel', 'basis_freq': BF}
+DRT = {'kernel': 'DRT', 'basis_freq': BF}
+CASES = {
+    'series_opt': (dict(), dict(mode='optimize')),
+    'series_sample': (dict(), dict(mode='sample')),
+    'series_pos_opt': (dict(), dict(mode='optimize', nonneg=True)),
+    'series_out_opt': (dict(), dict(mode='optimize', outliers=True)),
+    'series_pos_out_sample': (dict(), dict(mode='sample', nonneg=True, outliers=True, outlier_lambda=5, sigma_min=0.001,
+                                           inductance_scale=2)),
+    'series_basis_eq_freq': (dict(basis_freq=FREQ), dict(mode='optimize')),
+    'series_noscale': (dict(), dict(mode='optimize', scale_Z=False)),
+    'sp_opt': (dict(distributions={'DRT': dict(DRT), 'TP-DDT': dict(TP, x_scale=0.8)}), dict(mode='optimize', nonneg=True)),
+    'sp_sample': (dict(distributions={'DRT': dict(DRT), 'TP-DDT': dict(TP, x_scale=0.8)}), dict(mode='sample', nonneg=True)),
+    'parallel_tp_opt': (dict(distributions={'TP-DDT': dict(TP)}), dict(mode='optimize')),
+    'parallel_bp_sample': (dict(distributions={'BP-DDT': dict(BP)}), dict(mode='sample')),
+    's2p_opt': (dict(distributions={'DRT': dict(DRT), 'TP-DDT': dict(TP, x_scale=0.8), 'BP-DDT': dict(BP)}),
+                dict(mode='optimize', nonneg=True)),
+    's2p_sample': (dict(distributions={'DRT': dict(DRT), 'TP-DDT': dict(TP, x_scale=0.8), 'BP-DDT': dict(BP)}),
+                   dict(mode='sample', nonneg=True)),
+}
+
+
+class Abort(Exception):
+    pass
+
+
+class Recorder:
+    """stands in for capi.SeriesProblem: keeps the constructor arguments, stops the fit at the first solver call"""
+    last = None
+
+    def __init__(self, A, Z, freq, L, **kw):
+        self.A, self.Z, self.freq, self.L, self.kw = A, Z, freq, L, kw
+        self.B, self.Nf, self.K = Z.shape[0], Z.shape[1] // 2, A.shape[-1]
+        n_par = [kw[k].shape[-1] for k in ('Ap', 'Ap2') if kw.get(k) is not None]
+        self.D = 2 * (self.K + sum(n_par)) + 6 + 3 * (1 + len(n_par)) + (2 * self.Nf if kw.get('outliers') else 0)
+        Recorder.last = self
+
+    def map_lbfgs(self, *a, **k):
+        self.call = ('optimizing', k)
+        raise Abort
+
+    def nuts(self, *a, **k):
+        self.call = ('sampling', k)
+        raise Abort
+
+
+@pytest.fixture
+def host(monkeypatch):
+    from bayes_drt_b200 import inverter
+
+    def build_A(freq, tau, eps, kernel='DRT', dist_type='series', symmetry='planar', bc='transmissive', ct=False,
+                k_ct=None, device=None):
+        kw = dict(tau=np.asarray(tau, dtype=np.float64), epsilon=float(eps), kernel=kernel, dist_type=dist_type,
+                  symmetry=symmetry, bc=bc, ct=ct, k_ct=k_ct)
+        f = np.asarray(freq, dtype=np.float64)
+        return torch.tensor(om.construct_A(f, 'real', **kw)), torch.tensor(om.construct_A(f, 'imag', **kw))
+
+    def build_L(freq, tau, eps, order, device=None):
+        return torch.tensor(om.construct_L(np.asarray(freq, dtype=np.float64), tau=np.asarray(tau, dtype=np.float64),
+                                           epsilon=float(eps), order=order))
+    monkeypatch.setattr(inverter, 'context', lambda device=None: type('Ctx', (), {'device': torch.device('cpu')})())
+    monkeypatch.setattr(inverter.capi, 'build_A', build_A)
+    monkeypatch.setattr(inverter.capi, 'build_L', build_L)
+    monkeypatch.setattr(inverter.capi, 'SeriesProblem', Recorder)
+    return inverter
+
+
+def _proj(case, key, M, rtol=1e-11):
+    M = np.asarray(M, dtype=np.float64)
+    r = np.random.RandomState(M.shape[0] * 1000 + M.shape[1])
+    v, u = r.standard_normal(M.shape[1]), r.standard_normal(M.shape[0])
+    a, b = G[f'{case}/{key}@v'], G[f'{case}/u@{key}']
+    assert np.max(np.abs(M @ v - a)) <= rtol * np.max(np.abs(a)), (case, key)
+    assert np.max(np.abs(u @ M - b)) <= rtol * np.max(np.abs(b)), (case, key)
+
+
+@pytest.mark.parametrize('case', sorted(CASES))
+def test_fit_hands_the_solver_what_the_reference_hands_stan(case, host):
+    ikw, fkw = CASES[case]
+    inv = host.Inverter(**ikw)
+    with pytest.raises(Abort):
+        inv.fit(FREQ[::-1].copy(), Z[::-1].copy(), **fkw)  # ascending input: the sort is part of what is checked
+    p, kw = Recorder.last, Recorder.last.kw
+    assert p.call[0] == ('optimizing' if fkw['mode'] == 'optimize' else 'sampling')
+    # the Stan program the reference selects (Inverter._get_stan_model) <-> the model flags of the C ABI
+    ref_model = str(G[f'{case}/model'])[:-len('_StanModel.pkl')]
+    family = 'Series-2Parallel' if kw.get('Ap2') is not None else ('Series-Parallel' if kw.get('Ap') is not None else
+                                                                   ('Parallel' if kw.get('parallel') else 'Series'))
+    pos = kw['nonneg'] and family != 'Parallel'
+    assert ref_model == family + ('_pos' if pos else '') + ('_outliers' if kw.get('outliers') else '')
+    assert float(inv._Z_scale[0]) == pytest.approx(float(G[f'{case}/Z_scale']), rel=1e-13)
+    assert np.array_equal(p.freq.numpy(), G[f'{case}/freq'])
+    assert np.max(np.abs(p.Z[0].numpy() - G[f'{case}/Z'])) <= 1e-13 * np.max(np.abs(G[f'{case}/Z']))
+    names = {'Series': ('A', ['L0', 'L1', 'L2']), 'Parallel': ('A', ['L0', 'L1', 'L2']),
+             'Series-Parallel': ('As', ['L0s', 'L1s', 'L2s']), 'Series-2Parallel': ('As', ['L0s', 'L1s', 'L2s'])}[family]
+    _proj(case, names[0], p.A.numpy())
+    for o, nm in enumerate(names[1]):
+        _proj(case, nm, p.L[o].numpy())
+    for k_ref, k in (('sigma_min', 'sigma_min'), ('ups_alpha', 'ups_alpha'), ('ups_beta', 'ups_beta'),
+                     ('induc_scale', 'induc_scale')):
+        assert float(G[f'{case}/{k_ref}']) == pytest.approx(float(kw[k]), rel=1e-14), k
+    if kw.get('outliers'):
+        for k in ('sigma_out_lambda', 'sigma_out_alpha', 'sigma_out_beta'):
+            assert float(G[f'{case}/{k}']) == pytest.approx(float(kw[k]), rel=1e-14), k
+    if family == 'Series-Parallel':
+        _proj(case, 'Ap', kw['Ap'].numpy())
+        for o in range(3):
+            _proj(case, f'L{o}p', kw['Lp'][o].numpy())
+        assert float(G[f'{case}/x_sum_invscale']) == kw['x_sum_invscale'] and float(G[f'{case}/xp_scale']) == kw['xp_scale']
+    if family == 'Series-2Parallel':  # parallel distributions in the reference's by-name order
+        _proj(case, 'Ap1', kw['Ap'].numpy())
+        _proj(case, 'Ap2', kw['Ap2'].numpy())
+        for o in range(3):
+            _proj(case, f'L{o}p1', kw['Lp'][o].numpy())
+            _proj(case, f'L{o}p2', kw['Lp2'][o].numpy())
+        assert float(G[f'{case}/x_sum_invscale']) == kw['x_sum_invscale']
+        assert float(G[f'{case}/xp1_scale']) == kw['xp_scale'] and float(G[f'{case}/xp2_scale']) == kw['xp2_scale']
+    if fkw['mode'] == 'sample':  # inversion.py:1218-1221
+        assert p.call[1]['chains'] == int(G[f'{case}/chains']) and p.call[1]['warmup'] == int(G[f'{case}/warmup'])
+        assert p.call[1]['warmup'] + p.call[1]['samples'] == int(G[f'{case}/iter'])
+        assert p.call[1]['seed'] == int(G[f'{case}/seed'])
+    else:
+        assert p.call[1]['max_iter'] == int(G[f'{case}/iter'])
+
+
+RIDGE_CASES = [dict(), dict(preset='Huang'), dict(penalty='integral', lambda_0=1, hl_beta=5, weights='modulus'),
+               dict(nonneg=False, weights='proportional'), dict(reg_ord=[0.2, 0.3, 0.5], L1_penalty=0.01),
+               dict(penalty='cholesky', weights='Orazem'), dict(hl_fbeta=0.1, scale_Z=False)]
+
+
+@pytest.mark.parametrize('kw', RIDGE_CASES)
+def test_ridge_fit_hands_the_kernel_the_system_of_the_reference(kw, host, monkeypatch):
+    """Host side of ridge_fit: the weighted, augmented system and the options that reach bdrt_ridge_fit, against the
+    oracle's prep() -- whose results are pinned to the reference's own ridge_fit in ridge_reference.npz."""
+    from bayes_drt_b200 import ridge
+    from oracle import ridge as oridge
+    rec = {}
+
+    def ridge_fit(WA_re, WA_im, WZ_re, WZ_im, Pen, Lmat, **o):
+        rec.update(WA_re=WA_re, WA_im=WA_im, WZ_re=WZ_re, WZ_im=WZ_im, Pen=Pen, Lmat=Lmat, o=o)
+        raise Abort
+
+    def build_M(freq, eps, order, toeplitz, device=None):
+        return torch.tensor(om.construct_M(np.asarray(freq, dtype=np.float64), order=order, epsilon=float(eps)))
+    monkeypatch.setattr(ridge.capi, 'ridge_fit', ridge_fit)
+    monkeypatch.setattr(ridge.capi, 'build_M', build_M)
+    inv = host.Inverter()
+    with pytest.raises(Abort):
+        inv.ridge_fit(FREQ[::-1].copy(), Z[::-1].copy(), **kw)
+    k = dict(kw)
+    if k.pop('preset', None) == 'Huang':
+        k.update(penalty='integral', hl_beta=2.5, lambda_0=1e-2, weights='modulus')
+    p = oridge.prep(FREQ, Z, penalty=k.get('penalty', 'discrete'), weights=k.get('weights'), scale_Z=k.get('scale_Z', True))
+    close = lambda a, b: np.max(np.abs(np.asarray(a) - b)) <= 1e-12 * max(np.max(np.abs(b)), 1e-300)
+    WA_re, WA_im = rec['WA_re'].numpy(), rec['WA_im'].numpy()
+    assert close(WA_re[0] if WA_re.ndim == 3 else WA_re, p['WA_re']) and close(WA_im[0] if WA_im.ndim == 3 else WA_im, p['WA_im'])
+    assert close(rec['WZ_re'][0].numpy(), p['WZ_re']) and close(rec['WZ_im'][0].numpy(), p['WZ_im'])
+    assert close(rec['Pen'].numpy(), p['Pen'])
+    if k.get('penalty', 'discrete') != 'integral':
+        assert close(rec['Lmat'].numpy(), p['Lmat'])
+    o = rec['o']
+    assert o['penalty'] == ('integral' if k.get('penalty') == 'integral' else 'discrete')
+    assert o['nonneg'] == k.get('nonneg', True) and o['max_iter'] == 20 and o['xtol'] == 1e-3
+    assert o['hl_beta'] == k.get('hl_beta', 2.5) and o['lambda_0'] == k.get('lambda_0', 1e-2)
+    frac = np.zeros(3)
+    if isinstance(k.get('reg_ord', 2), int):
+        frac[k.get('reg_ord', 2)] = 1
+    else:
+        frac[:] = k['reg_ord']
+    assert np.array_equal(np.asarray(o['reg_ord'], dtype=np.float64), frac) and o['L1_penalty'] == k.get('L1_penalty', 0)
+    assert o['epsilon'] == pytest.approx(p['epsilon'], rel=1e-14) and o['hl_fbeta'] == k.get('hl_fbeta')
+    assert float(inv._Z_scale[0]) == pytest.approx(p['Z_scale'], rel=1e-14)
