@@ -77,6 +77,17 @@ for name in ('ZARC_uniform_0.25', '2ZARC_uniform_0.25'):
         if hasattr(inv, 'cv_result') and 'cv' in str(kw.get('lambda_0', '')) + str(kw.get('preset', '')).replace('Ciucci', 'cv'):
             out[key + '/cv_result'] = inv.cv_result.values.astype(np.float64)
         print(key, 'R_inf %.6f' % inv.R_inf, 'sum coef %.6f' % out[key + '/coef'].sum())
+# check_outliers without a Stan fit (inversion.py:3313-3367): ridge fit with preset 'Huang' + inter-quartile rule
+freq, Z = g['ZARC_uniform_0.25/freq'], g['ZARC_uniform_0.25/Z']
+Zo = Z.copy()
+Zo[30] += 0.2 + 0.2j
+Zo[55] -= 0.1j
+Zo[70] += 0.02
+out['outliers/Z'] = Zo
+for thr in (0.5, 1.5, 4):
+    inv = Inverter()
+    out[f'outliers/idx_t{thr}'] = np.asarray(inv.check_outliers(freq, Zo, threshold=thr, use_existing_fit=False)).ravel()
+    print('outliers at threshold', thr, out[f'outliers/idx_t{thr}'])
 dst = os.path.join(ROOT, 'tests', 'golden', 'ridge_reference.npz')
 np.savez_compressed(dst, **out)
 print('wrote', dst, os.path.getsize(dst), 'bytes')

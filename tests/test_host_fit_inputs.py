@@ -189,3 +189,38 @@ def test_ridge_fit_hands_the_kernel_the_system_of_the_reference(kw, host, monkey
     assert np.array_equal(np.asarray(o['reg_ord'], dtype=np.float64), frac) and o['L1_penalty'] == k.get('L1_penalty', 0)
     assert o['epsilon'] == pytest.approx(p['epsilon'], rel=1e-14) and o['hl_fbeta'] == k.get('hl_fbeta')
     assert float(inv._Z_scale[0]) == pytest.approx(p['Z_scale'], rel=1e-14)
+
+
+def test_check_outliers_ridge_branch_matches_the_reference(host, monkeypatch):
+    """Inverter.check_outliers without a Stan fit (inversion.py:3313-3367): ridge fit with preset 'Huang', residuals
+    relative to |Z|, inter-quartile rule.  The shipped host code runs on CPU with the device ridge solver replaced by
+    the oracle's (pinned to the reference's ridge_fit); the flagged indices are the reference's own."""
+    from bayes_drt_b200 import ridge
+    from oracle import ridge as oridge
+    R = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden', 'ridge_reference.npz'))
+    Zo = R['outliers/Z']
+    seen = {}
+
+    def ridge_fit(inv, frequencies, Zb, **kw):
+        seen.update(kw)
+        f = np.asarray(frequencies, dtype=np.float64)
+        Zn = np.asarray(Zb.cpu() if torch.is_tensor(Zb) else Zb).reshape(-1, len(f))
+        rs = [oridge.ridge_fit(f, z, **kw) for z in Zn]
+        inv.f_train, inv.Z_train = rs[0]['prep']['freq'], torch.tensor(Zn)
+        inv._Z_scale = torch.tensor([r['Z_scale'] for r in rs], dtype=torch.float64)
+        inv.distributions['DRT']['tau'], inv.distributions['DRT']['epsilon'] = rs[0]['prep']['tau'], rs[0]['prep']['epsilon']
+        inv.distribution_fits = {'DRT': {'coef': torch.tensor(np.stack([r['coef'] for r in rs]))}}
+        inv.R_inf = torch.tensor([r['R_inf'] for r in rs], dtype=torch.float64)
+        inv.inductance = torch.tensor([r['inductance'] for r in rs], dtype=torch.float64)
+        inv.fit_type, inv._recalc_mat = 'ridge', False
+        return inv
+    monkeypatch.setattr(ridge, 'ridge_fit', ridge_fit)
+    for thr in (0.5, 1.5, 4):
+        inv = host.Inverter()
+        idx = inv.check_outliers(FREQ, Zo, threshold=thr, use_existing_fit=False)
+        assert seen == {'preset': 'Huang'}
+        assert np.array_equal(np.asarray(idx), R[f'outliers/idx_t{thr}']), thr
+    # batch form: (spectrum, frequency) pairs; the clean spectrum contributes its own noise-level flags only
+    inv = host.Inverter()
+    pairs = inv.check_outliers(FREQ, np.stack([Z, Zo]), threshold=4, use_existing_fit=False)
+    assert [int(j) for i, j in pairs.tolist() if i == 1] == list(R['outliers/idx_t4'])
