@@ -92,12 +92,17 @@ CASES = {
     's2p_sample': (dict(distributions={'DRT': dict(DRT), 'TP-DDT': dict(TP, x_scale=0.8), 'BP-DDT': dict(BP)}),
                    dict(mode='sample', nonneg=True)),
 }
+# outliers='auto' (inversion.py:1171-1187) on a spectrum with two gross outliers (made by make_golden_ridge_reference.py)
+Zo = np.load(os.path.join(ROOT, 'tests', 'golden', 'ridge_reference.npz'))['outliers/Z']
+CASES['auto_contaminated'] = (dict(), dict(mode='optimize', outliers='auto'))
+CASES['auto_contaminated_ridge_init'] = (dict(), dict(mode='optimize', outliers='auto', init_from_ridge=True))
+CASES['auto_clean_ridge_init'] = (dict(), dict(mode='sample', outliers='auto', init_from_ridge=True))
 rng = np.random.RandomState(5)
-out = {'freq': freq, 'Z': Z}
+out = {'freq': freq, 'Z': Z, 'Z_contaminated': Zo}
 for case, (ikw, fkw) in CASES.items():
     inv = Inverter(**ikw)
     try:
-        inv.fit(freq, Z, **fkw)
+        inv.fit(freq, Zo if 'contaminated' in case else Z, **fkw)
     except Abort:
         pass
     dat = captured['dat']

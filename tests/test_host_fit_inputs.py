@@ -224,3 +224,72 @@ def test_check_outliers_ridge_branch_matches_the_reference(host, monkeypatch):
     inv = host.Inverter()
     pairs = inv.check_outliers(FREQ, np.stack([Z, Zo]), threshold=4, use_existing_fit=False)
     assert [int(j) for i, j in pairs.tolist() if i == 1] == list(R['outliers/idx_t4'])
+
+
+def _oracle_ridge(monkeypatch):
+    """replace the device ridge solver behind Inverter by the oracle's (pinned to the reference's ridge_fit)"""
+    from bayes_drt_b200 import ridge
+    from oracle import ridge as oridge
+
+    def ridge_fit(inv, frequencies, Zb, **kw):
+        f = np.asarray(frequencies, dtype=np.float64)
+        Zn = np.asarray(Zb.cpu() if torch.is_tensor(Zb) else Zb).reshape(-1, len(f))
+        kw = {k: v for k, v in kw.items() if k != 'hyper_lambda'}
+        rs = [oridge.ridge_fit(f, z, **kw) for z in Zn]
+        inv.f_train, inv.Z_train = rs[0]['prep']['freq'], torch.tensor(Zn)
+        inv._Z_scale = torch.tensor([r['Z_scale'] for r in rs], dtype=torch.float64)
+        inv.distributions['DRT']['tau'], inv.distributions['DRT']['epsilon'] = rs[0]['prep']['tau'], rs[0]['prep']['epsilon']
+        inv.distribution_fits = {'DRT': {'coef': torch.tensor(np.stack([r['coef'] for r in rs]))}}
+        inv.R_inf = torch.tensor([r['R_inf'] for r in rs], dtype=torch.float64)
+        inv.inductance = torch.tensor([r['inductance'] for r in rs], dtype=torch.float64)
+        inv.fit_type, inv._recalc_mat = 'ridge', False
+        return inv
+    monkeypatch.setattr(ridge, 'ridge_fit', ridge_fit)
+
+
+class InitRecorder(Recorder):
+    """also keeps the initial points handed to the solver"""
+    def map_lbfgs(self, u0, **k):
+        self.u0 = u0
+        return super().map_lbfgs(u0, **k)
+
+    def nuts(self, u0, **k):
+        self.u0 = u0
+        return super().nuts(u0, **k)
+
+
+@pytest.mark.parametrize('case,mode,ridge_init', [('auto_contaminated', 'optimize', False),
+                                                   ('auto_contaminated_ridge_init', 'optimize', True),
+                                                   ('auto_clean_ridge_init', 'sample', True),
+                                                   ('series_ridge_init', 'optimize', True)])
+def test_auto_outliers_and_ridge_initialisation_flow(case, mode, ridge_init, host, monkeypatch):
+    """outliers='auto' (inversion.py:1171-1187) and init_from_ridge (:1154-1160, :1616-1682) in the shipped fit():
+    the Stan program chosen for the spectrum, the data it gets, and the initial values taken from the ridge solution."""
+    _oracle_ridge(monkeypatch)
+    monkeypatch.setattr(host.capi, 'SeriesProblem', InitRecorder)
+    Zin = G['Z_contaminated'] if 'contaminated' in case else Z
+    inv = host.Inverter()
+    import warnings
+    with warnings.catch_warnings():
+        warnings.simplefilter('ignore')
+        with pytest.raises(Abort):
+            inv.fit(FREQ, Zin, mode=mode, outliers='auto' if case.startswith('auto') else False, init_from_ridge=ridge_init)
+    p = Recorder.last
+    ref_model = str(G[f'{case}/model'])[:-len('_StanModel.pkl')]
+    assert ref_model == 'Series' + ('_outliers' if p.kw.get('outliers') else '')
+    assert np.max(np.abs(p.Z[0].numpy() - G[f'{case}/Z'])) <= 1e-13 * np.max(np.abs(G[f'{case}/Z']))
+    K, Nf = p.K, p.Nf
+    u0 = p.u0.reshape(-1, p.D)
+    if not ridge_init:
+        assert str(G[f'{case}/init']) == 'random' and bool((u0.abs() <= 2).all())  # Stan's U(-2, 2) start
+        return
+    for row in u0:  # every chain starts from the ridge solution; what it does not fix stays random
+        row = row.numpy()
+        x = G[f'{case}/init/x']
+        assert np.max(np.abs(row[2:2 + K] - x)) <= 1e-9 * np.max(np.abs(x))
+        assert row[0] == pytest.approx(np.log(float(G[f'{case}/init/Rinf_raw'])), rel=1e-9)
+        assert row[1] == pytest.approx(np.log(float(G[f'{case}/init/induc_raw'])), rel=1e-9)
+        if p.kw.get('outliers'):
+            assert np.allclose(row[6 + K:6 + K + Nf], np.log(G[f'{case}/init/sigma_out_raw']), rtol=1e-12)
+        rest = np.r_[row[2 + K:6 + K], row[6 + K + (2 * Nf if p.kw.get('outliers') else 0):]]
+        assert np.all(np.abs(rest) <= 2)
