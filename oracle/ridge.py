@@ -137,6 +137,54 @@ def prep(freq, Z, basis_freq=None, epsilon=None, penalty='discrete', weights=Non
                 WZ_re=w.real * Zs.real, WZ_im=w.imag * Zs.imag, Pen=Pen, Lmat=Lmat, K=K)
 
 
+def hyper_loop(WA_re, WA_im, WZ_re, WZ_im, Pen, Lmat, penalty, frac, nonneg, hl_beta, hl_fbeta, lambda_0, L1_penalty,
+               epsilon, xtol, max_iter, fit_inductance, x0=None):
+    """The hyper-lambda iteration of ridge_fit (inversion.py:489-753) on an assembled system: lambda update from the
+    previous coefficients, P = G0 + sum_o frac_o Lam_o^1/2 Pen_o Lam_o^1/2, QP, stop test.  This is the interface of
+    bdrt_ridge_fit (include/bdrt.h).  Returns (coef [K+2] scaled, lam [3, K+2], history, converged)."""
+    n = WA_re.shape[1]
+    G0 = WA_re.T @ WA_re + WA_im.T @ WA_im
+    L1_vec = np.ones(n) * np.pi ** 0.5 / epsilon * L1_penalty
+    L1_vec[0:2] = 0
+    q = -(WA_re.T @ WZ_re) - (WA_im.T @ WZ_im) + L1_vec
+    lb = np.zeros(n) if nonneg else np.r_[0.0, 0.0, -10.0 * np.ones(n - 2)]
+    coef = np.zeros(n) + 1e-6 if x0 is None else np.asarray(x0, dtype=np.float64).copy()
+    lam = np.ones((3, n)) * lambda_0
+    F = None
+    hist = []
+    converged = False
+    it = 0
+    while it < max_iter:
+        prev = coef.copy()
+        for o in range(3):
+            if frac[o] > 0:
+                if penalty in ('discrete', 'cholesky') and hl_fbeta is not None:
+                    lam[o] = hyper_lambda_fbeta(Lmat[o][:, 2:], prev[2:], hl_fbeta, lambda_0)
+                elif penalty in ('discrete', 'cholesky'):
+                    lam[o] = hyper_lambda_discrete(Lmat[o][:, 2:], prev[2:], hl_beta, lambda_0)
+                else:
+                    factor = (100.0, 10.0, 1.0)[o]
+                    lv = hyper_lambda_integral(Pen[o], factor * prev, np.sqrt(lam[o]), hl_beta, lambda_0)
+                    lv[lv <= 0] = 1e-15
+                    lam[o] = lv
+        Pm = G0.copy()
+        for o in range(3):
+            if frac[o] > 0:
+                s = np.sqrt(lam[o])
+                Pm += frac[o] * (s[:, None] * Pen[o] * s[None, :])
+        coef, y, F, nit = qp_bound(Pm, q, lb, F0=F, strict=False)
+        hist.append(coef.copy())
+        with np.errstate(all='ignore'):
+            delta = (coef - prev) / prev
+            if not fit_inductance:
+                delta[1] = 0
+            if np.mean(np.abs(delta)) < xtol:
+                converged = True
+                break
+        it += 1
+    return coef, lam, hist, converged
+
+
 def ridge_ReImCV(freq, Z, lambdas=None, **kw):
     """Re-Im cross-validation of lambda_0 (Inverter.ridge_ReImCV, inversion.py:902-944): the real part is fitted and
     scored on the imaginary part and vice versa; returns (lambda_0 with the smallest total error, table
@@ -183,45 +231,9 @@ def ridge_fit(freq, Z, basis_freq=None, epsilon=None, penalty='discrete', reg_or
     if part not in ('both', 'real', 'imag'):
         raise ValueError(f"Invalid part {part}. Options are 'both', 'real', 'imag'")
     use_re, use_im = float(part != 'imag'), float(part != 'real')
-    G0 = use_re * (p['WA_re'].T @ p['WA_re']) + use_im * (p['WA_im'].T @ p['WA_im'])
-    L1_vec = np.ones(n) * np.pi ** 0.5 / p['epsilon'] * L1_penalty
-    L1_vec[0:2] = 0
-    q = -use_re * (p['WA_re'].T @ p['WZ_re']) - use_im * (p['WA_im'].T @ p['WZ_im']) + L1_vec
-    lb = np.zeros(n) if nonneg else np.r_[0.0, 0.0, -10.0 * np.ones(n - 2)]
-    coef = np.zeros(n) + 1e-6 if x0 is None else np.asarray(x0, dtype=np.float64).copy()
-    lam = np.ones((3, n)) * lambda_0
-    F = None
-    hist = []
-    converged = False
-    it = 0
-    while it < max_iter:
-        prev = coef.copy()
-        for o in range(3):
-            if frac[o] > 0:
-                if penalty in ('discrete', 'cholesky') and hl_fbeta is not None:
-                    lam[o] = hyper_lambda_fbeta(p['Lmat'][o][:, 2:], prev[2:], hl_fbeta, lambda_0)
-                elif penalty in ('discrete', 'cholesky'):
-                    lam[o] = hyper_lambda_discrete(p['Lmat'][o][:, 2:], prev[2:], hl_beta, lambda_0)
-                else:
-                    factor = (100.0, 10.0, 1.0)[o]
-                    lv = hyper_lambda_integral(p['Pen'][o], factor * prev, np.sqrt(lam[o]), hl_beta, lambda_0)
-                    lv[lv <= 0] = 1e-15
-                    lam[o] = lv
-        Pm = G0.copy()
-        for o in range(3):
-            if frac[o] > 0:
-                s = np.sqrt(lam[o])
-                Pm += frac[o] * (s[:, None] * p['Pen'][o] * s[None, :])
-        coef, y, F, nit = qp_bound(Pm, q, lb, F0=F, strict=False)
-        hist.append(coef.copy())
-        with np.errstate(all='ignore'):
-            delta = (coef - prev) / prev
-            if not fit_inductance:
-                delta[1] = 0
-            if np.mean(np.abs(delta)) < xtol:
-                converged = True
-                break
-        it += 1
+    coef, lam, hist, converged = hyper_loop(use_re * p['WA_re'], use_im * p['WA_im'], use_re * p['WZ_re'],
+                                            use_im * p['WZ_im'], p['Pen'], p['Lmat'], penalty, frac, nonneg, hl_beta,
+                                            hl_fbeta, lambda_0, L1_penalty, p['epsilon'], xtol, max_iter, fit_inductance, x0)
     iters = len(hist)
     coef = coef.copy()
     if part == 'imag':  # R_inf from the real part (inversion.py:855-863; a constant's least-squares fit is the mean)

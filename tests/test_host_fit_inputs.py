@@ -293,3 +293,76 @@ def test_auto_outliers_and_ridge_initialisation_flow(case, mode, ridge_init, hos
             assert np.allclose(row[6 + K:6 + K + Nf], np.log(G[f'{case}/init/sigma_out_raw']), rtol=1e-12)
         rest = np.r_[row[2 + K:6 + K], row[6 + K + (2 * Nf if p.kw.get('outliers') else 0):]]
         assert np.all(np.abs(rest) <= 2)
+
+
+@pytest.fixture
+def host_ridge(host, monkeypatch):
+    """the device entry points behind ridge_fit (bdrt_ridge_fit, bdrt_qp_bound, bdrt_build_M) served by the oracle"""
+    from bayes_drt_b200 import ridge
+    from oracle import ridge as oridge
+
+    def ridge_fit(WA_re, WA_im, WZ_re, WZ_im, Pen, Lmat, penalty='discrete', nonneg=True, max_iter=20, xtol=1e-3,
+                  hl_beta=2.5, lambda_0=1e-2, reg_ord=(0.0, 0.0, 1.0), L1_penalty=0.0, epsilon=1.0, fit_inductance=True,
+                  hl_fbeta=None, device=None):
+        B = WZ_re.shape[0]
+        coef, lam, iters, conv = [], [], [], []
+        for b in range(B):
+            war = (WA_re[b] if WA_re.dim() == 3 else WA_re).numpy()
+            wai = (WA_im[b] if WA_im.dim() == 3 else WA_im).numpy()
+            c, l, hist, cv = oridge.hyper_loop(war, wai, WZ_re[b].numpy(), WZ_im[b].numpy(), Pen.numpy(),
+                                               None if Lmat is None else Lmat.numpy(), penalty, np.asarray(reg_ord),
+                                               nonneg, hl_beta, hl_fbeta, lambda_0, L1_penalty, epsilon, xtol, max_iter,
+                                               fit_inductance)
+            coef.append(c), lam.append(l.copy()), iters.append(len(hist)), conv.append(int(cv))
+        return dict(coef=torch.tensor(np.stack(coef)), lam=torch.tensor(np.stack(lam)),
+                    iters=torch.tensor(iters, dtype=torch.int32), converged=torch.tensor(conv, dtype=torch.int32))
+
+    def qp_bound(P, q, lb, device=None):
+        xs = [oridge.qp_bound(P[b].numpy(), q[b].numpy(), lb.numpy())[0] for b in range(P.shape[0])]
+        return torch.tensor(np.stack(xs)), None, None
+
+    def build_M(freq, eps, order, toeplitz, device=None):
+        return torch.tensor(om.construct_M(np.asarray(freq, dtype=np.float64), order=order, epsilon=float(eps)))
+    monkeypatch.setattr(ridge.capi, 'ridge_fit', ridge_fit)
+    monkeypatch.setattr(ridge.capi, 'qp_bound', qp_bound)
+    monkeypatch.setattr(ridge.capi, 'build_M', build_M)
+    return host
+
+
+RIDGE_REFERENCE_CASES = {
+    'default': dict(), 'huang': dict(preset='Huang'),
+    'init_from_ridge': dict(penalty='integral', lambda_0=1, hl_beta=5, weights='modulus'),
+    'free_sign': dict(nonneg=False), 'mixed_orders': dict(reg_ord=[0.2, 0.3, 0.5], L1_penalty=0.01),
+    'real_part': dict(part='real'), 'imag_part': dict(part='imag', weights='modulus'), 'fbeta': dict(hl_fbeta=0.1),
+    'cholesky': dict(penalty='cholesky'), 'cv': dict(lambda_0='cv', cv_lambdas=np.logspace(-6, 0, 7)),
+    'ciucci': dict(preset='Ciucci', cv_lambdas=np.logspace(-6, 0, 7)),
+}
+
+
+@pytest.mark.parametrize('case', sorted(RIDGE_REFERENCE_CASES))
+def test_shipped_ridge_fit_reproduces_the_reference(case, host_ridge):
+    """bayes_drt_b200's ridge_fit (presets, weights, parts and their least-squares offsets, Re-Im cross-validation with
+    per-spectrum optima, rescaling) on a batch of two spectra, against the results of the reference's own ridge_fit
+    (tests/golden/ridge_reference.npz); the hyper-lambda loop / QP behind the C ABI is served by the oracle here and by
+    the CUDA kernels in tests/test_gpu_ridge.py."""
+    import warnings
+    R = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden', 'ridge_reference.npz'))
+    S = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden', 'spectra.npz'))
+    names = ('ZARC_uniform_0.25', '2ZARC_uniform_0.25')
+    Zb = np.stack([S[n + '/Z'] for n in names])
+    inv = host_ridge.Inverter()
+    with warnings.catch_warnings():
+        warnings.simplefilter('ignore')
+        inv.ridge_fit(S[names[0] + '/freq'], Zb, **RIDGE_REFERENCE_CASES[case])
+    tol = 1e-6 if case in ('fbeta', 'ciucci') else 1e-9
+    for b, n in enumerate(names):
+        key = f'{n}/{case}'
+        ref = R[key + '/coef']
+        assert np.max(np.abs(inv.distribution_fits['DRT']['coef'][b].numpy() - ref)) <= tol * np.abs(ref).max(), key
+        assert float(inv.R_inf[b]) == pytest.approx(float(R[key + '/R_inf']), rel=tol)
+        assert abs(float(inv.inductance[b]) - float(R[key + '/inductance'])) <= tol * max(abs(float(R[key + '/inductance'])), 1e-9)
+        if key + '/cv_result' in R.files:
+            tab = R[key + '/cv_result']
+            assert inv._cv_lambda_0[b] == tab[np.argmin(tab[:, 3]), 0]
+            for j, k in ((1, 'recv'), (2, 'imcv'), (3, 'totcv')):
+                assert np.allclose(inv.cv_result[k][b].numpy(), tab[:, j], rtol=1e-6), (key, k)
