@@ -294,9 +294,12 @@ class Inverter:
                                       "frequency grid per batch")
         ids = torch.arange(spectrum_offset, spectrum_offset + B, dtype=torch.int64, device=self.device)
         # ---- ridge initialisation and automatic outlier detection (inversion.py:1154-1187)
-        ridge_init, flags = None, None
+        ridge_init, flags, init_flags = None, None, None
         if init_from_ridge:
             ridge_init = self._get_init_from_ridge(freq, Zb, nonneg, inductance_scale, ridge_kw)
+            if outliers:  # True or 'auto': likely outliers start with a large sigma_out_raw; a less stringent threshold
+                # than the model choice below, so that none is missed (inversion.py:1668-1675)
+                init_flags = self._ridge_outlier_flags(freq, Zb, threshold=3, use_existing_fit=True)
         if outliers == 'auto':
             # existing ridge fit if one was just made, else a fresh one with preset='Huang'; stringent threshold 4
             flags = self._ridge_outlier_flags(freq, Zb, threshold=4, use_existing_fit=init_from_ridge, **ridge_kw)
@@ -324,7 +327,7 @@ class Inverter:
             res = self._fit_core(freq, Zs[sel], ids[sel], model_type, name, par, mode, nonneg, fl, sigma_min,
                                  inductance_scale, outlier_lambda, random_seed, max_iter, warmup, samples, chains,
                                  u_init, None if ridge_init is None else {k: v[sel] for k, v in ridge_init.items()},
-                                 flags[sel] if (flags is not None and fl) else None, polish, keep_draws)
+                                 init_flags[sel] if (init_flags is not None and fl) else None, polish, keep_draws)
             results.append((ix, fl, res))
             if ix is None:
                 self._outlier_model[:] = fl

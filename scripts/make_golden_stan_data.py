@@ -97,12 +97,18 @@ Zo = np.load(os.path.join(ROOT, 'tests', 'golden', 'ridge_reference.npz'))['outl
 CASES['auto_contaminated'] = (dict(), dict(mode='optimize', outliers='auto'))
 CASES['auto_contaminated_ridge_init'] = (dict(), dict(mode='optimize', outliers='auto', init_from_ridge=True))
 CASES['auto_clean_ridge_init'] = (dict(), dict(mode='sample', outliers='auto', init_from_ridge=True))
+# a third, marginal outlier: flagged at the initialisation's threshold 3 (inversion.py:1668-1675) but not at the model
+# choice's threshold 4 (:1171-1187)
+Zm = Zo.copy()
+Zm[70] = Z[70] + 0.04
+CASES['auto_marginal_ridge_init'] = (dict(), dict(mode='optimize', outliers='auto', init_from_ridge=True))
+CASES['true_marginal_ridge_init'] = (dict(), dict(mode='optimize', outliers=True, init_from_ridge=True))
 rng = np.random.RandomState(5)
-out = {'freq': freq, 'Z': Z, 'Z_contaminated': Zo}
+out = {'freq': freq, 'Z': Z, 'Z_contaminated': Zo, 'Z_marginal': Zm}
 for case, (ikw, fkw) in CASES.items():
     inv = Inverter(**ikw)
     try:
-        inv.fit(freq, Zo if 'contaminated' in case else Z, **fkw)
+        inv.fit(freq, Zo if 'contaminated' in case else (Zm if 'marginal' in case else Z), **fkw)
     except Abort:
         pass
     dat = captured['dat']

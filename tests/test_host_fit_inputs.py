@@ -261,19 +261,22 @@ class InitRecorder(Recorder):
 @pytest.mark.parametrize('case,mode,ridge_init', [('auto_contaminated', 'optimize', False),
                                                    ('auto_contaminated_ridge_init', 'optimize', True),
                                                    ('auto_clean_ridge_init', 'sample', True),
-                                                   ('series_ridge_init', 'optimize', True)])
+                                                   ('series_ridge_init', 'optimize', True),
+                                                   ('auto_marginal_ridge_init', 'optimize', True),
+                                                   ('true_marginal_ridge_init', 'optimize', True)])
 def test_auto_outliers_and_ridge_initialisation_flow(case, mode, ridge_init, host, monkeypatch):
     """outliers='auto' (inversion.py:1171-1187) and init_from_ridge (:1154-1160, :1616-1682) in the shipped fit():
     the Stan program chosen for the spectrum, the data it gets, and the initial values taken from the ridge solution."""
     _oracle_ridge(monkeypatch)
     monkeypatch.setattr(host.capi, 'SeriesProblem', InitRecorder)
-    Zin = G['Z_contaminated'] if 'contaminated' in case else Z
+    Zin = G['Z_contaminated'] if 'contaminated' in case else (G['Z_marginal'] if 'marginal' in case else Z)
     inv = host.Inverter()
     import warnings
     with warnings.catch_warnings():
         warnings.simplefilter('ignore')
         with pytest.raises(Abort):
-            inv.fit(FREQ, Zin, mode=mode, outliers='auto' if case.startswith('auto') else False, init_from_ridge=ridge_init)
+            inv.fit(FREQ, Zin, mode=mode, init_from_ridge=ridge_init,
+                    outliers='auto' if case.startswith('auto') else case.startswith('true'))
     p = Recorder.last
     ref_model = str(G[f'{case}/model'])[:-len('_StanModel.pkl')]
     assert ref_model == 'Series' + ('_outliers' if p.kw.get('outliers') else '')
