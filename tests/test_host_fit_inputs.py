@@ -72,6 +72,11 @@ def host(monkeypatch):
         kw = dict(tau=np.asarray(tau, dtype=np.float64), epsilon=float(eps), kernel=kernel, dist_type=dist_type,
                   symmetry=symmetry, bc=bc, ct=ct, k_ct=k_ct)
         f = np.asarray(freq, dtype=np.float64)
+        if f.ndim == 2:  # one grid per row (capi.build_A: freq [G, Nf], tau [K] or [G, K])
+            t = kw.pop('tau')
+            rows = [(om.construct_A(f[g], 'real', tau=t[g] if t.ndim == 2 else t, **kw),
+                     om.construct_A(f[g], 'imag', tau=t[g] if t.ndim == 2 else t, **kw)) for g in range(f.shape[0])]
+            return torch.tensor(np.stack([r[0] for r in rows])), torch.tensor(np.stack([r[1] for r in rows]))
         return torch.tensor(om.construct_A(f, 'real', **kw)), torch.tensor(om.construct_A(f, 'imag', **kw))
 
     def build_L(freq, tau, eps, order, device=None):
@@ -369,3 +374,34 @@ def test_shipped_ridge_fit_reproduces_the_reference(case, host_ridge):
             assert inv._cv_lambda_0[b] == tab[np.argmin(tab[:, 3]), 0]
             for j, k in ((1, 'recv'), (2, 'imcv'), (3, 'totcv')):
                 assert np.allclose(inv.cv_result[k][b].numpy(), tab[:, j], rtol=1e-6), (key, k)
+
+
+def test_per_spectrum_grids_prepare_each_row_like_a_single_fit(host):
+    """frequencies [B, Nf]: row b of what fit() hands the solver (grid, scaled spectrum, kernel matrix on that row's own
+    default basis) is what a single-spectrum fit of row b hands it -- which is pinned to the reference above."""
+    rng = np.random.RandomState(4)
+    deltas = np.array([0.0, 0.13, 0.5])
+    freq = 10.0 ** (6 - deltas[:, None] - np.arange(81)[None, :] / 10)
+    Zb = 1.0 + 1.0 / (1 + (2j * np.pi * freq * 10.0 ** rng.uniform(-4, 0, (3, 1))) ** 0.8) \
+        + 0.002 * (rng.randn(3, 81) + 1j * rng.randn(3, 81))
+    perm = rng.permutation(81)  # unsorted input: every row is sorted on its own
+    inv = host.Inverter()
+    with pytest.raises(Abort):
+        inv.fit(freq[:, perm], Zb[:, perm], mode='optimize')
+    batch = Recorder.last
+    assert tuple(batch.A.shape) == (3, 162, 101) and tuple(batch.freq.shape) == (3, 81) and batch.B == 3
+    assert tuple(np.shape(inv.distributions['DRT']['tau'])) == (3, 101)
+    for b in range(3):
+        one = host.Inverter()
+        with pytest.raises(Abort):
+            one.fit(freq[b], Zb[b], mode='optimize')
+        single = Recorder.last
+        assert np.array_equal(batch.freq[b].numpy(), single.freq.numpy())
+        assert np.allclose(batch.Z[b].numpy(), single.Z[0].numpy(), rtol=1e-14, atol=0)
+        assert np.allclose(inv.distributions['DRT']['tau'][b], one.distributions['DRT']['tau'], rtol=1e-15)
+        assert np.max(np.abs(batch.A[b].numpy() - single.A.numpy())) <= 1e-13 * np.abs(single.A.numpy()).max()
+        assert np.max(np.abs(batch.L.numpy() - single.L.numpy())) <= 1e-12 * np.abs(single.L.numpy()).max()
+    with pytest.raises(NotImplementedError):
+        host.Inverter().fit(freq, Zb, init_from_ridge=True)
+    with pytest.raises(ValueError):
+        host.Inverter().fit(freq, Zb[0])
