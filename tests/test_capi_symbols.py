@@ -64,3 +64,36 @@ def test_ctypes_structs_mirror_the_header():
                        ('bdrt_newton_opts', _lib.NewtonOpts), ('bdrt_nuts_opts', _lib.NutsOpts),
                        ('bdrt_ridge_opts', _lib.RidgeOpts)):
         assert _struct_fields(hdr, cname) == [f[0] for f in cls._fields_], cname
+
+
+def test_header_is_plain_c_and_links_from_c(lib, tmp_path):
+    """The boundary is a C ABI: include/bdrt.h compiles as strict C99 and a C program links against libbdrt.so and calls
+    the entry points that need no device (version, default options, sizes)."""
+    import shutil
+    import subprocess
+    from bayes_drt_b200 import _lib
+    if shutil.which('gcc') is None:
+        pytest.skip('no gcc')
+    src = tmp_path / 'use_bdrt.c'
+    src.write_text('''
+#include <stdio.h>
+#include <string.h>
+#include "bdrt.h"
+int main(void) {
+  bdrt_lbfgs_opts lo; bdrt_nuts_opts no; bdrt_ridge_opts ro; bdrt_newton_opts wo; bdrt_series_data d;
+  bdrt_lbfgs_default_opts(&lo); bdrt_nuts_default_opts(&no); bdrt_ridge_default_opts(&ro); bdrt_newton_default_opts(&wo);
+  memset(&d, 0, sizeof d);
+  d.model = BDRT_MODEL_SERIES | BDRT_MODEL_OUTLIERS; d.Nf = 81; d.K = 101; d.B = 1;
+  printf("%d %d %d %d %g %d %g %d\\n", bdrt_version(), lo.history, no.chains, no.warmup, no.adapt_delta, ro.max_iter,
+         ro.hl_beta, bdrt_num_params(&d));
+  return 0;
+}
+''')
+    exe = tmp_path / 'use_bdrt'
+    libdir = os.path.dirname(_lib.LIB_PATH)
+    subprocess.run(['gcc', '-std=c99', '-Wall', '-Wextra', '-Werror', '-pedantic', '-I', os.path.join(ROOT, 'include'),
+                    str(src), '-L', libdir, '-lbdrt', '-Wl,-rpath,' + libdir, '-o', str(exe)], check=True)
+    out = subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.split()
+    # Stan's defaults as the reference uses them (history 5; 2 chains, 200 warm-up, adapt_delta 0.9; ridge 20 / 2.5);
+    # Series_outliers: D = 2 K + 9 + 2 Nf = 373 (SURVEY 8a, a10)
+    assert out == ['100', '5', '2', '200', '0.9', '20', '2.5', '373']
