@@ -344,8 +344,16 @@ def run_ours(a):
         barrier()
         t_m = e0.elapsed_time(e1) * 1e-3
         nodes = 76
+        # ridge work, SURVEY 8d: P assembly 2 (2 Nf) n^2 once; per hyper-iteration the lambda-weighted penalty 2 n^2 and at
+        # least one Cholesky n^3 / 3 + two triangular solves 2 n^2 (the active-set QP may factor more than once per
+        # hyper-iteration and its pivots are not counted on device: this is a lower bound)
+        n_r, nf_r = len(bf) + 2, len(freq)
+        it_r = float(ivr._ridge_iters.float().mean().item())
+        ridge_flop = 2.0 * (2 * nf_r) * n_r ** 2 + it_r * (n_r ** 3 / 3.0 + 4.0 * n_r ** 2)
         extras = {'ridge_fits_per_s': ws * Br / t_r, 'ridge_batch': Br,
-                  'ridge_hyper_iterations': float(ivr._ridge_iters.float().mean().item()),
+                  'ridge_hyper_iterations': it_r,
+                  'ridge_tflops_lower_bound': Br * ridge_flop / t_r / 1e12,
+                  'ridge_frac_of_dfma_peak_lower_bound': Br * ridge_flop / t_r / 1e12 / dfma,
                   'A_builds_per_s': ws * 2 * Gm / t_m, 'A_build_shape': [81, 81],
                   'A_build_tflops': Gm * 81 * 81 * nodes * 12 / t_m / 1e12,  # 12 flop per entry and node for both parts
                   'A_build_frac_of_dfma_peak': Gm * 81 * 81 * nodes * 12 / t_m / 1e12 / dfma}
