@@ -172,3 +172,22 @@ def test_numeric_helpers_against_reference_vectors():
         avg = (wt * yt).sum(dim=1, keepdim=True) / wt.sum(dim=1, keepdim=True)
         r2 = 1 - (wt * (yh - yt) ** 2).sum(dim=1) / (wt * (yt - avg) ** 2).sum(dim=1)
         assert abs(float(r2) - float(g[key])) <= 1e-13
+
+
+def test_bench_reference_arm_under_torchrun_prints_once():
+    """launched the way the driver launches N > 1 (torchrun, one rank per GPU): rank 0 alone runs the CPU arm and prints
+    its line, the other ranks exit 0 without work."""
+    import json
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, '-m', 'torch.distributed.run', '--nnodes=1', '--nproc-per-node', '2',
+                        '--master-addr', '127.0.0.1', '--master-port', '29537', os.path.join(root, 'bench.py'), '--impl',
+                        'reference', '--gpus', '2', '--steps', '1', '--warmup', '0', '--cpu-sample', '2'],
+                       capture_output=True, text=True, timeout=900, cwd=root)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [ln for ln in r.stdout.splitlines() if ln.strip().startswith('{')]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d['impl'] == 'reference' and d['n_gpus'] == 2 and d['value'] > 0
