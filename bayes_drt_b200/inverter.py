@@ -601,8 +601,17 @@ class Inverter:
         if percentile is not None:
             if self.fit_type != 'bayes' or self._sample_result is None:
                 raise ValueError('Percentile prediction is only available for bayes_fit results')
-            if len(self.distributions) != 1:
-                raise NotImplementedError('percentile prediction of Z is implemented for single-distribution fits')
+            if len(self.distributions) != 1 or names != list(self.distribution_fits.keys()):
+                # several distributions (or a subset): the impedance of every draw, then the percentile of its real and
+                # imaginary parts (inversion.py:2705-2737)
+                single = self._single
+                self._single = False
+                with warnings.catch_warnings():
+                    warnings.simplefilter('ignore')
+                    Zd = self.predict_Z_distribution(frequencies, distributions=names, include_offsets=include_offsets)
+                self._single = single
+                return self._ret(torch.complex(self._pct(Zd.real.contiguous(), percentile),
+                                               self._pct(Zd.imag.contiguous(), percentile)))
             A_re, A_im = self._pred_matrices(f, names[0])
             s = self._Z_scale[:, None, None]
             x = self._sample_result['x'] * s

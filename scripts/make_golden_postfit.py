@@ -131,8 +131,9 @@ for case, (ikw, fkw) in CASES.items():
     out[p + 'score_chi_sq'] = np.float64(inv.score(freq, Z))
     out[p + 'score_r2_modulus'] = np.float64(inv.score(freq, Z, metric='r2', weights='modulus'))
     out[p + 'outlier_idx_z1'] = np.asarray(inv.check_outliers(freq, Z, threshold=1.0, use_existing_fit=True)).ravel()
-    if fkw['mode'] == 'sample' and len(inv.distributions) == 1:
+    if fkw['mode'] == 'sample':
         out[p + 'Z_pred_p25'] = inv.predict_Z(f_pred, percentile=25)
+    if fkw['mode'] == 'sample' and len(inv.distributions) == 1:
         out[p + 'Rp_p75'] = np.float64(inv.predict_Rp(percentile=75))
         s_re, s_im = inv.predict_sigma(f_pred, percentile=60)
         out[p + 'sigma_pred_p60'] = np.concatenate((s_re, s_im))

@@ -105,8 +105,9 @@ def test_extraction_and_queries_match_the_reference(case):
     assert float(inv.score(FREQ, Z, metric='r2', weights='modulus')[0]) == pytest.approx(float(G[p + 'score_r2_modulus']), rel=1e-9)
     idx = inv.check_outliers(threshold=1.0)
     assert np.array_equal(idx[:, 1].numpy(), G[p + 'outlier_idx_z1'])
-    if p + 'Z_pred_p25' in G.files:
+    if p + 'Z_pred_p25' in G.files:  # single- and multi-distribution fits (:2705-2737)
         assert close(inv.predict_Z(F_PRED, percentile=25)[0], G[p + 'Z_pred_p25'], 1e-10)
+    if p + 'Rp_p75' in G.files:
         assert float(inv.predict_Rp(percentile=75)[0]) == pytest.approx(float(G[p + 'Rp_p75']), rel=1e-12)
         s_re, s_im = inv.predict_sigma(inv.f_train, percentile=60)
         assert close(torch.cat((s_re[0], s_im[0])), G[p + 'sigma_train_p60'])
