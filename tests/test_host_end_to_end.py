@@ -100,3 +100,23 @@ def test_multi_distribution_fits_shapes_and_scaling(inverter):
     assert par.distribution_fits['TP-DDT']['coef'].shape == (21,) and (par.distribution_fits['TP-DDT']['coef'] > 0).all()
     with pytest.raises(NotImplementedError):
         sp.fit(f, z, outliers=True)
+
+
+def test_hooks_bench_py_relies_on(inverter):
+    """bench.py assembles its resident-input leg from Inverter's own preprocessing (_to_batch, _scale_Z, _grid) and reads
+    _opt_result / _sample_result / _sample_stats: keep those hooks working."""
+    from bayes_drt_b200 import synth
+    freq, Z, _ = synth.make_spectra(3, seed=20240601)
+    _, bf = synth.bench_grid()
+    inv = inverter.Inverter(basis_freq=bf.numpy(), device=None)
+    fs, Zb = inv._to_batch(freq, Z)
+    Zs = inv._scale_Z(Zb, True)
+    tau, eps, m = inv._grid(fs, 'DRT')
+    assert tuple(Zs.shape) == (3, 70) and len(tau) == 100 and abs(eps - 4.342944819) < 1e-8
+    assert {'A_re', 'A_im', 'L0', 'L1', 'L2'} <= set(m) and tuple(m['A_re'].shape) == (70, 100)
+    inv.fit(freq, Z[:2], mode='optimize', max_iter=30)
+    assert {'u', 'lp', 'iters', 'n_eval', 'status'} <= set(inv._opt_result)
+    hm = inverter.Inverter(basis_freq=np.logspace(5, -1, 13), device=None)
+    hm.fit(freq, Z[:1], mode='sample', chains=2, warmup=6, samples=4, check_outliers=False, spectrum_offset=5)
+    assert tuple(hm._sample_result['x'].shape) == (1, 8, 13)
+    assert {'stepsize', 'n_leapfrog', 'n_divergent', 'n_maxdepth', 'accept'} <= set(hm._sample_stats)
