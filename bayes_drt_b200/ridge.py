@@ -56,6 +56,8 @@ def ridge_fit(inv, frequencies, Z, part='both', penalty='discrete', reg_ord=2, L
             penalty, lambda_0, hl_fbeta = 'discrete', 'cv', 0.1
         else:  # inversion.py:278-282
             penalty, hl_beta, lambda_0, weights = 'integral', 2.5, 1e-2, 'modulus'
+    if not isinstance(hl_beta, (int, float, np.floating, np.integer)):
+        raise NotImplementedError('one hl_beta per derivative order is not implemented in this build (pass a scalar)')
     if penalty in ('discrete', 'cholesky'):
         if hl_beta <= 1:
             raise ValueError("hl_beta must be greater than 1 for penalty 'cholesky' and 'discrete'")
