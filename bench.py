@@ -356,7 +356,9 @@ def run_ours(a):
                   'ridge_frac_of_dfma_peak_lower_bound': Br * ridge_flop / t_r / 1e12 / dfma,
                   'A_builds_per_s': ws * 2 * Gm / t_m, 'A_build_shape': [81, 81],
                   'A_build_tflops': Gm * 81 * 81 * nodes * 12 / t_m / 1e12,  # 12 flop per entry and node for both parts
-                  'A_build_frac_of_dfma_peak': Gm * 81 * 81 * nodes * 12 / t_m / 1e12 / dfma}
+                  'A_build_frac_of_dfma_peak': Gm * 81 * 81 * nodes * 12 / t_m / 1e12 / dfma,
+                  # the same launches in the reference's own accounting (all 1000 trapezoid nodes, SURVEY 8d "Q_ref")
+                  'A_build_tflops_reference_literal': Gm * 81 * 81 * 1000 * 12 / t_m / 1e12}
 
     # -------------------------------------------------------------------------------- CPU baseline (rank 0, N = 1)
     cpu = None
