@@ -18,6 +18,7 @@ struct bdrt_ctx {
   int sm_count;
   int smem_optin;  // max dynamic shared memory per block (opt-in), bytes
   int smem_per_sm; // shared memory per SM, bytes
+  unsigned long long* dbg_clk;  // profiling builds (-DBDRT_PHASE_CLOCKS): [16] device counters
 };
 
 #define BDRT_FAIL(ctx, code, ...)                             \

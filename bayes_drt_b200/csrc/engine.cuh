@@ -24,6 +24,17 @@
 //            dense matrix, fragment loads become broadcast table look-ups, and two CTAs fit on an SM.
 // Inside the engine the stacked vectors are laid out [re: nfp | im: nfp] with nfp = Nf rounded up to 8, so that neither
 // an 8-row tile nor a 4-row k-step straddles the two parts.
+//
+// Third mode (TOEP == 2, "warp mode"): Toeplitz operands AND warp-private products.  With A_p[r][c] = T_p[c - r] the
+// product of ONE slot is itself a small matrix product once the vector is viewed as a Hankel matrix:
+//     Zhat_p[n + 8 i] = sum_kk T_p[kk - 8 - 8 i] * x[n + kk - 8]        (M = (part, row group i), N = n in 0..7, K = kk)
+//     G[n + 8 i]      = sum_p sum_kk T_p[8 i + 7 - kk] * V_p[n - 7 + kk]  (M = column group i,     N = n,       K = (p, kk))
+// so every warp runs mma.sync.m8n8k4.f64 on its own slot (the A fragment is a table look-up shared by all row groups,
+// the B fragment a sliding window of the slot's vector) and the CTA-wide rendezvous disappears: no barrier inside an
+// evaluation, warps of a CTA are at different phases and the FP64 tensor pipe, the FP64 FMA pipe and the L2 round trips
+// of the solvers' own vector code overlap across warps.  Cost: the sliding window pads the K dimension by 7-8 and the
+// tiles are not full (Nf = 70, K = 100: 161 DMMA per evaluation and slot against 112.5), on a pipe that is otherwise
+// ~15 % busy.  Per-spectrum grids get per-slot tables, so eight different grids share a CTA.
 #pragma once
 #include "common.cuh"
 
@@ -39,8 +50,12 @@
 #define F_POS 1  // lower=0 coefficients of the series distribution (x = exp(u))
 #define F_OUT 2  // outlier error model (Series family only)
 
+#define TPAD 4                          // zero entries in front of a warp-mode table (keeps every fragment load in range)
+
 struct BdrtDist {
   int K, kpad4, kpad8, lda, lt;
+  int lt2;                    // warp mode: pitch of one part of the table (% 16 == 4: conflict-free A fragments)
+  int oTs;                    // warp mode, per-spectrum grids: offset of the slot's own table inside its scratch
   int off_x, off_ups, off_d;  // offsets of x, ups_raw, d_strength inside the unconstrained vector
   int oA, oTap;               // shared-memory offsets (doubles) of the resident operand and of the stencil taps
   int pos;                    // coefficients are lower=0
@@ -60,6 +75,14 @@ struct BdrtModel {
   int nfp;    // Nf rounded up to a multiple of 8
   int n2p;    // 2 * nfp
   int toepA;  // Toeplitz-resident operands
+  int wmode;  // warp mode: Toeplitz operands, warp-private Hankel products (engine_eval<2, ..>), no CTA barriers
+  int pslot;  // warp mode with per-spectrum grids: tables and omega live in the slot's scratch
+  int vim;    // offset of the imaginary part inside a V row (nfp; warp mode: nfp + 12, zero gap for the sliding window)
+  int xz;     // phase 1 zeroes x[K .. xz)
+  int oOmS;   // pslot: offset of the slot's omega [Nf] inside its scratch
+#ifdef BDRT_PHASE_CLOCKS
+  unsigned long long* dbg_clk;  // [16] per-phase clock sums of all warps (profiling builds only, scripts/gpu_phase_clocks.py)
+#endif
   int fast;   // register-tiled per-slot phases: Toeplitz L with bw <= FBW and K <= 128 for every distribution
   int off_err, off_so;
   int bw;
@@ -83,14 +106,16 @@ static inline int bdrt_pad_stride(int n) {  // smallest s >= n with s % 16 in {4
   return s;
 }
 
-// Fills the derived fields of m (everything but the pointers / scalars; needs ND, Nf, d[].K, d[].pos, flags, bw, toepA).
-// Returns the doubles of engine shared memory.
+// Fills the derived fields of m (everything but the pointers / scalars; needs ND, Nf, d[].K, d[].pos, flags, bw, toepA,
+// wmode, pslot).  Returns the doubles of engine shared memory.
 static inline int bdrt_model_layout(BdrtModel* m) {
   m->N2 = 2 * m->Nf;
   m->nfp = (m->Nf + 7) / 8 * 8;
   m->n2p = 2 * m->nfp;
   m->xoff = m->bw > FBW ? m->bw : FBW;  // even, so that 4-element windows of a row are 16-byte aligned
   m->xoff += m->xoff & 1;
+  if (m->wmode && m->xoff < 8) m->xoff = 8;  // the sliding window of the forward product starts at x[-8]
+  m->vim = m->wmode ? m->nfp + 12 : m->nfp;
   m->Kmax = 0;
   int kx = 0, k8 = 0;
   for (int i = 0; i < m->ND; ++i) {
@@ -98,14 +123,19 @@ static inline int bdrt_model_layout(BdrtModel* m) {
     d.kpad4 = (d.K + 3) / 4 * 4;
     d.kpad8 = (d.K + 7) / 8 * 8;
     d.lt = m->nfp + d.kpad8;
+    d.lt2 = m->nfp + d.kpad8 + 8;
+    while ((d.lt2 & 15) != 4) ++d.lt2;
     d.lda = bdrt_pad_stride(d.K);
     if (d.K > m->Kmax) m->Kmax = d.K;
     int k = d.kpad4 > d.K + m->bw ? d.kpad4 : d.K + m->bw;
+    if (m->wmode && k < d.K + 12) k = d.K + 12;            // the forward window reads x up to K + 10
     if (m->fast && k < 128 + FBW + 4) k = 128 + FBW + 4;  // the fast path addresses 4 x 32 entries + window
     if (k > kx) kx = k;
     if (d.kpad8 > k8) k8 = d.kpad8;
   }
-  const int mx = kx > m->n2p ? kx : m->n2p;
+  m->xz = kx;
+  const int vext = m->wmode ? m->vim + m->nfp + 12 : m->n2p;  // warp mode: zero gap after either part of V
+  const int mx = kx > vext ? kx : vext;
   m->ldxv = bdrt_pad_stride(m->xoff + mx);
   m->wm = m->bw > FBW ? m->bw : FBW;
   m->ws = m->Kmax + 2 * m->wm;
@@ -113,6 +143,15 @@ static inline int bdrt_model_layout(BdrtModel* m) {
   m->kup = (m->Kmax + 3) & ~3;  // a lane's 4 consecutive coefficients never run past the row
   m->sd = 3 * m->ws + 2 * m->kup;
   m->st = m->ND * m->sd + 16 + ((m->flags & F_OUT) ? 2 * m->Nf : 0);
+  m->st += m->st & 1;
+  if (m->pslot) {  // per-slot tables and omega
+    for (int i = 0; i < m->ND; ++i) {
+      m->d[i].oTs = m->st;
+      m->st += 2 * m->d[i].lt2;
+    }
+    m->oOmS = m->st;
+    m->st += (m->Nf + 1) & ~1;
+  }
   int mz = k8 > m->n2p ? k8 : m->n2p;
   if (m->fast && mz < 128) mz = 128;  // the fast path reads 4 x 32 gradient entries per row
   m->ldzg = mz + 4;  // % 8 == 4
@@ -130,7 +169,8 @@ static inline int bdrt_model_layout(BdrtModel* m) {
   o = 0;
   for (int i = 0; i < m->ND; ++i) {
     m->d[i].oA = o;
-    o += m->toepA ? 2 * m->d[i].lt : m->n2p * m->d[i].lda + 8;
+    if (m->wmode) o += m->pslot ? 0 : 2 * m->d[i].lt2;
+    else o += m->toepA ? 2 * m->d[i].lt : m->n2p * m->d[i].lda + 8;
   }
   m->oXV = o;  o += m->ND * NSLOT * m->ldxv;
   m->oZG = o;  o += m->ND * NSLOT * m->ldzg;
@@ -152,6 +192,12 @@ __device__ __forceinline__ void cta_sync() {
   __syncwarp();
   asm volatile("bar.sync 0;" ::: "memory");
 }
+// boundary between two phases of an evaluation: CTA rendezvous for the cooperative products, warp-local in warp mode
+template <int TOEP>
+__device__ __forceinline__ void phase_sync() {
+  if (TOEP == 2) __syncwarp();
+  else cta_sync();
+}
 
 __device__ __forceinline__ void ld2(const double* p, double& a, double& b) {  // 16-byte aligned shared-memory pair
   const double2 v = *reinterpret_cast<const double2*>(p);
@@ -167,15 +213,30 @@ __device__ __forceinline__ bool bdrt_is_exp(const BdrtModel& m, int i) {
   return true;
 }
 
+// Warp-mode table of one distribution: T_p[(col - row) + nfp - 1 + TPAD] = A_p[row][col] * ascale, zero elsewhere
+// (first row of A_p for col - row >= 0, first column below).  Filled by `nthr` threads (a CTA or one warp).
+__device__ inline void engine_fill_table(const BdrtModel& m, const BdrtDist& D, double* sT, const double* gA, int tid,
+                                         int nthr) {
+  for (int i = tid; i < 2 * D.lt2; i += nthr) {
+    const int p = i >= D.lt2, d = i - p * D.lt2 - (m.nfp - 1) - TPAD;
+    double v = 0.0;
+    if (d >= 0 && d < D.K) v = gA[(long long)p * m.Nf * D.K + d];
+    else if (d < 0 && -d < m.Nf) v = gA[((long long)p * m.Nf - d) * D.K];
+    sT[i] = v * D.ascale;
+  }
+}
+
 // Cooperative load of the resident operands.  Called by all threads once (or once per spectrum when the grid is
-// per-spectrum); ends with a CTA barrier.
+// per-spectrum and the kernel is not in warp mode); ends with a CTA barrier.
 __device__ inline void engine_load(const BdrtModel& m, double* sm, long long spec) {
   const int tid = threadIdx.x;
   for (int dd = 0; dd < m.ND; ++dd) {
     const BdrtDist& D = m.d[dd];
     double* sA = sm + D.oA;
     const double* gA = D.A + spec * D.A_stride;
-    if (m.toepA) {
+    if (m.wmode) {
+      if (!m.pslot) engine_fill_table(m, D, sA, gA, tid, NTHREADS);
+    } else if (m.toepA) {
       // table of part p: T_p[(col - row) + nfp - 1] = A_p[row][col]; first row for col - row >= 0, first column below
       for (int i = tid; i < 2 * D.lt; i += NTHREADS) {
         const int p = i >= D.lt, d = i - p * D.lt - (m.nfp - 1);
@@ -205,6 +266,18 @@ __device__ inline void engine_load(const BdrtModel& m, double* sm, long long spe
   cta_sync();
 }
 
+// Warp mode with per-spectrum grids: the calling warp loads the tables and omega of spectrum `spec` into its own slot.
+__device__ inline void engine_load_slot(const BdrtModel& m, double* sm, long long spec) {
+  const int lane = threadIdx.x & 31, slot = threadIdx.x >> 5;
+  double* sSt = sm + m.oSt + slot * m.st;
+  __syncwarp();
+  for (int dd = 0; dd < m.ND; ++dd)
+    engine_fill_table(m, m.d[dd], sSt + m.d[dd].oTs, m.d[dd].A + spec * m.d[dd].A_stride, lane, 32);
+  const double* f = m.freq + spec * m.f_stride;
+  for (int i = lane; i < m.Nf; i += 32) sSt[m.oOmS + i] = 2.0 * M_PI * f[i];
+  __syncwarp();
+}
+
 // log p(u) and d/du for the slot of the calling warp; all NWARP warps of the CTA must call it together.
 //   active : this slot has a point to evaluate (inactive slots only help with the matrix products)
 //   u, grad: the slot's D-vectors (generic pointers: shared or global)
@@ -228,8 +301,25 @@ __device__ inline double engine_eval(const BdrtModel& m, double* sm, bool active
   double* sSt = sm + m.oSt + slot * m.st;
   double* sTh = sSt + ND * m.sd;  // Rinf_raw, induc_raw, sigma_res_raw, alpha_prop/re/im_raw, d_0(3) [, d_1(3)]
   double* sSo = sTh + 16;         // sigma_out_raw [Nf], sigma_out_scale [Nf]
-  const double* sOm = sm + m.oOm;
+  const double* sOm = (TOEP == 2 && m.pslot) ? sSt + m.oOmS : sm + m.oOm;
   const double jac = jacobian ? 1.0 : 0.0;
+  if (TOEP == 2) {
+    if (!active) return 0.0;  // warp mode: nobody else needs this warp
+    __syncwarp();
+  }
+#ifdef BDRT_PHASE_CLOCKS
+  long long pc_ = clock64();
+#define PCLK(i)                                                                         \
+  do {                                                                                  \
+    const long long c_ = clock64();                                                     \
+    if (lane == 0 && m.dbg_clk) atomicAdd(&m.dbg_clk[i], (unsigned long long)(c_ - pc_)); \
+    pc_ = c_;                                                                           \
+  } while (0)
+#else
+#define PCLK(i)
+#endif
+  // warp-mode table of distribution dd (CTA-shared, or the slot's own with per-spectrum grids)
+  auto tabp = [&](int dd) { return m.pslot ? sSt + m.d[dd].oTs : sm + m.d[dd].oA; };
   // per-distribution views of the slot's rows
   auto rowX = [&](int dd) { return sm + m.oXV + (dd * NSLOT + slot) * m.ldxv + m.xoff; };  // x_k at [k], zero margins
   auto rowZ = [&](int dd) { return sm + m.oZG + (dd * NSLOT + slot) * m.ldzg; };
@@ -287,7 +377,7 @@ __device__ inline double engine_eval(const BdrtModel& m, double* sm, bool active
             sX[k] = 0.0;  // zeros past K (phase 3 of the previous call wrote V here)
           }
         }
-        if (lane < FBW + 2) sX[128 + lane] = 0.0;
+        for (int k = 128 + lane; k < (TOEP == 2 ? m.xz : 128 + FBW + 2); k += 32) sX[k] = 0.0;
         __syncwarp();
         // 1b. a_j = L_j x, q^2, dups, d lp / d ups, W_j = d_j a_j / ups^2
         const double d0 = sTh[6 + 3 * dd], d1 = sTh[7 + 3 * dd], d2 = sTh[8 + 3 * dd];
@@ -413,7 +503,7 @@ __device__ inline double engine_eval(const BdrtModel& m, double* sm, bool active
         ujac += uu + (Dd.pos ? ux : 0.0);
         if (ND > 1) xsum += xv;
       }
-      const int kend = (Dd.kpad4 > K + bw) ? Dd.kpad4 : K + bw;
+      const int kend = TOEP == 2 ? m.xz : ((Dd.kpad4 > K + bw) ? Dd.kpad4 : K + bw);
       for (int k = K + lane; k < kend; k += 32) sX[k] = 0.0;  // right margin (phase 3 of the previous call wrote V here)
     }
     __syncwarp();
@@ -567,12 +657,59 @@ __device__ inline double engine_eval(const BdrtModel& m, double* sm, bool active
       for (int k = lane; k < kend; k += 32) sX[k] = 0.0;
     }
   }
-  cta_sync();
+  phase_sync<TOEP>();
+  PCLK(1);
   if (snap) *snap = *nact;
 
   // ---------------------------------------------------------------- phase 2: Zhat_d = A_d X_d on the FP64 tensor cores
   const int g = lane >> 2, t = lane & 3;
-  {
+  if (TOEP == 2) {
+    // Warp-private Hankel product: M = (part p, row group i) pairs, N = n (row inside the group), K = kk.
+    //   A[(p, i)][kk] = T_p[kk - 8 - 8 i + nfp - 1 + TPAD],   B[kk][n] = x[n + kk - 8],   C[(p, i)][n] = Zhat_p[n + 8 i]
+    // Rows g of a tile alternate the parts (p = g & 1) so that a half-warp's A fragment spans 16 distinct banks.
+    const int NR8 = nfp >> 3;
+    const int p = g & 1;
+#pragma unroll
+    for (int dd = 0; dd < ND; ++dd) {
+      const BdrtDist& Dd = m.d[dd];
+      const double* sT = tabp(dd) + p * Dd.lt2 + (nfp - 1 + TPAD - 8) + t;
+      const double* bp = rowX(dd) + g + t - 8;
+      double* sZ = rowZ(dd) + p * nfp + 2 * t;
+      const int KKf = (Dd.K + 8 + 3) & ~3;
+      for (int q0 = 0; q0 < NR8; q0 += 12) {  // up to three M tiles (12 row groups of both parts) share the B fragments
+        const int i0 = q0 + (g >> 1), i1 = i0 + 4, i2 = i0 + 8;
+        const bool t1 = q0 + 4 < NR8, t2 = q0 + 8 < NR8;  // warp-uniform
+        const double* a0 = sT - 8 * (i0 < NR8 ? i0 : NR8 - 1);
+        const double* a1 = sT - 8 * (i1 < NR8 ? i1 : NR8 - 1);
+        const double* a2 = sT - 8 * (i2 < NR8 ? i2 : NR8 - 1);
+        double c0[4] = {0, 0, 0, 0}, c1[4] = {0, 0, 0, 0}, c2[4] = {0, 0, 0, 0};  // two accumulation chains per tile
+        int kk = 0;
+#pragma unroll 2
+        for (; kk + 4 < KKf; kk += 8) {
+          const double b0 = bp[kk], b1 = bp[kk + 4];
+          dmma(c0[0], c0[1], a0[kk], b0);
+          dmma(c0[2], c0[3], a0[kk + 4], b1);
+          if (t1) {
+            dmma(c1[0], c1[1], a1[kk], b0);
+            dmma(c1[2], c1[3], a1[kk + 4], b1);
+          }
+          if (t2) {
+            dmma(c2[0], c2[1], a2[kk], b0);
+            dmma(c2[2], c2[3], a2[kk + 4], b1);
+          }
+        }
+        if (kk < KKf) {
+          const double b0 = bp[kk];
+          dmma(c0[0], c0[1], a0[kk], b0);
+          if (t1) dmma(c1[0], c1[1], a1[kk], b0);
+          if (t2) dmma(c2[0], c2[1], a2[kk], b0);
+        }
+        if (i0 < NR8) st2(sZ + 8 * i0, c0[0] + c0[2], c0[1] + c0[3]);
+        if (t1 && i1 < NR8) st2(sZ + 8 * i1, c1[0] + c1[2], c1[1] + c1[3]);
+        if (t2 && i2 < NR8) st2(sZ + 8 * i2, c2[0] + c2[2], c2[1] + c2[3]);
+      }
+    }
+  } else {
     const int nmt = m.n2p >> 3;
     for (int ti = warp; ti < ND * nmt; ti += 2 * NWARP) {
       const int ti2 = ti + NWARP;
@@ -617,7 +754,8 @@ __device__ inline double engine_eval(const BdrtModel& m, double* sm, bool active
       }
     }
   }
-  cta_sync();
+  phase_sync<TOEP>();
+  PCLK(2);
 
   // ---------------------------------------------------------------- phase 3: error model, residual weights (per slot)
   if (active) {
@@ -679,10 +817,10 @@ __device__ inline double engine_eval(const BdrtModel& m, double* sm, bool active
           const double i2 = iM[dd] * iM[dd];
           const double c1 = (Yi[dd] * Yi[dd] - Yr[dd] * Yr[dd]) * i2, c2 = 2.0 * Yr[dd] * Yi[dd] * i2;
           sVd[n] = v_re * c1 + v_im * c2;
-          sVd[nfp + n] = -v_re * c2 + v_im * c1;
+          sVd[m.vim + n] = -v_re * c2 + v_im * c1;
         } else {
           sVd[n] = v_re;
-          sVd[nfp + n] = v_im;
+          sVd[m.vim + n] = v_im;
         }
       }
       Sv += v_re;
@@ -701,9 +839,11 @@ __device__ inline double engine_eval(const BdrtModel& m, double* sm, bool active
 #pragma unroll
     for (int dd = 0; dd < ND; ++dd) {
       double* sVd = rowX(dd);
-      for (int n = Nf + lane; n < nfp; n += 32) {  // padding rows of both parts
+      // padding rows of both parts (warp mode: also the zero gap behind either part that the sliding window reads;
+      // phase 1 wrote x there)
+      for (int n = Nf + lane; n < m.vim; n += 32) {
         sVd[n] = 0.0;
-        sVd[nfp + n] = 0.0;
+        sVd[m.vim + n] = 0.0;
       }
     }
     Sv = warp_sum(Sv);
@@ -727,10 +867,43 @@ __device__ inline double engine_eval(const BdrtModel& m, double* sm, bool active
       for (int n = lane; n < m.n2p; n += 32) sVd[n] = 0.0;
     }
   }
-  cta_sync();
+  phase_sync<TOEP>();
+  PCLK(3);
 
   // ---------------------------------------------------------------- phase 4: G_d = A_d^T V_d on the FP64 tensor cores
-  {
+  if (TOEP == 2) {
+    // Warp-private Hankel product: M = column group i, N = n (column inside the group), K = (part p, kk).
+    //   A[i][(p, kk)] = T_p[8 i + 7 - kk + nfp - 1 + TPAD],   B[(p, kk)][n] = V_p[n - 7 + kk],   C[i][n] = G[n + 8 i]
+    const int KKt = (Nf + 7 + 3) & ~3;
+#pragma unroll
+    for (int dd = 0; dd < ND; ++dd) {
+      const BdrtDist& Dd = m.d[dd];
+      const int K8 = Dd.kpad8 >> 3, lt2 = Dd.lt2;
+      const double* sT = tabp(dd) + (nfp + 6 + TPAD) - t;
+      const double* bp = rowX(dd) + g - 7 + t;
+      const double* bq = bp + m.vim;
+      double* sG = rowZ(dd) + 2 * t;
+      for (int q0 = 0; q0 < K8; q0 += 16) {  // two M tiles share the B fragments; one chain per (tile, part)
+        const int i0 = q0 + g, i1 = i0 + 8;
+        const bool t1 = q0 + 8 < K8;  // warp-uniform
+        const double* a0 = sT + 8 * (i0 < K8 ? i0 : K8 - 1);
+        const double* a1 = sT + 8 * (i1 < K8 ? i1 : K8 - 1);
+        double c0[4] = {0, 0, 0, 0}, c1[4] = {0, 0, 0, 0};
+#pragma unroll 2
+        for (int kk = 0; kk < KKt; kk += 4) {
+          const double b0 = bp[kk], b1 = bq[kk];
+          dmma(c0[0], c0[1], a0[-kk], b0);
+          dmma(c0[2], c0[3], a0[lt2 - kk], b1);
+          if (t1) {
+            dmma(c1[0], c1[1], a1[-kk], b0);
+            dmma(c1[2], c1[3], a1[lt2 - kk], b1);
+          }
+        }
+        if (i0 < K8) st2(sG + 8 * i0, c0[0] + c0[2], c0[1] + c0[3]);
+        if (t1 && i1 < K8) st2(sG + 8 * i1, c1[0] + c1[2], c1[1] + c1[3]);
+      }
+    }
+  } else {
     int nmt_d[MAXD], nmt_tot = 0;
 #pragma unroll
     for (int dd = 0; dd < ND; ++dd) {
@@ -784,7 +957,8 @@ __device__ inline double engine_eval(const BdrtModel& m, double* sm, bool active
       }
     }
   }
-  cta_sync();
+  phase_sync<TOEP>();
+  PCLK(4);
 
   // ---------------------------------------------------------------- phase 5: assemble d lp / d u_x (per slot)
   if (active) {
@@ -827,13 +1001,21 @@ __device__ inline double engine_eval(const BdrtModel& m, double* sm, bool active
     lp = warp_sum(lp);
     __syncwarp();
   }
+  PCLK(5);
+#ifdef BDRT_PHASE_CLOCKS
+  if (lane == 0 && m.dbg_clk) atomicAdd(&m.dbg_clk[0], 1ull);
+#endif
   return lp;
 }
 #endif  // __CUDACC__
 
 // host side (model.cu)
+// allow_wmode: 0 the calling kernel only has the cooperative instantiations (engine_eval<0 / 1, ..>: Newton);
+// 1 it has all three (the log_prob test hook: warp mode whenever the operands are Toeplitz, BDRT_COOP=1 in the
+// environment selects the cooperative Toeplitz products instead, so that the tests cover them);
+// 2 it has warp mode and the dense layout only (the L-BFGS and NUTS drivers: BDRT_COOP is ignored)
 int bdrt_model_prepare(bdrt_ctx* ctx, const bdrt_series_data* data, BdrtModel* m, size_t extra_ws_bytes,
-                       void** extra_ws);
+                       void** extra_ws, int allow_wmode = 0);
 
 // Shared-memory plan of a persistent solver kernel: the engine region plus as many of the solver's per-slot work
 // vectors (Dpad doubles each, NSLOT slots) as fit.  With Toeplitz-resident operands two CTAs share an SM.
@@ -875,11 +1057,31 @@ static inline BdrtPlan bdrt_plan(const bdrt_ctx* ctx, const BdrtModel& m, int Dp
     else if ((m).ND == 2) BDRT_LAUNCH_ONE(ctx, KERNEL, T, 2, F, grid, smem, __VA_ARGS__);    \
     else BDRT_LAUNCH_ONE(ctx, KERNEL, T, 3, F, grid, smem, __VA_ARGS__);                     \
   } while (0)
-#define BDRT_LAUNCH(ctx, m, KERNEL, grid, smem, ...)                                          \
-  do {                                                                                        \
-    if ((m).toepA && (m).fast) BDRT_LAUNCH_ND(ctx, m, KERNEL, 1, 1, grid, smem, __VA_ARGS__); \
-    else if ((m).toepA) BDRT_LAUNCH_ND(ctx, m, KERNEL, 1, 0, grid, smem, __VA_ARGS__);        \
+// BDRT_LAUNCH: every layout (model_prepare(.., allow_wmode = 1)); BDRT_LAUNCH_COOP: cooperative products only
+// (allow_wmode = 0); BDRT_LAUNCH_SOLVER: warp mode or dense (allow_wmode = 2)
+#define BDRT_LAUNCH_WARP_(ctx, m, KERNEL, grid, smem, ...)                                    \
+    if ((m).wmode && (m).fast) BDRT_LAUNCH_ND(ctx, m, KERNEL, 2, 1, grid, smem, __VA_ARGS__); \
+    else if ((m).wmode) BDRT_LAUNCH_ND(ctx, m, KERNEL, 2, 0, grid, smem, __VA_ARGS__);
+#define BDRT_LAUNCH_COOP_(ctx, m, KERNEL, grid, smem, ...)                                         \
+    if ((m).toepA && (m).fast) BDRT_LAUNCH_ND(ctx, m, KERNEL, 1, 1, grid, smem, __VA_ARGS__);      \
+    else if ((m).toepA) BDRT_LAUNCH_ND(ctx, m, KERNEL, 1, 0, grid, smem, __VA_ARGS__);
+#define BDRT_LAUNCH_END_(ctx, m, KERNEL, grid, smem, ...)                                     \
     else BDRT_LAUNCH_ND(ctx, m, KERNEL, 0, 0, grid, smem, __VA_ARGS__);                       \
     (ctx)->launches++;                                                                        \
-    BDRT_CUDA(ctx, cudaGetLastError());                                                       \
+    BDRT_CUDA(ctx, cudaGetLastError());
+#define BDRT_LAUNCH(ctx, m, KERNEL, grid, smem, ...)                      \
+  do {                                                                    \
+    BDRT_LAUNCH_WARP_(ctx, m, KERNEL, grid, smem, __VA_ARGS__)            \
+    else BDRT_LAUNCH_COOP_(ctx, m, KERNEL, grid, smem, __VA_ARGS__)       \
+    BDRT_LAUNCH_END_(ctx, m, KERNEL, grid, smem, __VA_ARGS__)             \
+  } while (0)
+#define BDRT_LAUNCH_COOP(ctx, m, KERNEL, grid, smem, ...)                 \
+  do {                                                                    \
+    BDRT_LAUNCH_COOP_(ctx, m, KERNEL, grid, smem, __VA_ARGS__)            \
+    BDRT_LAUNCH_END_(ctx, m, KERNEL, grid, smem, __VA_ARGS__)             \
+  } while (0)
+#define BDRT_LAUNCH_SOLVER(ctx, m, KERNEL, grid, smem, ...)               \
+  do {                                                                    \
+    BDRT_LAUNCH_WARP_(ctx, m, KERNEL, grid, smem, __VA_ARGS__)            \
+    BDRT_LAUNCH_END_(ctx, m, KERNEL, grid, smem, __VA_ARGS__)             \
   } while (0)

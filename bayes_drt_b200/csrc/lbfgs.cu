@@ -402,6 +402,19 @@ lbfgs_kernel(BdrtModel m, bdrt_lbfgs_opts o, double* __restrict__ U, double* lp_
   // slots of a CTA share the resident operands, so the CTA takes one spectrum at a time, slot 0 optimises it and the
   // other warps only serve the cooperative products.  Either way a warp that is out of work keeps serving engine_eval()
   // until every slot of the CTA is done (single call site: the engine is inlined there).
+  if (TOEP == 2) {
+    // warp mode: the slots are independent -- every warp pulls spectra until the queue is empty (with per-spectrum
+    // grids it first loads that spectrum's tables into its own slot)
+    while (true) {
+      int b = 0;
+      if (lane == 0) b = atomicAdd(queue, 1);
+      b = __shfl_sync(0xffffffffu, b, 0);
+      if (b >= m.B) break;
+      if (m.pslot) engine_load_slot(m, sm, b);
+      run_spectrum(b);
+    }
+    return;
+  }
   const bool per_spec = m.d[0].A_stride != 0;
   __shared__ int s_spec;
   while (true) {
@@ -469,9 +482,10 @@ extern "C" int bdrt_map_lbfgs(bdrt_ctx* ctx, const bdrt_series_data* data, const
   const size_t hist_bytes = (size_t)grid_max * NSLOT * 2 * opts->history * Dpad * sizeof(double);
   const size_t gvec_bytes = (size_t)grid_max * NSLOT * 5 * Dpad * sizeof(double);
   void* extra = nullptr;
-  int rc = bdrt_model_prepare(ctx, data, &m, 256 + hist_bytes + gvec_bytes, &extra);
+  int rc = bdrt_model_prepare(ctx, data, &m, 256 + hist_bytes + gvec_bytes, &extra, 2);
   if (rc) return rc;
   if (data->B == 0) return BDRT_OK;
+  if (m.wmode && grid > (data->B + NSLOT - 1) / NSLOT) grid = (data->B + NSLOT - 1) / NSLOT;  // 8 spectra per CTA
   int* queue = (int*)extra;
   double* hist = (double*)((char*)extra + 256);
   double* gvec = (double*)((char*)extra + 256 + hist_bytes);
@@ -479,7 +493,7 @@ extern "C" int bdrt_map_lbfgs(bdrt_ctx* ctx, const bdrt_series_data* data, const
   // how many of the 5 work vectors per slot fit in shared memory
   const BdrtPlan pl = bdrt_plan(ctx, m, Dpad, 5, 2);
   if (grid > ctx->sm_count * pl.ctas_per_sm) grid = ctx->sm_count * pl.ctas_per_sm;
-  BDRT_LAUNCH(ctx, m, lbfgs_kernel, grid, pl.smem, m, *opts, u, lp, iters, n_eval, status, queue, hist, gvec, pl.nvec,
+  BDRT_LAUNCH_SOLVER(ctx, m, lbfgs_kernel, grid, pl.smem, m, *opts, u, lp, iters, n_eval, status, queue, hist, gvec, pl.nvec,
               Dpad);
   return BDRT_OK;
 }

@@ -32,6 +32,17 @@ extern "C" int bdrt_ctx_destroy(bdrt_ctx* ctx) {
   return BDRT_OK;
 }
 
+#ifdef BDRT_PHASE_CLOCKS
+// profiling builds only (not part of include/bdrt.h): read and reset the per-phase clock sums
+extern "C" int bdrt_debug_phase_clocks(bdrt_ctx* ctx, unsigned long long* out16_host) {
+  if (!ctx->dbg_clk) return BDRT_E_NULL;
+  BDRT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  BDRT_CUDA(ctx, cudaMemcpy(out16_host, ctx->dbg_clk, 16 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+  BDRT_CUDA(ctx, cudaMemset(ctx->dbg_clk, 0, 16 * sizeof(unsigned long long)));
+  return BDRT_OK;
+}
+#endif
+
 extern "C" const char* bdrt_last_error(const bdrt_ctx* ctx) { return ctx ? ctx->err : "null context"; }
 extern "C" long long bdrt_launch_count(const bdrt_ctx* ctx) { return ctx ? ctx->launches : 0; }
 
@@ -129,7 +140,7 @@ __global__ void toep_check_kernel(const double* A0, long long stride, int Nf, in
 }
 
 int bdrt_model_prepare(bdrt_ctx* ctx, const bdrt_series_data* d, BdrtModel* m, size_t extra_ws_bytes,
-                       void** extra_ws) {
+                       void** extra_ws, int allow_wmode) {
   if (!d) BDRT_FAIL(ctx, BDRT_E_NULL, "null data");
   if (!d->A || !d->Z || !d->freq || !d->L) BDRT_FAIL(ctx, BDRT_E_NULL, "bdrt_series_data: null matrix pointer");
   const int base = d->model & 15;
@@ -237,6 +248,16 @@ int bdrt_model_prepare(bdrt_ctx* ctx, const bdrt_series_data* d, BdrtModel* m, s
   m->bw = bw;
   for (int i = 0; i < nd; ++i) m->d[i].toepL = hinfo[4 * i + 1] && (Ks[i] >= 2 * bw + 1);
   m->toepA = hinfo[2];
+#ifdef BDRT_PHASE_CLOCKS
+  if (!ctx->dbg_clk) {
+    BDRT_CUDA(ctx, cudaMalloc(&ctx->dbg_clk, 16 * sizeof(unsigned long long)));
+    BDRT_CUDA(ctx, cudaMemset(ctx->dbg_clk, 0, 16 * sizeof(unsigned long long)));
+  }
+  m->dbg_clk = ctx->dbg_clk;
+#endif
+  const char* fc = getenv("BDRT_COOP");
+  m->wmode = m->toepA && allow_wmode && !(allow_wmode == 1 && fc && fc[0] == '1');
+  m->pslot = m->wmode && d->per_spectrum_grid;
   // register-tiled per-slot phases: every distribution has Toeplitz L within FBW off-diagonals and K <= 128
   // (BDRT_FORCE_GENERIC=1 keeps the generic per-slot code, for tests)
   const char* fg = getenv("BDRT_FORCE_GENERIC");
@@ -271,7 +292,21 @@ logpost_kernel(BdrtModel m, const double* u, const int* spec, int n_cols, int ja
                int cta_per_spec) {
   extern __shared__ __align__(16) double sm[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  if (!cta_per_spec) {
+  if (TOEP == 2 && m.pslot) {
+    // warp mode with per-spectrum grids: every warp walks its own columns and reloads its tables when the spectrum changes
+    engine_load(m, sm, 0);
+    int loaded = -1;
+    for (int c = blockIdx.x * NSLOT + warp; c < n_cols; c += gridDim.x * NSLOT) {
+      const int b = spec ? spec[c] : c % m.B;
+      if (b != loaded) {
+        engine_load_slot(m, sm, b);
+        loaded = b;
+      }
+      const double v = engine_eval<TOEP, MK, FAST>(m, sm, true, u + (long long)c * m.D, grad + (long long)c * m.D,
+                                                   m.Z + (long long)b * m.N2, jacobian);
+      if (lane == 0) lp[c] = v;
+    }
+  } else if (!cta_per_spec) {
     engine_load(m, sm, 0);
     const int ngroups = (n_cols + NSLOT - 1) / NSLOT;
     for (int gidx = blockIdx.x; gidx < ngroups; gidx += gridDim.x) {
@@ -318,13 +353,13 @@ extern "C" int bdrt_logpost_grad(bdrt_ctx* ctx, const bdrt_series_data* data, co
   if (!u || !lp || !grad) BDRT_FAIL(ctx, BDRT_E_NULL, "bdrt_logpost_grad: null pointer");
   if (n_cols < 0) BDRT_FAIL(ctx, BDRT_E_SIZE, "n_cols < 0");
   BdrtModel m;
-  int rc = bdrt_model_prepare(ctx, data, &m, 0, nullptr);
+  int rc = bdrt_model_prepare(ctx, data, &m, 0, nullptr, 1);
   if (rc) return rc;
   if (n_cols == 0 || data->B == 0) return BDRT_OK;
   const BdrtPlan pl = bdrt_plan(ctx, m, 2, 0, 0);
   const int slots = ctx->sm_count * pl.ctas_per_sm;
   int grid;
-  if (data->per_spectrum_grid)
+  if (data->per_spectrum_grid && !m.wmode)
     grid = data->B < slots ? data->B : slots;
   else {
     const int ngroups = (n_cols + NSLOT - 1) / NSLOT;

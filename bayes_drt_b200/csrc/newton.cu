@@ -254,7 +254,7 @@ extern "C" int bdrt_map_newton(bdrt_ctx* ctx, const bdrt_series_data* data, cons
   const int in_smem = packed <= smem_doubles;
   size_t smem = (size_t)m.oUser * sizeof(double);
   if (in_smem && (size_t)packed * 8 > smem) smem = (size_t)packed * 8;
-  BDRT_LAUNCH(ctx, m, newton_kernel, grid, smem, m, *opts, u, lp, gnorm, iters, n_eval, (double*)extra, per_cta, in_smem,
+  BDRT_LAUNCH_COOP(ctx, m, newton_kernel, grid, smem, m, *opts, u, lp, gnorm, iters, n_eval, (double*)extra, per_cta, in_smem,
               Dpad);
   return BDRT_OK;
 }

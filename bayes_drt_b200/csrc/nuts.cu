@@ -369,6 +369,23 @@ nuts_kernel(BdrtModel m, bdrt_nuts_opts o, const double* __restrict__ U0, double
   // Per-spectrum grids: the 8 slots of a CTA share the resident operands, so a CTA takes one spectrum at a time and
   // its slots run that spectrum's chains (chain = warp, warp + 8, ...).  A warp that is out of work keeps serving
   // engine_eval() until every slot of the CTA is done (single call site: the engine is inlined there).
+  if (TOEP == 2) {
+    // warp mode: the slots are independent -- every warp pulls (spectrum, chain) items until the queue is empty (with
+    // per-spectrum grids it first loads that spectrum's tables into its own slot)
+    long long loaded = -1;
+    while (true) {
+      long long wi = 0;
+      if (lane == 0) wi = atomicAdd(queue, 1);
+      wi = __shfl_sync(0xffffffffu, wi, 0);
+      if (wi >= n_work) break;
+      if (m.pslot && wi / o.chains != loaded) {
+        loaded = wi / o.chains;
+        engine_load_slot(m, sm, loaded);
+      }
+      run_chain(wi);
+    }
+    return;
+  }
   const bool per_spec = m.d[0].A_stride != 0;
   __shared__ int s_spec;
   while (true) {
@@ -444,16 +461,17 @@ extern "C" int bdrt_nuts(bdrt_ctx* ctx, const bdrt_series_data* data, const bdrt
   const size_t ck_bytes = (size_t)grid_max * NSLOT * 2 * MAXDEPTH * Dpad * sizeof(double);
   BdrtModel m;
   void* extra = nullptr;
-  int rc = bdrt_model_prepare(ctx, data, &m, 256 + gvec_bytes + ck_bytes, &extra);
+  int rc = bdrt_model_prepare(ctx, data, &m, 256 + gvec_bytes + ck_bytes, &extra, 2);
   if (rc) return rc;
   if (n_work == 0) return BDRT_OK;
+  if (m.wmode && grid > (n_work + NSLOT - 1) / NSLOT) grid = (int)((n_work + NSLOT - 1) / NSLOT);  // 8 chains per CTA
   int* queue = (int*)extra;
   double* gvec = (double*)((char*)extra + 256);
   double* ckpt = (double*)((char*)extra + 256 + gvec_bytes);
   BDRT_CUDA(ctx, cudaMemsetAsync(queue, 0, 256, ctx->stream));
   const BdrtPlan pl = bdrt_plan(ctx, m, Dpad, NV, 2);
   if (grid > ctx->sm_count * pl.ctas_per_sm) grid = ctx->sm_count * pl.ctas_per_sm;
-  BDRT_LAUNCH(ctx, m, nuts_kernel, grid, pl.smem, m, *opts, u0, draws, stepsize, n_leapfrog, n_divergent, n_maxdepth,
+  BDRT_LAUNCH_SOLVER(ctx, m, nuts_kernel, grid, pl.smem, m, *opts, u0, draws, stepsize, n_leapfrog, n_divergent, n_maxdepth,
               accept, queue, gvec, ckpt, pl.nvec, Dpad);
   return BDRT_OK;
 }

@@ -42,7 +42,10 @@ def polish(func, x0, max_iter=60, gtol=1e-9, verbose=False):
                 continue
             step = -np.linalg.solve(Lc.T, np.linalg.solve(Lc, g))
             res = func(x + step)
-            if res is not None and res[0] < f + 1e-4 * (g @ step):
+            # sufficient decrease, or -- at the rounding floor of f (|f| ~ 1e3, decrements ~ gnorm^2), where the Armijo
+            # test is decided by noise -- a halved gradient norm: Newton's quadratic phase by its own measure
+            if res is not None and (res[0] < f + 1e-4 * (g @ step) or
+                                    (gn < 1e-5 and np.max(np.abs(res[1])) < 0.5 * gn and res[0] < f + 1e-9 * abs(f))):
                 x = x + step
                 f, g = res
                 mu = max(mu * 0.1, 1e-12)

@@ -17,15 +17,18 @@ def golden_dir():
     return os.path.join(ROOT, 'tests', 'golden')
 
 
-@pytest.fixture(params=['toeplitz', 'toeplitz-generic', 'dense'])
+@pytest.fixture(params=['toeplitz', 'toeplitz-generic', 'toeplitz-coop', 'dense'])
 def resident_A(request, monkeypatch):
-    """Run a GPU test on every code path of the engine: the Toeplitz tables (picked automatically for shared log-uniform
-    grids, two CTAs per SM) with the register-tiled per-slot phases, the same with the generic per-slot phases
-    (BDRT_FORCE_GENERIC=1), and the dense-resident A (BDRT_FORCE_DENSE=1)."""
-    monkeypatch.delenv('BDRT_FORCE_DENSE', raising=False)
-    monkeypatch.delenv('BDRT_FORCE_GENERIC', raising=False)
+    """Run a GPU test on every code path of the engine: the Toeplitz tables with warp-private Hankel products (picked
+    automatically for shared log-uniform grids, two CTAs per SM) and the register-tiled per-slot phases, the same with
+    the generic per-slot phases (BDRT_FORCE_GENERIC=1), the Toeplitz tables with the cooperative CTA-wide products
+    (BDRT_COOP=1; what the Newton kernel always uses), and the dense-resident A (BDRT_FORCE_DENSE=1)."""
+    for k in ('BDRT_FORCE_DENSE', 'BDRT_FORCE_GENERIC', 'BDRT_COOP'):
+        monkeypatch.delenv(k, raising=False)
     if request.param == 'dense':
         monkeypatch.setenv('BDRT_FORCE_DENSE', '1')
     elif request.param == 'toeplitz-generic':
         monkeypatch.setenv('BDRT_FORCE_GENERIC', '1')
+    elif request.param == 'toeplitz-coop':
+        monkeypatch.setenv('BDRT_COOP', '1')
     return request.param
