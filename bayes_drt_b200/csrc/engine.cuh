@@ -141,7 +141,13 @@ static inline int bdrt_model_layout(BdrtModel* m) {
   m->ws = m->Kmax + 2 * m->wm;
   m->ws += m->ws & 1;  // even
   m->kup = (m->Kmax + 3) & ~3;  // a lane's 4 consecutive coefficients never run past the row
+  int mz = k8 > m->n2p ? k8 : m->n2p;
+  if (m->fast && mz < 128) mz = 128;  // the fast path reads 4 x 32 gradient entries per row
+  m->ldzg = mz + 4;  // % 8 == 4
+  // The Z / G row of a slot (products of phases 2 and 4, read by phases 3 and 5) lives on top of the stencil scratch of
+  // phase 1 (dead by then); phase 1 re-zeroes the margins of its scratch vectors on every evaluation.
   m->sd = 3 * m->ws + 2 * m->kup;
+  if (m->sd < m->ldzg) m->sd = m->ldzg;
   m->st = m->ND * m->sd + 16 + ((m->flags & F_OUT) ? 2 * m->Nf : 0);
   m->st += m->st & 1;
   if (m->pslot) {  // per-slot tables and omega
@@ -152,9 +158,6 @@ static inline int bdrt_model_layout(BdrtModel* m) {
     m->oOmS = m->st;
     m->st += (m->Nf + 1) & ~1;
   }
-  int mz = k8 > m->n2p ? k8 : m->n2p;
-  if (m->fast && mz < 128) mz = 128;  // the fast path reads 4 x 32 gradient entries per row
-  m->ldzg = mz + 4;  // % 8 == 4
   // unconstrained vector, Stan declaration order:
   //   Rinf_raw induc_raw | x_0 .. x_{ND-1} | sigma_res alpha_prop alpha_re alpha_im | [sigma_out_raw sigma_out_scale] |
   //   ups_0 .. ups_{ND-1} | d_0(3) .. d_{ND-1}(3)
@@ -173,7 +176,7 @@ static inline int bdrt_model_layout(BdrtModel* m) {
     else o += m->toepA ? 2 * m->d[i].lt : m->n2p * m->d[i].lda + 8;
   }
   m->oXV = o;  o += m->ND * NSLOT * m->ldxv;
-  m->oZG = o;  o += m->ND * NSLOT * m->ldzg;
+  m->oZG = o;  // (no region of its own: see sd above)
   m->oSt = o;  o += NSLOT * m->st;
   for (int i = 0; i < m->ND; ++i) { m->d[i].oTap = o; o += 3 * LBW; }
   m->oOm = o;  o += m->Nf;
@@ -205,6 +208,69 @@ __device__ __forceinline__ void ld2(const double* p, double& a, double& b) {  //
   b = v.y;
 }
 __device__ __forceinline__ void st2(double* p, double a, double b) { *reinterpret_cast<double2*>(p) = make_double2(a, b); }
+
+// Branch-free exp for the register-tiled phases: Cody-Waite reduction x = k ln2 + r, |r| <= ln2 / 2, Taylor polynomial of
+// degree 13 (truncation 4e-18 relative), scaling by 2^k in two exact steps (so results in the subnormal range are right
+// and +-inf / overflow / underflow come out as in libm); NaN propagates.  About 1 ulp, like CUDA's exp(), but without
+// its slow-path branch, so the independent calls of an unrolled loop are interleaved by the compiler.
+__device__ __forceinline__ double bdrt_exp(double x) {
+  const double xc = fmin(fmax(x, -746.0), 710.0);
+  const double t = fma(xc, 1.4426950408889634, 6755399441055744.0);  // 1.5 * 2^52: rint(x log2 e) in the low word
+  const int ki = __double2loint(t);
+  const double kf = t - 6755399441055744.0;
+  double r = fma(kf, -6.93147180369123816490e-01, xc);
+  r = fma(kf, -1.90821492927058770002e-10, r);
+  double q = 1.6059043836821613e-10;        // 1/13!
+  q = fma(q, r, 2.08767569878681e-09);      // 1/12!
+  q = fma(q, r, 2.505210838544172e-08);     // 1/11!
+  q = fma(q, r, 2.755731922398589e-07);     // 1/10!
+  q = fma(q, r, 2.7557319223985893e-06);    // 1/9!
+  q = fma(q, r, 2.48015873015873e-05);      // 1/8!
+  q = fma(q, r, 1.984126984126984e-04);     // 1/7!
+  q = fma(q, r, 1.388888888888889e-03);     // 1/6!
+  q = fma(q, r, 8.333333333333333e-03);     // 1/5!
+  q = fma(q, r, 4.1666666666666664e-02);    // 1/4!
+  q = fma(q, r, 1.6666666666666666e-01);    // 1/3!
+  q = fma(q, r, 0.5);
+  q = fma(q, r, 1.0);
+  q = fma(q, r, 1.0);
+  const int k1 = ki >> 1, k2 = ki - k1;
+  const double s1 = __hiloint2double((1023 + k1) << 20, 0), s2 = __hiloint2double((1023 + k2) << 20, 0);
+  const double y = q * s1 * s2;
+  return x != x ? x : y;
+}
+// Branch-free reciprocal: hardware seed (rcp.approx.ftz.f64) + two Newton steps; about 1 ulp for normal arguments.
+// 0 and +-inf give NaN instead of +-inf / 0: the engine only divides by variances and scales that are positive and
+// finite at every point the solvers can accept, and a non-finite log density is a rejected point either way.
+__device__ __forceinline__ double bdrt_rcp(double x) {
+  double y;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+  double e = fma(-x, y, 1.0);
+  y = fma(y, e, y);
+  e = fma(-x, y, 1.0);
+  return fma(y, e, y);
+}
+// Sums of N = 2^n per-lane values over the warp in one transposed butterfly: the first n exchange steps halve the number
+// of values a lane carries (it keeps the sums its lane bits select and sends the others), the remaining 5 - n steps are
+// plain butterflies.  N + 4 - n... shuffles instead of 5 N.  On return v[0] of lane L is the total of value number
+// L >> (5 - n) (identical bits in every lane of that group; the summation order depends on nothing but N).
+template <int N>
+__device__ __forceinline__ double warp_sum_multi(double (&v)[N], int lane) {
+  static_assert(N == 2 || N == 4 || N == 8 || N == 16, "N must be 2, 4, 8 or 16");
+  int off = 16;
+#pragma unroll
+  for (int n = N; n > 1; n >>= 1, off >>= 1) {
+    const bool up = lane & off;
+#pragma unroll
+    for (int i = 0; i < n / 2; ++i) {
+      const double send = up ? v[i] : v[i + n / 2], keep = up ? v[i + n / 2] : v[i];
+      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+    }
+  }
+#pragma unroll
+  for (; off > 0; off >>= 1) v[0] += __shfl_xor_sync(0xffffffffu, v[0], off);
+  return v[0];
+}
 
 // Is coordinate i of the unconstrained vector a lower=0 parameter (theta = exp(u))?
 __device__ __forceinline__ bool bdrt_is_exp(const BdrtModel& m, int i) {
@@ -259,7 +325,6 @@ __device__ inline void engine_load(const BdrtModel& m, double* sm, long long spe
     }
   }
   for (int i = tid; i < m.ND * NSLOT * m.ldxv; i += NTHREADS) sm[m.oXV + i] = 0.0;
-  for (int i = tid; i < m.ND * NSLOT * m.ldzg; i += NTHREADS) sm[m.oZG + i] = 0.0;
   for (int i = tid; i < NSLOT * m.st; i += NTHREADS) sm[m.oSt + i] = 0.0;
   const double* f = m.freq + spec * m.f_stride;
   for (int i = tid; i < m.Nf; i += NTHREADS) sm[m.oOm + i] = 2.0 * M_PI * f[i];
@@ -322,7 +387,7 @@ __device__ inline double engine_eval(const BdrtModel& m, double* sm, bool active
   auto tabp = [&](int dd) { return m.pslot ? sSt + m.d[dd].oTs : sm + m.d[dd].oA; };
   // per-distribution views of the slot's rows
   auto rowX = [&](int dd) { return sm + m.oXV + (dd * NSLOT + slot) * m.ldxv + m.xoff; };  // x_k at [k], zero margins
-  auto rowZ = [&](int dd) { return sm + m.oZG + (dd * NSLOT + slot) * m.ldzg; };
+  auto rowZ = [&](int dd) { return sSt + dd * m.sd; };  // on top of the phase-1 scratch
 
   double lp = 0.0;
   double xsum = 0.0;  // sum(xs) + sum(xp_raw)  (Series-Parallel :56)
@@ -335,7 +400,7 @@ __device__ inline double engine_eval(const BdrtModel& m, double* sm, bool active
       const int i = lane < 2 ? lane : (lane < 6 ? m.off_err + lane - 2 : m.d[0].off_d + lane - 6);
       const double ui = u[i];
       ujac += ui;
-      sTh[lane] = exp(ui);
+      sTh[lane] = bdrt_exp(ui);
     }
     if (outl) {
       for (int i = lane; i < 2 * Nf; i += 32) {
@@ -345,10 +410,18 @@ __device__ inline double engine_eval(const BdrtModel& m, double* sm, bool active
       }
     }
     if (FAST) {
-      // Register-tiled per-slot phase (Toeplitz L with |d| <= FBW, K <= 128).  Everything that touches u / grad uses the
-      // interleaved ownership k = lane + 32 j (conflict-free 8-byte accesses); the stencils use the tiled ownership
-      // kq .. kq+3 with 16-byte shared-memory windows, and the taps come straight from the parameter bank.
+      // Register-tiled per-slot phase (Toeplitz L with |d| <= FBW, K <= 128), written branch-free: every lane runs the
+      // same straight-line code on clamped indices and masks the results by selects / predicated stores, so that the
+      // compiler interleaves the independent exp / reciprocal / FMA chains of the lane's four coefficients (at 4 warps
+      // per scheduler the kernel is latency bound: instruction-level parallelism inside the warp is what fills the
+      // pipes).  Everything that touches u / grad uses the interleaved ownership k = lane + 32 j (conflict-free 8-byte
+      // accesses); the stencils use the tiled ownership kq .. kq+3 with 16-byte shared-memory windows, and the taps
+      // come straight from the parameter bank.  Warp sums are deferred and batched (warp_sum_multi).
       const int kq = 4 * lane;
+      constexpr int NRED = ND == 1 ? 4 : (ND == 2 ? 8 : 16);
+      double red[NRED];
+#pragma unroll
+      for (int i = 0; i < NRED; ++i) red[i] = 0.0;
 #pragma unroll
       for (int dd = 0; dd < ND; ++dd) {
         const BdrtDist& Dd = m.d[dd];
@@ -358,32 +431,44 @@ __device__ inline double engine_eval(const BdrtModel& m, double* sm, bool active
         double* sUps = sSt + dd * m.sd + 3 * m.ws;
         double* sIu = sUps + m.kup;
         // 1a. transforms; the separable hyper-prior terms are summed here
+        {
+          double ux[4], uu[4], xv[4];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const int k = lane + 32 * j;
-          if (k < K) {
-            const double ux = u[Dd.off_x + k], uu = u[Dd.off_ups + k];
-            const double xv = Dd.pos ? exp(ux) : ux;
-            const double ups = 0.15 * exp(uu);
-            const double iu = __drcp_rn(ups);
-            sX[k] = xv;
-            sUps[k] = ups;
-            sIu[k] = iu;
-            ujac += uu + (Dd.pos ? ux : 0.0);
-            if (ND > 1) xsum += xv;
+          for (int j = 0; j < 4; ++j) {
+            const int k = lane + 32 * j, kc = k < K ? k : K - 1;
+            ux[j] = u[Dd.off_x + kc];
+            uu[j] = u[Dd.off_ups + kc];
+            xv[j] = ux[j];
+          }
+          if (Dd.pos) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) xv[j] = bdrt_exp(ux[j]);
+          }
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const int k = lane + 32 * j;
+            const bool v = k < K;
+            const double ups = 0.15 * bdrt_exp(uu[j]);
+            const double iu = bdrt_rcp(ups);
+            sX[k] = v ? xv[j] : 0.0;  // zeros past K (phase 3 of the previous call wrote V here)
+            if (v) {
+              sUps[k] = ups;
+              sIu[k] = iu;
+            }
+            ujac += v ? uu[j] + (Dd.pos ? ux[j] : 0.0) : 0.0;
+            if (ND > 1) xsum += v ? xv[j] : 0.0;
             // - log ups ; ups_raw ~ inv_gamma(alpha, beta)
-            lp += -(LOG_015 + uu) - (m.ups_alpha + 1.0) * uu - m.ups_beta * 0.15 * iu;
-          } else if (k < 128 + FBW + 2) {
-            sX[k] = 0.0;  // zeros past K (phase 3 of the previous call wrote V here)
+            lp += v ? -(LOG_015 + uu[j]) - (m.ups_alpha + 1.0) * uu[j] - m.ups_beta * 0.15 * iu : 0.0;
           }
         }
         for (int k = 128 + lane; k < (TOEP == 2 ? m.xz : 128 + FBW + 2); k += 32) sX[k] = 0.0;
         __syncwarp();
-        // 1b. a_j = L_j x, q^2, dups, d lp / d ups, W_j = d_j a_j / ups^2
+        // 1b. a_j = L_j x, q^2, dups, d lp / d ups, W_j = d_j a_j / ups^2   (lanes past K work on zeros / stale scratch
+        // and store nothing)
         const double d0 = sTh[6 + 3 * dd], d1 = sTh[7 + 3 * dd], d2 = sTh[8 + 3 * dd];
         double sa0 = 0, sa1 = 0, sa2 = 0;
-        double gu4[4] = {0, 0, 0, 0};
-        if (kq < K) {
+        double gu4[4];
+        {
           double xw[16];  // x[kq - 6 .. kq + 9]
 #pragma unroll
           for (int i = 0; i < 8; ++i) ld2(sX + kq - FBW + 2 * i, xw[2 * i], xw[2 * i + 1]);
@@ -409,64 +494,73 @@ __device__ inline double engine_eval(const BdrtModel& m, double* sm, bool active
             const int k = kq + j;
             const bool v = k < K;
             const double upk = upw[j + 2], iuk = iuw[j + 2], iu2 = iuk * iuk;
-            const double q2 = d0 * a0[j] * a0[j] + d1 * a1[j] * a1[j] + d2 * a2[j] * a2[j];
-            if (v) {
-              lp += -0.5 * q2 * iu2;  // q ~ normal(0, ups)
-              sa0 = fma(a0[j] * a0[j], iu2, sa0);
-              sa1 = fma(a1[j] * a1[j], iu2, sa1);
-              sa2 = fma(a2[j] * a2[j], iu2, sa2);
-            }
+            const double q0 = a0[j] * a0[j] * iu2, q1 = a1[j] * a1[j] * iu2, q2 = a2[j] * a2[j] * iu2;
+            const double qq = d0 * q0 + d1 * q1 + d2 * q2;  // q^2 / ups^2
+            lp += v ? -0.5 * qq : 0.0;  // q ~ normal(0, ups)
+            sa0 += v ? q0 : 0.0;
+            sa1 += v ? q1 : 0.0;
+            sa2 += v ? q2 : 0.0;
             w0[j] = v ? d0 * a0[j] * iu2 : 0.0;
             w1[j] = v ? d1 * a1[j] * iu2 : 0.0;
             w2[j] = v ? d2 * a2[j] * iu2 : 0.0;
             // dups_i = 0.5 - 0.25 (ups_i + ups_{i+2}) / ups_{i+1}  (Series_modelcode.txt:51-53); window index j + 2 + e
-            double gu = q2 * iu2 * iuk - iuk;
-            if (k + 2 < K) {
+            double gu = qq * iuk - iuk;
+            {
               const double e = 0.5 - 0.25 * (upk + upw[j + 4]) * iuw[j + 3];
-              gu += e * 0.25 * iuw[j + 3];
-              lp += -0.5 * e * e;
+              const bool c = k + 2 < K;
+              gu += c ? e * 0.25 * iuw[j + 3] : 0.0;
+              lp += c ? -0.5 * e * e : 0.0;
             }
-            if (k >= 1 && k + 1 < K) {
+            {
               const double sum = upw[j + 1] + upw[j + 3];
               const double e = 0.5 - 0.25 * sum * iuk;
-              gu -= e * 0.25 * sum * iu2;
+              gu -= (k >= 1 && k + 1 < K) ? e * 0.25 * sum * iu2 : 0.0;
             }
-            if (k >= 2 && v) {
+            {
               const double e = 0.5 - 0.25 * (upw[j] + upk) * iuw[j + 1];
-              gu += e * 0.25 * iuw[j + 1];
+              gu += (k >= 2 && v) ? e * 0.25 * iuw[j + 1] : 0.0;
             }
             gu4[j] = gu * upk - (m.ups_alpha + 1.0) + m.ups_beta * 0.15 * iuk + jac;
           }
-          st2(sW + kq, w0[0], w0[1]);  // zeros past K keep the right margin zero
-          st2(sW + kq + 2, w0[2], w0[3]);
-          st2(sW + m.ws + kq, w1[0], w1[1]);
-          st2(sW + m.ws + kq + 2, w1[2], w1[3]);
-          st2(sW + 2 * m.ws + kq, w2[0], w2[1]);
-          st2(sW + 2 * m.ws + kq + 2, w2[2], w2[3]);
+          // margins of the three scratch vectors (the previous evaluation's Z / G row was here)
+#pragma unroll
+          for (int q = 0; q < 3; ++q) {
+            if (lane < m.wm) sW[q * m.ws - m.wm + lane] = 0.0;
+            for (int k = Dd.kpad4 + lane; k < m.ws - m.wm; k += 32) sW[q * m.ws + k] = 0.0;
+          }
+          if (kq < K) {
+            st2(sW + kq, w0[0], w0[1]);  // zeros past K keep the right margin zero
+            st2(sW + kq + 2, w0[2], w0[3]);
+            st2(sW + m.ws + kq, w1[0], w1[1]);
+            st2(sW + m.ws + kq + 2, w1[2], w1[3]);
+            st2(sW + 2 * m.ws + kq, w2[0], w2[1]);
+            st2(sW + 2 * m.ws + kq + 2, w2[2], w2[3]);
+          }
         }
         __syncwarp();  // every lane has its ups / 1/ups windows: the 1/ups row now stages d lp / d u_ups
         if (kq < K) {
           st2(sIu + kq, gu4[0], gu4[1]);
           st2(sIu + kq + 2, gu4[2], gu4[3]);
         }
-        // 1c. prior part of d lp / d x:  - sum_j L_j^T W_j  (kept in registers until phase 5)
+        // 1c. prior part of d lp / d x:  - sum_j L_j^T W_j  (kept in registers until phase 5); one accumulator set per
+        // derivative order: twelve independent chains
         {
-          double acc[4] = {0, 0, 0, 0};
-          if (kq < K) {
+          double acc[3][4];
 #pragma unroll
-            for (int q = 0; q < 3; ++q) {
-              double ww[16];  // W_q[kq - 6 .. kq + 9]
+          for (int q = 0; q < 3; ++q) {
+            double ww[16];  // W_q[kq - 6 .. kq + 9]
 #pragma unroll
-              for (int i = 0; i < 8; ++i) ld2(sW + q * m.ws + kq - FBW + 2 * i, ww[2 * i], ww[2 * i + 1]);
+            for (int i = 0; i < 8; ++i) ld2(sW + q * m.ws + kq - FBW + 2 * i, ww[2 * i], ww[2 * i + 1]);
 #pragma unroll
-              for (int t = 0; t < 2 * FBW + 1; ++t) {  // row n = k + d, column k -> tap_q[-d]
+            for (int j = 0; j < 4; ++j) acc[q][j] = 0.0;
 #pragma unroll
-                for (int j = 0; j < 4; ++j) acc[j] = fma(Dd.tapc[q][2 * FBW - t], ww[j + t], acc[j]);
-              }
+            for (int t = 0; t < 2 * FBW + 1; ++t) {  // row n = k + d, column k -> tap_q[-d]
+#pragma unroll
+              for (int j = 0; j < 4; ++j) acc[q][j] = fma(Dd.tapc[q][2 * FBW - t], ww[j + t], acc[q][j]);
             }
           }
 #pragma unroll
-          for (int j = 0; j < 4; ++j) gpr[dd][j] = -acc[j];
+          for (int j = 0; j < 4; ++j) gpr[dd][j] = -(acc[0][j] + acc[1][j] + acc[2][j]);
         }
         __syncwarp();
 #pragma unroll
@@ -474,15 +568,23 @@ __device__ inline double engine_eval(const BdrtModel& m, double* sm, bool active
           const int k = lane + 32 * j;
           if (k < K) grad[Dd.off_ups + k] = sIu[k];
         }
-        sa0 = warp_sum(sa0);
-        sa1 = warp_sum(sa1);
-        sa2 = warp_sum(sa2);
-        if (lane == 0) {
+        red[3 * dd] = sa0;
+        red[3 * dd + 1] = sa1;
+        red[3 * dd + 2] = sa2;
+      }
+      if (ND > 1) red[3 * ND] = xsum;
+      // one batched reduction: value i ends up in the lanes with lane >> LSH == i; its first lane writes the gradient
+      constexpr int LSH = ND == 1 ? 3 : (ND == 2 ? 2 : 1);
+      const double tot = warp_sum_multi<NRED>(red, lane);
+      if (ND > 1) xsum = __shfl_sync(0xffffffffu, tot, (3 * ND) << LSH);
+      {
+        const int i = lane >> LSH;  // i = 3 dd + j
+        if (i < 3 * ND && (lane & ((1 << LSH) - 1)) == 0) {
+          const int dd = i / 3, j = i - 3 * dd;
+          const double dj = sTh[6 + i], idj = bdrt_rcp(dj);
           // d_j ~ inv_gamma(5, 5): -6 log d - 5/d
-          lp += -6.0 * (u[Dd.off_d] + u[Dd.off_d + 1] + u[Dd.off_d + 2]) - 5.0 / d0 - 5.0 / d1 - 5.0 / d2;
-          grad[Dd.off_d] = -0.5 * sa0 * d0 - 6.0 + 5.0 / d0 + jac;
-          grad[Dd.off_d + 1] = -0.5 * sa1 * d1 - 6.0 + 5.0 / d1 + jac;
-          grad[Dd.off_d + 2] = -0.5 * sa2 * d2 - 6.0 + 5.0 / d2 + jac;
+          lp += -6.0 * u[m.d[dd].off_d + j] - 5.0 * idj;
+          grad[m.d[dd].off_d + j] = -0.5 * tot * dj - 6.0 + 5.0 * idj + jac;
         }
       }
     } else {
@@ -519,6 +621,11 @@ __device__ inline double engine_eval(const BdrtModel& m, double* sm, bool active
       const double* sTap = sm + Dd.oTap + MAXBW;  // tap_j[d] at sTap[j * LBW + d]
       const double d0 = sTh[6 + 3 * dd], d1 = sTh[7 + 3 * dd], d2 = sTh[8 + 3 * dd];
       double sa0 = 0, sa1 = 0, sa2 = 0;
+      // margins of the three scratch vectors (the previous evaluation's Z / G row was here)
+      for (int q = 0; q < 3; ++q) {
+        for (int k = lane; k < m.wm; k += 32) sW[q * m.ws - m.wm + k] = 0.0;
+        for (int k = K + lane; k < m.ws - m.wm; k += 32) sW[q * m.ws + k] = 0.0;
+      }
       for (int kb = 0; kb < K; kb += 128) {
         double a0[4] = {0, 0, 0, 0}, a1[4] = {0, 0, 0, 0}, a2[4] = {0, 0, 0, 0};
         if (Dd.toepL) {
@@ -644,7 +751,7 @@ __device__ inline double engine_eval(const BdrtModel& m, double* sm, bool active
       lp += -0.5 * ss;
     }
     if (ND > 1) {
-      xsum = warp_sum(xsum);
+      if (!FAST) xsum = warp_sum(xsum);  // (the register-tiled path has it already: batched reduction above)
       // x_sum = x_sum_raw * x_sum_invscale ~ std_normal(); real<lower=0> x_sum_raw is validity-checked by Stan (:56-57)
       if (lane == 0) lp += (xsum < 0.0) ? -INFINITY : -0.5 * (xsum * m.x_sum_invscale) * (xsum * m.x_sum_invscale);
     }
@@ -744,13 +851,13 @@ __device__ inline double engine_eval(const BdrtModel& m, double* sm, bool active
 #pragma unroll 5
         for (int kk = 0; kk < Db.kpad4; kk += 4) dmma(c10, c11, a1p[kk], b1p[kk]);
       }
-      double* z0 = sm + m.oZG + da * NSLOT * m.ldzg;
-      z0[(2 * t) * m.ldzg + mt * 8 + g] = c00;
-      z0[(2 * t + 1) * m.ldzg + mt * 8 + g] = c01;
+      double* z0 = sm + m.oSt + da * m.sd;  // column (slot) 2 t, 2 t + 1 -> that slot's Z / G row
+      z0[(2 * t) * m.st + mt * 8 + g] = c00;
+      z0[(2 * t + 1) * m.st + mt * 8 + g] = c01;
       if (two) {
-        double* z1 = sm + m.oZG + db * NSLOT * m.ldzg;
-        z1[(2 * t) * m.ldzg + mt2 * 8 + g] = c10;
-        z1[(2 * t + 1) * m.ldzg + mt2 * 8 + g] = c11;
+        double* z1 = sm + m.oSt + db * m.sd;
+        z1[(2 * t) * m.st + mt2 * 8 + g] = c10;
+        z1[(2 * t + 1) * m.st + mt2 * 8 + g] = c11;
       }
     }
   }
@@ -766,6 +873,87 @@ __device__ inline double engine_eval(const BdrtModel& m, double* sm, bool active
     const double base = m.sigma_min2 + sr * sr;
     const double ap2 = ap * ap, are2 = are * are, aim2 = aim * aim;
     double Sv = 0, Swv = 0, Sg = 0, Sgz = 0, SGre = 0, SGim = 0;
+    if (FAST) {
+      // Branch-free: three frequencies per lane and pass on clamped indices, results masked by selects / predicated
+      // stores, so the three reciprocal chains are interleaved; the log-determinant term takes ONE logarithm per lane
+      // and pass, of the product of the (up to six) variances -- each is >= sigma_min^2, far from under/overflow.
+      for (int nb = 0; nb < Nf; nb += 96) {
+        double prodS = 1.0;
+#pragma unroll
+        for (int jn = 0; jn < 3; ++jn) {
+          const int n = nb + lane + 32 * jn;
+          const bool vld = n < Nf;
+          const int nc = vld ? n : Nf - 1;
+          const double om = sOm[nc];
+          double zre = Rinf, zim = induc * om;
+          double Yr[ND], Yi[ND], iM[ND];
+#pragma unroll
+          for (int dd = 0; dd < ND; ++dd) {
+            const double* sZd = rowZ(dd);
+            if (is_par(dd)) {
+              // Z_p = 1 / (Y' + i Y'')  (Parallel_modelcode.txt:46-50, Series-Parallel :63-66)
+              Yr[dd] = sZd[nc];
+              Yi[dd] = sZd[nfp + nc];
+              iM[dd] = bdrt_rcp(Yr[dd] * Yr[dd] + Yi[dd] * Yi[dd]);
+              zre += Yr[dd] * iM[dd];
+              zim -= Yi[dd] * iM[dd];
+            } else {
+              zre += sZd[nc];
+              zim += sZd[nfp + nc];
+            }
+          }
+          double common = are2 * zre * zre + aim2 * zim * zim;
+          double so_raw = 0, so_scale = 0, so = 0;
+          if (outl) {
+            so_raw = sSo[nc];
+            so_scale = sSo[Nf + nc];
+            so = 0.05 * so_raw * so_scale;  // Series_outliers_modelcode.txt:45
+            common += so * so;
+            // sigma_out_raw ~ exponential(lambda); sigma_out_scale ~ inv_gamma(alpha, beta)
+            const double t_ = -m.so_lambda * so_raw - (m.so_alpha + 1.0) * u[m.off_so + Nf + nc] -
+                              m.so_beta * bdrt_rcp(so_scale);
+            lp += vld ? t_ : 0.0;
+          }
+          const double s_re = base + ap2 * zre * zre + common, s_im = base + ap2 * zim * zim + common;
+          const double i_re = bdrt_rcp(s_re), i_im = bdrt_rcp(s_im);
+          const double r_re = Zs[nc] - zre, r_im = Zs[Nf + nc] - zim;
+          const double e_re = r_re * r_re * i_re, e_im = r_im * r_im * i_im;
+          lp += vld ? -0.5 * (e_re + e_im) : 0.0;
+          prodS *= vld ? s_re * s_im : 1.0;
+          const double g_re = 0.5 * (e_re - 1.0) * i_re, g_im = 0.5 * (e_im - 1.0) * i_im;
+          const double G = g_re + g_im;
+          const double v_re = r_re * i_re + 2.0 * zre * (ap2 * g_re + are2 * G);
+          const double v_im = r_im * i_im + 2.0 * zim * (ap2 * g_im + aim2 * G);
+#pragma unroll
+          for (int dd = 0; dd < ND; ++dd) {
+            double* sVd = rowX(dd);
+            double o_re = v_re, o_im = v_im;
+            if (is_par(dd)) {  // d lp / d Y
+              const double i2 = iM[dd] * iM[dd];
+              const double c1 = (Yi[dd] * Yi[dd] - Yr[dd] * Yr[dd]) * i2, c2 = 2.0 * Yr[dd] * Yi[dd] * i2;
+              o_re = v_re * c1 + v_im * c2;
+              o_im = -v_re * c2 + v_im * c1;
+            }
+            if (vld) {
+              sVd[n] = o_re;
+              sVd[m.vim + n] = o_im;
+            }
+          }
+          Sv += vld ? v_re : 0.0;
+          Swv += vld ? om * v_im : 0.0;
+          Sg += vld ? G : 0.0;
+          Sgz += vld ? g_re * zre * zre + g_im * zim * zim : 0.0;
+          SGre += vld ? G * zre * zre : 0.0;
+          SGim += vld ? G * zim * zim : 0.0;
+          if (outl && vld) {
+            const double dso = 2.0 * so * G * so;  // (d lp/d sigma_out) * sigma_out ; sigma_out = .05 raw scale
+            grad[m.off_so + n] = dso - m.so_lambda * so_raw + jac;
+            grad[m.off_so + Nf + n] = dso - (m.so_alpha + 1.0) + m.so_beta * bdrt_rcp(so_scale) + jac;
+          }
+        }
+        lp -= 0.5 * log(prodS);
+      }
+    } else
     // three independent frequencies per lane and pass (instruction-level parallelism: the body is a long chain of
     // reciprocals / a logarithm)
     for (int nb = 0; nb < Nf; nb += 96) {
@@ -846,6 +1034,19 @@ __device__ inline double engine_eval(const BdrtModel& m, double* sm, bool active
         sVd[m.vim + n] = 0.0;
       }
     }
+    if (FAST) {
+      // batched reduction of the six scalar sums and of lp (complete here: phases 4 and 5 add nothing to it); value i
+      // ends up in lanes 4 i .. 4 i + 3, lane 4 i writes its gradient entry
+      double red[8] = {Sv, Swv, Sg, Sgz, SGre, SGim, lp, 0.0};
+      const double tot = warp_sum_multi<8>(red, lane);
+      lp = __shfl_sync(0xffffffffu, tot, 24);
+      if ((lane & 3) == 0 && lane < 24) {
+        const int i = lane >> 2;
+        const double sc = i == 0 ? 100.0 : (i == 1 ? m.induc_scale : 0.1 * (i == 2 ? sr : (i == 3 ? ap : (i == 4 ? are : aim))));
+        const double raw = sTh[i];
+        grad[i < 2 ? i : m.off_err + i - 2] = (sc * tot - raw) * raw + jac;
+      }
+    } else {
     Sv = warp_sum(Sv);
     Swv = warp_sum(Swv);
     Sg = warp_sum(Sg);
@@ -859,6 +1060,7 @@ __device__ inline double engine_eval(const BdrtModel& m, double* sm, bool active
       grad[m.off_err + 1] = (0.1 * ap * Sgz - ap_raw) * ap_raw + jac;
       grad[m.off_err + 2] = (0.1 * are * SGre - are_raw) * are_raw + jac;
       grad[m.off_err + 3] = (0.1 * aim * SGim - aim_raw) * aim_raw + jac;
+    }
     }
   } else {
 #pragma unroll
@@ -947,13 +1149,13 @@ __device__ inline double engine_eval(const BdrtModel& m, double* sm, bool active
           }
         }
       }
-      double* z0 = sm + m.oZG + da * NSLOT * m.ldzg;
-      z0[(2 * t) * m.ldzg + mt * 8 + g] = c00;
-      z0[(2 * t + 1) * m.ldzg + mt * 8 + g] = c01;
+      double* z0 = sm + m.oSt + da * m.sd;  // column (slot) 2 t, 2 t + 1 -> that slot's Z / G row
+      z0[(2 * t) * m.st + mt * 8 + g] = c00;
+      z0[(2 * t + 1) * m.st + mt * 8 + g] = c01;
       if (two) {
-        double* z1 = sm + m.oZG + db * NSLOT * m.ldzg;
-        z1[(2 * t) * m.ldzg + mt2 * 8 + g] = c10;
-        z1[(2 * t + 1) * m.ldzg + mt2 * 8 + g] = c11;
+        double* z1 = sm + m.oSt + db * m.sd;
+        z1[(2 * t) * m.st + mt2 * 8 + g] = c10;
+        z1[(2 * t + 1) * m.st + mt2 * 8 + g] = c11;
       }
     }
   }
@@ -998,7 +1200,7 @@ __device__ inline double engine_eval(const BdrtModel& m, double* sm, bool active
         grad[Dd.off_x + k] = gx;
       }
     }
-    lp = warp_sum(lp);
+    if (!FAST) lp = warp_sum(lp);  // (register-tiled path: reduced with the sums of phase 3)
     __syncwarp();
   }
   PCLK(5);

@@ -36,6 +36,9 @@ def clocks(label, n_warp_slots, dt):
     print(f'{label}: {n} evals in {dt*1e3:.1f} ms; clocks/eval in engine {tot:.0f} = ' +
           ' | '.join(f'p{i+1} {p:.0f} ({100*p/tot:.0f}%)' for i, p in enumerate(ph)) +
           f' ; wall clocks per eval per warp {dt*1.965e9*n_warp_slots/max(n,1):.0f}')
+    if any(out[i] for i in range(6, 12)):
+        names = {6: 'linesearch+step', 7: 'engine', 8: 'grad post-pass', 9: 'shift+sweepA', 10: 'recursion', 11: 'sweepB'}
+        print('   solver clocks/eval: ' + ' | '.join(f'{names[i]} {out[i]/max(n,1):.0f}' for i in range(6, 12)))
 
 
 for mode in ('optimize', 'sample'):
