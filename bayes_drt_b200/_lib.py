@@ -16,7 +16,7 @@ SYMBOLS = [
     'bdrt_version', 'bdrt_ctx_create', 'bdrt_ctx_destroy', 'bdrt_last_error', 'bdrt_launch_count',
     'bdrt_build_A', 'bdrt_build_L', 'bdrt_build_M', 'bdrt_num_params', 'bdrt_num_outputs', 'bdrt_logpost_grad',
     'bdrt_lbfgs_default_opts', 'bdrt_map_lbfgs', 'bdrt_newton_default_opts', 'bdrt_map_newton',
-    'bdrt_nuts_default_opts', 'bdrt_nuts', 'bdrt_constrain', 'bdrt_summarize', 'bdrt_qp_bound', 'bdrt_ridge_default_opts',
+    'bdrt_nuts_default_opts', 'bdrt_nuts', 'bdrt_constrain', 'bdrt_summarize', 'bdrt_diagnostics', 'bdrt_qp_bound', 'bdrt_ridge_default_opts',
     'bdrt_ridge_fit', 'bdrt_peak_fp64',
 ]
 
@@ -62,7 +62,7 @@ class RidgeOpts(C.Structure):
     _fields_ = [('penalty', C.c_int), ('nonneg', C.c_int), ('max_iter', C.c_int), ('xtol', C.c_double),
                 ('hl_beta', C.c_double), ('lambda_0', C.c_double), ('reg_ord', C.c_double * 3),
                 ('L1_penalty', C.c_double), ('epsilon', C.c_double), ('fit_inductance', C.c_int),
-                ('hl_fbeta', C.c_double)]
+                ('hl_fbeta', C.c_double), ('stop_rule', C.c_int)]
 
 
 class BdrtError(RuntimeError):

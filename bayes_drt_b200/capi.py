@@ -156,7 +156,7 @@ class SeriesProblem:
                                                    ptr(iters), ptr(nev), ptr(status)))
         return dict(u=u, lp=lp, iters=iters, n_eval=nev, status=status)
 
-    def map_newton(self, u0, max_iter=40, gtol=1e-9, fd_step=1e-6):
+    def map_newton(self, u0, max_iter=200, gtol=1e-9, fd_step=1e-6):
         u = f64(u0, self.ctx.device).clone()
         o = NewtonOpts()
         self.ctx.lib.bdrt_newton_default_opts(C.byref(o))
@@ -236,6 +236,22 @@ def summarize(draws, percentiles=(), want_mean=True, device=None):
     return mean, quant
 
 
+SUMMARIZE_MAX_DRAWS = 16384  # merged draws per parameter the shared-memory sort of bdrt_summarize holds on B200
+
+
+def diagnostics(draws, chains, device=None):
+    """Split R-hat and rank-normalised bulk ESS of draws [G, chains * n, P] (chain-major) -> (rhat [G, P], ess [G, P])."""
+    ctx = context(device)
+    draws = f64(draws, ctx.device)
+    if draws.dim() != 3 or draws.shape[1] % chains:
+        raise ValueError('draws must be [G, chains * n, P]')
+    G, S, P = draws.shape
+    rhat = torch.empty((G, P), dtype=torch.float64, device=ctx.device)
+    ess = torch.empty((G, P), dtype=torch.float64, device=ctx.device)
+    ctx.check(ctx.lib.bdrt_diagnostics(ctx._h, ptr(draws), G, int(chains), S // chains, P, ptr(rhat), ptr(ess)))
+    return rhat, ess
+
+
 def qp_bound(P, q, lb, device=None):
     ctx = context(device)
     P, q, lb = f64(P, ctx.device), f64(q, ctx.device), f64(lb, ctx.device)
@@ -249,7 +265,9 @@ def qp_bound(P, q, lb, device=None):
 
 def ridge_fit(WA_re, WA_im, WZ_re, WZ_im, Pen, Lmat, penalty='discrete', nonneg=True, max_iter=20, xtol=1e-3,
               hl_beta=2.5, lambda_0=1e-2, reg_ord=(0.0, 0.0, 1.0), L1_penalty=0.0, epsilon=1.0, fit_inductance=True,
-              hl_fbeta=None, device=None):
+              hl_fbeta=None, stop_rule=1, device=None):
+    """stop_rule: see bdrt_ridge_opts in include/bdrt.h (0 numpy 0/0 = NaN semantics, 1 unchanged-on-the-bound counts as
+    converged).  Returns coef, lam, iters (hyper-iterations), converged, n_factor (Cholesky factorisations)."""
     ctx = context(device)
     dev = ctx.device
     WA_re, WA_im = f64(WA_re, dev), f64(WA_im, dev)
@@ -266,14 +284,16 @@ def ridge_fit(WA_re, WA_im, WZ_re, WZ_im, Pen, Lmat, penalty='discrete', nonneg=
         o.reg_ord[i] = float(reg_ord[i])
     o.L1_penalty, o.epsilon, o.fit_inductance = float(L1_penalty), float(epsilon), int(fit_inductance)
     o.hl_fbeta = 0.0 if hl_fbeta is None else float(hl_fbeta)
+    o.stop_rule = int(stop_rule)
     coef = torch.empty((B, n), dtype=torch.float64, device=dev)
     lam = torch.empty((B, 3, n), dtype=torch.float64, device=dev)
     iters = torch.empty(B, dtype=torch.int32, device=dev)
     conv = torch.empty(B, dtype=torch.int32, device=dev)
+    nfac = torch.empty(B, dtype=torch.int32, device=dev)
     ctx.check(ctx.lib.bdrt_ridge_fit(ctx._h, C.byref(o), ptr(WA_re), ptr(WA_im), int(WA_re.dim() == 3), ptr(WZ_re),
                                      ptr(WZ_im), ptr(Pen), ptr(Lm), B, Nf, n - 2, ptr(coef), ptr(lam), ptr(iters),
-                                     ptr(conv)))
-    return dict(coef=coef, lam=lam, iters=iters, converged=conv)
+                                     ptr(conv), ptr(nfac)))
+    return dict(coef=coef, lam=lam, iters=iters, converged=conv, n_factor=nfac)
 
 
 def peak_fp64(device=None):

@@ -263,8 +263,12 @@ nuts_kernel(BdrtModel m, bdrt_nuts_opts o, const double* __restrict__ U0, double
                 d_s = fma(mi * cp[i], rho_s, d_s);
                 d_e = fma(mi * v[V_ZP][i], rho_s, d_e);
               }
-              d_s = warp_sum(d_s);
-              d_e = warp_sum(d_e);
+              {  // both dot products in one butterfly: value 0 in lanes 0..15, value 1 in lanes 16..31
+                double two[2] = {d_s, d_e};
+                const double tot = warp_sum_multi<2>(two, lane);
+                d_s = __shfl_sync(0xffffffffu, tot, 0);
+                d_e = __shfl_sync(0xffffffffu, tot, 16);
+              }
               if (!(d_s > 0.0 && d_e > 0.0)) { valid = false; break; }
             }
             if (!valid) break;
@@ -289,8 +293,12 @@ nuts_kernel(BdrtModel m, bdrt_nuts_opts o, const double* __restrict__ U0, double
           d_z = fma(mi * v[V_ZP][i], r, d_z);
           d_o = fma(mi * v[V_OP][i], r, d_o);
         }
-        d_z = warp_sum(d_z);
-        d_o = warp_sum(d_o);
+        {
+          double two[2] = {d_z, d_o};
+          const double tot = warp_sum_multi<2>(two, lane);
+          d_z = __shfl_sync(0xffffffffu, tot, 0);
+          d_o = __shfl_sync(0xffffffffu, tot, 16);
+        }
         __syncwarp();
         if (!(d_z > 0.0 && d_o > 0.0)) break;
       }

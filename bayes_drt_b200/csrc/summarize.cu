@@ -179,3 +179,130 @@ extern "C" int bdrt_summarize(bdrt_ctx* ctx, const double* draws, int G, int S, 
   BDRT_CUDA(ctx, cudaGetLastError());
   return BDRT_OK;
 }
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Sampler diagnostics on the device: split R-hat and rank-normalised split-chain bulk ESS (Vehtari et al. 2021) of every
+// column of draws [G, chains * n, P] (chain-major along the draw axis) -- what pystan prints after
+// StanModel.sampling (bayes_drt/inversion.py:1218-1221) and what the benchmark's ESS/s metric is made of.
+// One warp per (spectrum, parameter) column: the column and its normal scores live in shared memory; ranks by counting
+// (average rank for ties, like scipy.stats.rankdata), autocovariances lag-parallel over the lanes, Geyer's initial
+// monotone sequence by lane 0.  Same estimator as oracle/nuts.py: ess_bulk (the tests compare the two).
+// ---------------------------------------------------------------------------------------------------------------------
+#define DIAG_WARPS 4
+
+__global__ void __launch_bounds__(DIAG_WARPS * 32)
+diag_kernel(const double* __restrict__ draws, int G, int chains, int n, int P, double* __restrict__ rhat,
+            double* __restrict__ ess) {
+  extern __shared__ __align__(16) double sm[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int h = n / 2, m = 2 * chains, S = m * h;  // split chains; an odd n drops its last draw
+  double* x = sm + (size_t)warp * 2 * S;  // values, later rho[t]
+  double* z = x + S;                       // normal scores, centred per split chain
+  const long long ncol = (long long)G * P;
+  for (long long col = (long long)blockIdx.x * DIAG_WARPS + warp; col < ncol; col += (long long)gridDim.x * DIAG_WARPS) {
+    const int g = (int)(col / P), p = (int)(col - (long long)g * P);
+    const double* base = draws + (long long)g * chains * n * P + p;
+    __syncwarp();
+    for (int s = lane; s < S; s += 32) {  // split chain k = s / h: chain k / 2, half k & 1
+      const int k = s / h, i = s - k * h;
+      x[s] = base[(long long)((k >> 1) * n + (k & 1) * h + i) * P];
+    }
+    __syncwarp();
+    // ---- classic split R-hat on the raw values
+    double sumv = 0.0, summ = 0.0, summ2 = 0.0;
+    for (int k = 0; k < m; ++k) {
+      double a = 0.0;
+      for (int i = lane; i < h; i += 32) a += x[k * h + i];
+      const double mu = warp_sum(a) / h;
+      double v = 0.0;
+      for (int i = lane; i < h; i += 32) { const double d = x[k * h + i] - mu; v = fma(d, d, v); }
+      sumv += warp_sum(v) / (h - 1.0);
+      summ += mu;
+      summ2 = fma(mu, mu, summ2);
+    }
+    {
+      const double W = sumv / m, mm = summ / m;
+      const double Bn = (summ2 - m * mm * mm) / (m - 1.0);  // variance of the split-chain means
+      if (lane == 0 && rhat) rhat[col] = sqrt(((h - 1.0) / h * W + Bn) / W);
+    }
+    // ---- rank-normalise
+    for (int s = lane; s < S; s += 32) {
+      const double v = x[s];
+      int less = 0, eq = 0;
+      for (int j = 0; j < S; ++j) {
+        const double o = x[j];
+        less += o < v;
+        eq += o == v;
+      }
+      const double r = less + 0.5 * (eq + 1);
+      z[s] = normcdfinv((r - 0.375) / (S + 0.25));
+    }
+    __syncwarp();
+    sumv = 0.0; summ = 0.0; summ2 = 0.0;
+    for (int k = 0; k < m; ++k) {  // centre every split chain
+      double a = 0.0;
+      for (int i = lane; i < h; i += 32) a += z[k * h + i];
+      const double mu = warp_sum(a) / h;
+      double v = 0.0;
+      for (int i = lane; i < h; i += 32) {
+        const double d = z[k * h + i] - mu;
+        z[k * h + i] = d;
+        v = fma(d, d, v);
+      }
+      sumv += warp_sum(v) / (h - 1.0);  // acov_k[0] h / (h - 1)
+      summ += mu;
+      summ2 = fma(mu, mu, summ2);
+    }
+    __syncwarp();
+    const double Wz = sumv / m, mz = summ / m;
+    const double var_plus = Wz * (h - 1.0) / h + (summ2 - m * mz * mz) / (m - 1.0);
+    // rho_t = 1 - (W - mean_k acov_k[t]) / var_plus, lag-parallel
+    for (int t = lane; t < h; t += 32) {
+      double a = 0.0;
+      for (int k = 0; k < m; ++k) {
+        const double* zk = z + k * h;
+        for (int i = 0; i + t < h; ++i) a = fma(zk[i], zk[i + t], a);
+      }
+      x[t] = t == 0 ? 1.0 : 1.0 - (Wz - a / (h * (double)m)) / var_plus;
+    }
+    __syncwarp();
+    if (lane == 0 && ess) {
+      double tau = -1.0, prev = INFINITY;
+      for (int t = 0; t + 1 < h; t += 2) {
+        double pair = x[t] + x[t + 1];
+        if (pair < 0.0) break;
+        pair = fmin(pair, prev);
+        prev = pair;
+        tau += 2.0 * pair;
+      }
+      tau = fmax(tau, 1.0 / log10((double)S));
+      ess[col] = S / tau;
+    }
+  }
+}
+
+// draws [G, chains * n, P] (device, draw index = chain * n + i); rhat [G, P], ess_bulk [G, P] (device; either may be
+// NULL).  n >= 4, chains >= 1.
+extern "C" int bdrt_diagnostics(bdrt_ctx* ctx, const double* draws, int G, int chains, int n, int P, double* rhat,
+                                double* ess_bulk) {
+  if (!ctx) return BDRT_E_NULL;
+  if (!draws) BDRT_FAIL(ctx, BDRT_E_NULL, "bdrt_diagnostics: null pointer");
+  if (G < 0 || chains < 1 || n < 4 || P < 1) BDRT_FAIL(ctx, BDRT_E_SIZE, "bdrt_diagnostics: bad sizes");
+  if (G == 0 || (!rhat && !ess_bulk)) return BDRT_OK;
+  const size_t S = (size_t)2 * chains * (n / 2);
+  const size_t smem = DIAG_WARPS * 2 * S * sizeof(double);
+  if (smem > (size_t)ctx->smem_optin)
+    BDRT_FAIL(ctx, BDRT_E_SMEM, "bdrt_diagnostics: %zu draws per parameter exceed the shared-memory buffers (max %zu)", S,
+              (size_t)ctx->smem_optin / (DIAG_WARPS * 2 * sizeof(double)));
+  BDRT_CUDA(ctx, cudaFuncSetAttribute(diag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const long long ncol = (long long)G * P;
+  int per_sm = (int)((size_t)ctx->smem_per_sm / (smem + 1024));
+  if (per_sm < 1) per_sm = 1;
+  if (per_sm > 16) per_sm = 16;
+  long long grid = (long long)ctx->sm_count * per_sm;
+  if (grid > (ncol + DIAG_WARPS - 1) / DIAG_WARPS) grid = (ncol + DIAG_WARPS - 1) / DIAG_WARPS;
+  diag_kernel<<<(int)grid, DIAG_WARPS * 32, smem, ctx->stream>>>(draws, G, chains, n, P, rhat, ess_bulk);
+  ctx->launches++;
+  BDRT_CUDA(ctx, cudaGetLastError());
+  return BDRT_OK;
+}

@@ -260,22 +260,7 @@ class Inverter:
             raise NotImplementedError('model_str / add_stan_data (Stan escape hatches) are not available')
         if mode not in ('optimize', 'sample'):
             raise ValueError(f"Invalid mode {mode}. Options are 'optimize', 'sample'")
-        # model selection (Inverter._get_stan_model, inversion.py:1576-1610)
-        ser = [k for k, v in self.distributions.items() if v['dist_type'] == 'series']
-        par = [k for k, v in self.distributions.items() if v['dist_type'] == 'parallel']
-        if len(ser) == 1 and len(par) == 0:
-            model_type = 'Series'
-        elif len(ser) == 0 and len(par) == 1:
-            model_type = 'Parallel'
-        elif len(ser) == 1 and len(par) == 1:
-            model_type = 'Series-Parallel'
-        elif len(ser) == 1 and len(par) == 2:
-            model_type = 'Series-2Parallel'
-            par = sorted(par)  # the reference orders the parallel distributions by name (inversion.py:1963-1968)
-            self.distributions[par[0]]['order'], self.distributions[par[1]]['order'] = 1, 2
-        else:
-            raise NotImplementedError("the 'MultiDist' model (arbitrary numbers of distributions) is a placeholder in the "
-                                      "reference (its Stan file is not shipped) and is not implemented")
+        model_type, ser, par = self._model_type()
         if model_type != 'Series' and outliers:
             raise NotImplementedError("Parallel_outliers / Series-Parallel*_outliers are dimensionally inconsistent as "
                                       "shipped by the reference (N override vs matrix[N,K] A) and are not implemented")
@@ -289,9 +274,6 @@ class Inverter:
         freq, Zb = self._to_batch(frequencies, Z)
         single = self._single
         B = Zb.shape[0]
-        if freq.dim() == 2 and (init_from_ridge or outliers == 'auto'):
-            raise NotImplementedError("init_from_ridge / outliers='auto' need the ridge solver, which takes one "
-                                      "frequency grid per batch")
         ids = torch.arange(spectrum_offset, spectrum_offset + B, dtype=torch.int64, device=self.device)
         # ---- ridge initialisation and automatic outlier detection (inversion.py:1154-1187)
         ridge_init, flags, init_flags = None, None, None
@@ -324,7 +306,8 @@ class Inverter:
             if init is not None:
                 u_init = torch.as_tensor(init, dtype=torch.float64, device=self.device)
                 u_init = u_init.reshape(B, -1, u_init.shape[-1])[sel]
-            res = self._fit_core(freq, Zs[sel], ids[sel], model_type, name, par, mode, nonneg, fl, sigma_min,
+            fsel = freq if (ix is None or freq.dim() == 1) else freq[ix.cpu()]  # per-spectrum grids follow their rows
+            res = self._fit_core(fsel, Zs[sel], ids[sel], model_type, name, par, mode, nonneg, fl, sigma_min,
                                  inductance_scale, outlier_lambda, random_seed, max_iter, warmup, samples, chains,
                                  u_init, None if ridge_init is None else {k: v[sel] for k, v in ridge_init.items()},
                                  init_flags[sel] if (init_flags is not None and fl) else None, polish, keep_draws)
@@ -333,6 +316,9 @@ class Inverter:
                 self._outlier_model[:] = fl
             else:
                 self._outlier_model[ix] = fl
+        if freq.dim() == 2 and len(groups) > 1:  # the sub-batches left their own grids behind: back to the whole batch
+            for nm in self.distributions:
+                self._grid(freq, nm)
         self._merge_results(results, B, model_type, name, par, mode, sigma_min, keep_draws)
         self.stan_model_name = model_type + ('_pos' if nonneg and ser else '') + \
             ('_outliers' if bool(self._outlier_model.any()) else '') + '_StanModel.pkl'
@@ -347,10 +333,47 @@ class Inverter:
         return self
 
     # ------------------------------------------------------------------------------------------------------------
-    def _fit_core(self, freq, Zs, ids, model_type, name, par, mode, nonneg, outliers, sigma_min, inductance_scale,
-                  outlier_lambda, random_seed, max_iter, warmup, samples, chains, init, ridge_init, flags, polish,
-                  keep_draws):
-        """One Stan program on one (sub-)batch: build the problem, initialise, run the solver, read back."""
+    def _model_type(self):
+        """model selection (Inverter._get_stan_model, inversion.py:1576-1610) -> (model_type, series names, parallel names)"""
+        ser = [k for k, v in self.distributions.items() if v['dist_type'] == 'series']
+        par = [k for k, v in self.distributions.items() if v['dist_type'] == 'parallel']
+        if len(ser) == 1 and len(par) == 0:
+            return 'Series', ser, par
+        if len(ser) == 0 and len(par) == 1:
+            return 'Parallel', ser, par
+        if len(ser) == 1 and len(par) == 1:
+            return 'Series-Parallel', ser, par
+        if len(ser) == 1 and len(par) == 2:
+            par = sorted(par)  # the reference orders the parallel distributions by name (inversion.py:1963-1968)
+            self.distributions[par[0]]['order'], self.distributions[par[1]]['order'] = 1, 2
+            return 'Series-2Parallel', ser, par
+        raise NotImplementedError("the 'MultiDist' model (arbitrary numbers of distributions) is a placeholder in the "
+                                  "reference (its Stan file is not shipped) and is not implemented")
+
+    def prepare(self, frequencies, Z, mode='optimize', nonneg=False, outliers=False, scale_Z=True, sigma_min=0.002,
+                inductance_scale=1, outlier_lambda=None, random_seed=1234, chains=2, spectrum_offset=0):
+        """Everything ``fit`` does before it calls a solver, as a public hook (bench.py times the solver alone with it):
+        sorting, scaling, kernel / penalty matrices, the Stan data of the selected program, Stan-style random initial
+        points.  Returns (problem, u0): a ``capi.SeriesProblem`` (``map_lbfgs`` / ``map_newton`` / ``nuts`` /
+        ``logpost_grad`` / ``constrain``) and the initial points [B, D] ('optimize') or [B, chains, D] ('sample')."""
+        if mode not in ('optimize', 'sample'):
+            raise ValueError(f"Invalid mode {mode}. Options are 'optimize', 'sample'")
+        model_type, ser, par = self._model_type()
+        name = ser[0] if ser else par[0]
+        freq, Zb = self._to_batch(frequencies, Z)
+        self.f_train, self.Z_train = freq.numpy(), Zb
+        Zs = self._scale_Z(Zb, scale_Z, fit_type='map' if mode == 'optimize' else 'bayes')
+        B = Zs.shape[0]
+        ids = torch.arange(spectrum_offset, spectrum_offset + B, dtype=torch.int64, device=self.device)
+        prob = self._build_problem(freq, Zs, model_type, name, par, mode, nonneg, bool(outliers), sigma_min,
+                                   inductance_scale, outlier_lambda)
+        nch = 1 if mode == 'optimize' else chains
+        u0 = self._initial_points(prob, ids, nch, random_seed, 0)
+        return prob, (u0.reshape(B, prob.D) if mode == 'optimize' else u0)
+
+    def _build_problem(self, freq, Zs, model_type, name, par, mode, nonneg, outliers, sigma_min, inductance_scale,
+                       outlier_lambda):
+        """The Stan data of one program for one (sub-)batch (Inverter._prep_stan_data, inversion.py:1684-2122)."""
         tau, eps, m = self._grid(freq, name)
         c = _MODE[mode]
         Zst = torch.cat((Zs.real, Zs.imag), dim=1).contiguous()
@@ -358,57 +381,110 @@ class Inverter:
                       induc_scale=float(inductance_scale), device=self.device)
         if model_type in ('Series', 'Parallel'):  # same constants (inversion.py:1714-1754)
             L = torch.stack([c['l'][0] * m['L0'], c['l'][1] * m['L1'], c['l'][2] * m['L2']])
-            prob = capi.SeriesProblem(torch.cat((m['A_re'], m['A_im']), dim=-2), Zst, freq, L, outliers=bool(outliers),
+            return capi.SeriesProblem(torch.cat((m['A_re'], m['A_im']), dim=-2), Zst, freq, L, outliers=bool(outliers),
                                       parallel=model_type == 'Parallel',
                                       sigma_out_lambda=10.0 if outlier_lambda is None else float(outlier_lambda),
                                       sigma_out_alpha=c['sigma_out_alpha'], sigma_out_beta=1.0, **common)
-        else:
-            _, _, mp = self._grid(freq, par[0])
-            csp = _MODE_SP[mode]
-            Ls = torch.stack([csp['ls'][j] * m[f'L{j}'] for j in range(3)])
-            Lp = torch.stack([csp['lp'][j] * mp[f'L{j}'] for j in range(3)])
-            extra = {}
-            x_sum_invscale = csp['x_sum_invscale']
-            if model_type == 'Series-2Parallel':  # inversion.py:1961-2049
-                _, _, mp2 = self._grid(freq, par[1])
-                extra = dict(Ap2=torch.cat((mp2['A_re'], mp2['A_im']), dim=-2),
-                             Lp2=torch.stack([csp['lp'][j] * mp2[f'L{j}'] for j in range(3)]),
-                             xp2_scale=float(self.distributions[par[1]].get('x_scale', 1)))
-                x_sum_invscale = 0.1 if mode == 'sample' else 0.0
-            prob = capi.SeriesProblem(torch.cat((m['A_re'], m['A_im']), dim=-2), Zst, freq, Ls,
-                                      Ap=torch.cat((mp['A_re'], mp['A_im']), dim=-2), Lp=Lp, x_sum_invscale=x_sum_invscale,
-                                      xp_scale=float(self.distributions[par[0]].get('x_scale', 1)), **extra, **common)
+        _, _, mp = self._grid(freq, par[0])
+        csp = _MODE_SP[mode]
+        Ls = torch.stack([csp['ls'][j] * m[f'L{j}'] for j in range(3)])
+        Lp = torch.stack([csp['lp'][j] * mp[f'L{j}'] for j in range(3)])
+        extra = {}
+        x_sum_invscale = csp['x_sum_invscale']
+        if model_type == 'Series-2Parallel':  # inversion.py:1961-2049
+            _, _, mp2 = self._grid(freq, par[1])
+            extra = dict(Ap2=torch.cat((mp2['A_re'], mp2['A_im']), dim=-2),
+                         Lp2=torch.stack([csp['lp'][j] * mp2[f'L{j}'] for j in range(3)]),
+                         xp2_scale=float(self.distributions[par[1]].get('x_scale', 1)))
+            x_sum_invscale = 0.1 if mode == 'sample' else 0.0
+        return capi.SeriesProblem(torch.cat((m['A_re'], m['A_im']), dim=-2), Zst, freq, Ls,
+                                  Ap=torch.cat((mp['A_re'], mp['A_im']), dim=-2), Lp=Lp, x_sum_invscale=x_sum_invscale,
+                                  xp_scale=float(self.distributions[par[0]].get('x_scale', 1)), **extra, **common)
+
+    def _initial_points(self, prob, ids, nch, random_seed, attempt):
+        """Stan: init='random' -> U(-2, 2) per unconstrained coordinate; rows keyed by the global (spectrum, chain) index
+        (and by the attempt number when a point is redrawn), so a spectrum's start does not depend on the sharding."""
+        rows = (ids[:, None] * nch + torch.arange(nch, device=self.device)[None, :]).reshape(-1)
+        seed = int(random_seed) + 7919 * int(attempt)
+        return _hash_uniform(seed, 0, 0, prob.D, self.device, ids=rows).reshape(len(ids), nch, prob.D)
+
+    MAX_INIT_ATTEMPTS = 100  # Stan's own limit [Stan-upstream]
+
+    # ------------------------------------------------------------------------------------------------------------
+    def _fit_core(self, freq, Zs, ids, model_type, name, par, mode, nonneg, outliers, sigma_min, inductance_scale,
+                  outlier_lambda, random_seed, max_iter, warmup, samples, chains, init, ridge_init, flags, polish,
+                  keep_draws):
+        """One Stan program on one (sub-)batch: build the problem, initialise, run the solver, read back."""
+        prob = self._build_problem(freq, Zs, model_type, name, par, mode, nonneg, outliers, sigma_min,
+                                   inductance_scale, outlier_lambda)
         self._problem = prob
         B, D, K, Nf = prob.B, prob.D, prob.K, prob.Nf
         nch = 1 if mode == 'optimize' else chains
+        if mode == 'sample' and chains * samples > capi.SUMMARIZE_MAX_DRAWS:
+            raise ValueError(f'chains * samples = {chains * samples} exceeds the {capi.SUMMARIZE_MAX_DRAWS} merged draws '
+                             f'per spectrum that the on-device percentile kernel holds')
+
+        def ridge_overlay(u0):
+            # partial init from the ridge fit (inversion.py:1649-1677); Stan draws the remaining parameters randomly
+            if ridge_init is None:
+                return u0
+            x = ridge_init['x']
+            if nonneg:  # exact zeros of the active-set QP cannot be log-transformed: floor them (cvxopt's interior
+                x = torch.clamp(x, min=1e-8 * x.abs().max(dim=1, keepdim=True).values)  # iterates sit ~1e-9 above)
+                x = torch.log(x)
+            u0[:, :, 2:2 + K] = x[:, None, :]
+            u0[:, :, 0] = torch.log(ridge_init['Rinf_raw'])[:, None]
+            u0[:, :, 1] = torch.log(ridge_init['induc_raw'])[:, None]
+            if outliers:
+                so = torch.full((B, Nf), 0.1, dtype=torch.float64, device=self.device)
+                if flags is not None:
+                    so[flags] = 1.0
+                u0[:, :, 6 + K:6 + K + Nf] = torch.log(so)[:, None, :]
+            return u0
+
         if init is not None:
-            u0 = init.reshape(B, nch, D).clone()
+            if init.shape[-1] != D or init.numel() not in (B * D, B * nch * D):
+                raise ValueError(f'init must be [{B}, {D}] or [{B}, {nch}, {D}] (unconstrained parameters, Stan order)')
+            u0 = init.reshape(B, -1, D)
+            u0 = (u0.expand(B, nch, D) if u0.shape[1] == 1 else u0).clone()  # one point per spectrum: every chain starts there
         else:
-            # Stan: init='random' -> U(-2, 2) per unconstrained coordinate; rows keyed by global (spectrum, chain) index
-            rows = (ids[:, None] * nch + torch.arange(nch, device=self.device)[None, :]).reshape(-1)
-            u0 = _hash_uniform(random_seed, 0, 0, D, self.device, ids=rows).reshape(B, nch, D)
-            if ridge_init is not None:
-                # partial init from the ridge fit (inversion.py:1649-1677); Stan draws the remaining parameters randomly
-                x = ridge_init['x']
-                if nonneg:  # exact zeros of the active-set QP cannot be log-transformed: floor them (cvxopt's interior
-                    x = torch.clamp(x, min=1e-8 * x.abs().max(dim=1, keepdim=True).values)  # iterates sit ~1e-9 above)
-                    x = torch.log(x)
-                u0[:, :, 2:2 + K] = x[:, None, :]
-                u0[:, :, 0] = torch.log(ridge_init['Rinf_raw'])[:, None]
-                u0[:, :, 1] = torch.log(ridge_init['induc_raw'])[:, None]
-                if outliers:
-                    so = torch.full((B, Nf), 0.1, dtype=torch.float64, device=self.device)
-                    if flags is not None:
-                        so[flags] = 1.0
-                    u0[:, :, 6 + K:6 + K + Nf] = torch.log(so)[:, None, :]
+            u0 = ridge_overlay(self._initial_points(prob, ids, nch, random_seed, 0))
+        # Stan rejects an initial point whose log density or gradient is not finite and, for random inits, draws again
+        # (up to 100 times) before it gives up with an error; a user-supplied point is an error right away
+        lp0, g0 = prob.logpost_grad(u0.reshape(B * nch, D), jacobian=mode == 'sample',
+                                    spec=torch.arange(B, device=self.device).repeat_interleave(nch).to(torch.int32))
+        bad = ~(torch.isfinite(lp0) & torch.isfinite(g0).all(dim=1)).reshape(B, nch)
+        attempt = 0
+        while bool(bad.any()):
+            attempt += 1
+            if init is not None or attempt >= self.MAX_INIT_ATTEMPTS:
+                rows = torch.nonzero(bad.any(dim=1))[:, 0].tolist()
+                raise RuntimeError(f'Initialization failed: log density or gradient not finite at the initial point of '
+                                   f'spectra {rows[:10]}{" ..." if len(rows) > 10 else ""}')
+            fresh = ridge_overlay(self._initial_points(prob, ids, nch, random_seed, attempt))
+            u0 = torch.where(bad[:, :, None], fresh, u0)
+            sel = torch.nonzero(bad.reshape(-1))[:, 0]
+            lp1, g1 = prob.logpost_grad(u0.reshape(B * nch, D)[sel], jacobian=mode == 'sample',
+                                        spec=(sel // nch).to(torch.int32))
+            still = ~(torch.isfinite(lp1) & torch.isfinite(g1).all(dim=1))
+            bad = torch.zeros(B * nch, dtype=torch.bool, device=self.device).index_put_((sel,), still).reshape(B, nch)
         if mode == 'optimize':
             r = prob.map_lbfgs(u0.reshape(B, D), max_iter=max_iter)
+            failed = r['status'] < 0
+            if bool(failed.any()):  # Stan raises on a failed line search; a batch keeps its other spectra and warns
+                rows = torch.nonzero(failed)[:, 0].tolist()
+                warnings.warn(f'L-BFGS terminated with an error (line search failed) for {len(rows)} spectra: '
+                              f'{rows[:10]}{" ..." if len(rows) > 10 else ""}; see _opt_result["status"]')
             if polish:
                 p = prob.map_newton(r['u'])
                 r.update(u=p['u'], lp=p['lp'], gnorm=p['gnorm'], newton_iters=p['iters'])
             point = prob.split_outputs(prob.constrain(r['u']))
             return dict(point=point, opt=r, draws=None, stats=None)
         r = prob.nuts(u0, chains=chains, warmup=warmup, samples=samples, seed=random_seed, spectrum_ids=ids)
+        lost = ~torch.isfinite(r['stepsize'])
+        if bool(lost.any()):
+            rows = torch.nonzero(lost.any(dim=1))[:, 0].tolist()
+            raise RuntimeError(f'NUTS could not find a step size for chains of spectra {rows[:10]}')
         spec = torch.arange(B, dtype=torch.int32, device=self.device).repeat_interleave(chains * samples)
         cons = prob.constrain(r['draws'].reshape(B * chains * samples, D), spec=spec).reshape(
             B, chains * samples, prob.P)
@@ -417,7 +493,16 @@ class Inverter:
         pm, _ = capi.summarize(cons, device=self.device)
         point = prob.split_outputs(pm)
         stats = {k: r[k] for k in ('stepsize', 'n_leapfrog', 'n_divergent', 'n_maxdepth', 'accept')}
+        stats['rhat'], stats['ess_bulk'] = self._diagnostics(draws, chains, samples)
         return dict(point=point, opt=None, draws=draws if keep_draws else None, stats=stats)
+
+    def _diagnostics(self, draws, chains, samples):
+        """Split R-hat and bulk ESS of every coefficient of every distribution, R_inf and the inductance (what pystan
+        prints after sampling, inversion.py:1218-1221): [B, n_quantities] each, computed on the device
+        (bdrt_diagnostics)."""
+        keys = [k for k in ('x', 'xs', 'xp', 'xp2') if k in draws and not (k == 'x' and 'xs' in draws)]
+        q = torch.cat([draws[k] for k in keys] + [draws['Rinf'][..., None], draws['induc'][..., None]], dim=-1)
+        return capi.diagnostics(q.contiguous(), chains, device=self.device)
 
     def _merge_results(self, results, B, model_type, name, par, mode, sigma_min, keep_draws):
         """Scatter the sub-batch results (one per Stan program) back into batch order and rescale
@@ -601,9 +686,11 @@ class Inverter:
         if percentile is not None:
             if self.fit_type != 'bayes' or self._sample_result is None:
                 raise ValueError('Percentile prediction is only available for bayes_fit results')
-            if len(self.distributions) != 1 or names != list(self.distribution_fits.keys()):
-                # several distributions (or a subset): the impedance of every draw, then the percentile of its real and
-                # imaginary parts (inversion.py:2705-2737)
+            if len(self.distributions) != 1 or names != list(self.distribution_fits.keys()) or \
+                    self.distributions[names[0]]['dist_type'] != 'series':
+                # several distributions, a subset, or a parallel distribution (coefficients rescale as x / scale and enter
+                # as Z = 1 / (A x), inversion.py:2712-2725): the impedance of every draw, then the percentile of its real
+                # and imaginary parts (inversion.py:2705-2737)
                 single = self._single
                 self._single = False
                 with warnings.catch_warnings():
@@ -795,8 +882,6 @@ class Inverter:
                 raise ValueError('frequencies and Z must be given if the Inverter has not been fitted')
             frequencies, Z, fit_exists = self.f_train, self.Z_train, True
         if not (use_existing_fit and fit_exists) or self.fit_type == 'ridge':
-            if np.ndim(frequencies) != 1:
-                raise NotImplementedError('the ridge solver takes one frequency grid per batch')
             single = torch.as_tensor(np.asarray(Z) if not torch.is_tensor(Z) else Z).dim() == 1
             freq, Zb = self._to_batch(frequencies, Z)
             flags = self._ridge_outlier_flags(freq, Zb, threshold, use_existing_fit and fit_exists, **ridge_kw)

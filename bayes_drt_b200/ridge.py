@@ -47,7 +47,15 @@ def ridge_fit(inv, frequencies, Z, part='both', penalty='discrete', reg_ord=2, L
               weights=None, preset=None, hyper_lambda=True, hl_solution='analytic', hl_beta=2.5, hl_fbeta=None,
               lambda_0=1e-2, cv_lambdas=None, hyper_weights=False, hw_beta=2, hw_wbar=1, xtol=1e-3, max_iter=20,
               hyper_a=False, alpha_a=2, hl_beta_a=2, hyper_b=False, sb=1, correct_phase_offset=False, IERange=None,
-              lambda_phz=1, init_phase_offset=False, x0=None, dZ=False, dZ_power=0.5):
+              lambda_phz=1, init_phase_offset=False, x0=None, dZ=False, dZ_power=0.5, stop_rule='unchanged'):
+    """Inverter.ridge_fit (inversion.py:142-900) for a batch.  ``frequencies`` may be [Nf] (one grid) or [B, Nf] (one grid
+    per spectrum: kernel matrices built per row on the GPU; the rows' bases share one spacing, so the penalty matrices
+    are common).  ``stop_rule``: how the hyper-lambda stop test treats a coefficient that is exactly 0 in two consecutive
+    iterations -- 'unchanged' (default): no change; 'nan': numpy's 0/0 = NaN never passes, which is what the
+    reference's code does with an exact QP solver (it then always runs max_iter iterations; cvxopt's interior iterates
+    are never exactly 0, SURVEY.md section 7 hard part 1b)."""
+    if stop_rule not in ('unchanged', 'nan'):
+        raise ValueError(f"Invalid stop_rule {stop_rule}. Options are 'unchanged', 'nan'")
     presets = ['Ciucci', 'Huang']
     if preset is not None:
         if preset not in presets:
@@ -90,34 +98,37 @@ def ridge_fit(inv, frequencies, Z, part='both', penalty='discrete', reg_ord=2, L
 
     dev = inv.device
     freq, Zb = inv._to_batch(frequencies, Z)
-    if freq.dim() == 2:
-        raise NotImplementedError('ridge_fit takes one frequency grid per batch (per-spectrum grids: Inverter.fit)')
+    per_grid = freq.dim() == 2
     inv.f_train, inv.Z_train = freq.numpy(), Zb
     Zs = inv._scale_Z(Zb, scale_Z)
     tau, eps, m = inv._grid(freq, name)
     B, Nf = Zs.shape
-    K = len(tau)
+    K = tau.shape[-1]
     n = K + 2
-    # augmented matrices: [1 | 0 | A_re], [0 | 2 pi f 1e-4 | A_im]   (inversion.py:401-417)
-    A_re = torch.zeros((Nf, n), dtype=torch.float64, device=dev)
-    A_im = torch.zeros((Nf, n), dtype=torch.float64, device=dev)
-    A_re[:, 2:], A_im[:, 2:] = m['A_re'], m['A_im']
-    A_re[:, 0] = 1.0
+    # augmented matrices: [1 | 0 | A_re], [0 | 2 pi f 1e-4 | A_im]   (inversion.py:401-417); one pair per spectrum when
+    # every spectrum has its own grid
+    lead = (B,) if per_grid else ()
+    A_re = torch.zeros(lead + (Nf, n), dtype=torch.float64, device=dev)
+    A_im = torch.zeros(lead + (Nf, n), dtype=torch.float64, device=dev)
+    A_re[..., 2:], A_im[..., 2:] = m['A_re'], m['A_im']
+    A_re[..., 0] = 1.0
     if inv.fit_inductance:
-        A_im[:, 1] = 2 * np.pi * freq.to(dev) * 1e-4
+        A_im[..., 1] = 2 * np.pi * freq.to(dev) * 1e-4
     w_re, w_im = _weights(Zs, weights)
-    shared_w = weights is None or (isinstance(weights, str) and weights == 'unity')
+    shared_w = (weights is None or (isinstance(weights, str) and weights == 'unity')) and not per_grid
     if shared_w:
         WA_re, WA_im = A_re, A_im
     else:
-        WA_re, WA_im = w_re[:, :, None] * A_re[None], w_im[:, :, None] * A_im[None]
+        WA_re, WA_im = w_re[:, :, None] * (A_re if per_grid else A_re[None]), \
+            w_im[:, :, None] * (A_im if per_grid else A_im[None])
     WZ_re, WZ_im = (w_re * Zs.real).contiguous(), (w_im * Zs.imag).contiguous()
     frac = np.zeros(3)
     if isinstance(reg_ord, (int, np.integer)):
         frac[int(reg_ord)] = 1
     else:
         frac[:] = np.asarray(reg_ord, dtype=np.float64)
-    bft = torch.as_tensor(1 / (2 * np.pi * tau))
+    # penalty matrices depend on ratios of the basis time constants only: the first row stands for all
+    bft = torch.as_tensor(1 / (2 * np.pi * (tau[0] if tau.ndim == 2 else tau)))
     Pen = torch.zeros((3, n, n), dtype=torch.float64, device=dev)
     Lmat = None
     if penalty in ('integral', 'cholesky'):
@@ -152,8 +163,9 @@ def ridge_fit(inv, frequencies, Z, part='both', penalty='discrete', reg_ord=2, L
                                penalty='integral' if penalty == 'integral' else 'discrete',  # 'cholesky': discrete rule
                                xtol=xtol, hl_beta=float(hl_beta), lambda_0=float(lam0), reg_ord=frac,
                                L1_penalty=L1_penalty, epsilon=eps,
-                               fit_inductance=inv.fit_inductance and part_ != 'real', hl_fbeta=hl_fbeta, device=dev)
-            coef, lam, iters, conv = r['coef'], r['lam'], r['iters'], r['converged']
+                               fit_inductance=inv.fit_inductance and part_ != 'real', hl_fbeta=hl_fbeta,
+                               stop_rule=1 if stop_rule == 'unchanged' else 0, device=dev)
+            coef, lam, iters, conv, nfac = r['coef'], r['lam'], r['iters'], r['converged'], r.get('n_factor')
         else:
             # ordinary ridge: one QP with lambda = lambda_0 (inversion.py:835-850)
             G0 = (war.transpose(-1, -2) @ war + wai.transpose(-1, -2) @ wai)
@@ -170,12 +182,16 @@ def ridge_fit(inv, frequencies, Z, part='both', penalty='discrete', reg_ord=2, L
             lam = torch.full((b, 3, n), float(lam0), dtype=torch.float64, device=dev)
             iters = torch.ones(b, dtype=torch.int32, device=dev)
             conv = torch.ones(b, dtype=torch.int32, device=dev)
+            nfac = None
+        are, aim = (A_re, A_im) if not per_grid else (pick(A_re), pick(A_im))
         if part_ == 'imag':  # R_inf from the real part: the least-squares fit of a constant is the mean
-            coef[:, 0] = (zs.real - coef[:, 2:] @ A_re[:, 2:].T).mean(dim=1)
+            coef[:, 0] = (zs.real - inv._apply(are[..., 2:], coef[:, 2:])).mean(dim=1)
         elif part_ == 'real' and inv.fit_inductance:  # inductance from the imaginary part
-            a_l = A_im[:, 1]
-            coef[:, 1] = ((zs.imag - coef[:, 2:] @ A_im[:, 2:].T) @ a_l) / (a_l @ a_l)
-        return coef, lam, iters, conv
+            a_l = aim[..., 1]
+            coef[:, 1] = ((zs.imag - inv._apply(aim[..., 2:], coef[:, 2:])) * a_l).sum(dim=-1) / (a_l * a_l).sum(dim=-1)
+        if nfac is None:
+            nfac = torch.zeros(b, dtype=torch.int32, device=dev)
+        return coef, lam, iters, conv, nfac
 
     if cv:
         # Re-Im cross-validation of lambda_0 (Inverter.ridge_ReImCV, inversion.py:902-944): fit the real part and score
@@ -185,9 +201,9 @@ def ridge_fit(inv, frequencies, Z, part='both', penalty='discrete', reg_ord=2, L
         imcv = torch.zeros_like(recv)
         for i, lam_i in enumerate(lambdas):
             c = core(lam_i, 'real')[0]
-            imcv[:, i] = ((Zs.imag - c @ A_im.T) ** 2).sum(dim=1)
+            imcv[:, i] = ((Zs.imag - inv._apply(A_im, c)) ** 2).sum(dim=1)
             c = core(lam_i, 'imag')[0]
-            recv[:, i] = ((Zs.real - c @ A_re.T) ** 2).sum(dim=1)
+            recv[:, i] = ((Zs.real - inv._apply(A_re, c)) ** 2).sum(dim=1)
         s2 = (inv._Z_scale ** 2)[:, None]  # the reference scores in unscaled units
         recv, imcv = recv * s2, imcv * s2
         totcv = recv + imcv
@@ -209,11 +225,13 @@ def ridge_fit(inv, frequencies, Z, part='both', penalty='discrete', reg_ord=2, L
         lam = torch.empty((B, 3, n), dtype=torch.float64, device=dev)
         iters = torch.empty(B, dtype=torch.int32, device=dev)
         conv = torch.empty(B, dtype=torch.int32, device=dev)
+        nfac = torch.empty(B, dtype=torch.int32, device=dev)
         for lv in np.unique(lam_b):  # one launch per selected lambda_0
             sel = torch.as_tensor(np.nonzero(lam_b == lv)[0], device=dev)
-            coef[sel], lam[sel], iters[sel], conv[sel] = core(lv, part, sel)
+            coef[sel], lam[sel], iters[sel], conv[sel], nfac[sel] = core(lv, part, sel)
     else:
-        coef, lam, iters, conv = core(lambda_0, part)
+        coef, lam, iters, conv, nfac = core(lambda_0, part)
+    inv._ridge_factorisations = nfac  # Cholesky factorisations of the QP solver per spectrum, counted on the device
     if hyper_lambda:
         inv._ridge_iters, inv._ridge_converged = iters, conv
         if inv._single and not bool(conv[0]):

@@ -159,7 +159,7 @@ int bdrt_map_lbfgs(bdrt_ctx* ctx, const bdrt_series_data* data, const bdrt_lbfgs
 /* Damped-Newton polish of MAP estimates (not in the reference: brings both sides of the parity test to the unique
  * optimum, SURVEY.md section 7 hard part 1).  u [B,D] in/out; gnorm [B] = max|grad| at the result. */
 typedef struct {
-  int max_iter;   /* Newton iterations (default 40) */
+  int max_iter;   /* Newton iterations (default 200) */
   double gtol;    /* stop when max|grad| < gtol (default 1e-9) */
   double fd_step; /* relative forward-difference step of the Hessian (default 1e-6) */
 } bdrt_newton_opts;
@@ -208,6 +208,14 @@ int bdrt_constrain(bdrt_ctx* ctx, const bdrt_series_data* data, const double* u,
 int bdrt_summarize(bdrt_ctx* ctx, const double* draws, int G, int S, int P, const double* probs_host, int nq,
                    double* mean, double* quant);
 
+/* Sampler diagnostics, on device: split R-hat and rank-normalised split-chain bulk ESS (Vehtari et al. 2021) of every
+ * column -- the numbers pystan prints after StanModel.sampling (inversion.py:1218-1221; SURVEY.md section 8b lists
+ * them among the outputs of the sampler) and the ESS behind the benchmark's ESS/s metric.
+ * draws [G, chains * n, P] (draw index = chain * n + i, i.e. the layout of bdrt_constrain applied to bdrt_nuts draws);
+ * outputs rhat [G, P], ess_bulk [G, P] (either may be NULL).  n >= 4. */
+int bdrt_diagnostics(bdrt_ctx* ctx, const double* draws, int G, int chains, int n, int P, double* rhat,
+                     double* ess_bulk);
+
 /* ---- hyper-parametric ridge: replaces cvxopt.solvers.qp inside Inverter._convex_opt (inversion.py:1043-1067)
  *      and the hyper-lambda loop of Inverter.ridge_fit (inversion.py:489-753) ---------------------------------- */
 /* Batched bound-constrained strictly convex QP   min 1/2 x'Px + q'x  s.t. x >= lb.
@@ -228,6 +236,10 @@ typedef struct {
   int fit_inductance;
   double hl_fbeta;  /* > 0: lambda_k = lambda_0 / ((L c)_k^2 / (max_k (L c)_k^2 hl_fbeta) + 1) instead of the hl_beta rule
                      * (discrete penalty, _hyper_lambda_fbeta inversion.py:956-964; preset 'Ciucci' uses 0.1); 0: off */
+  int stop_rule;    /* stop test mean(|(c - c_prev) / c_prev|) < xtol (inversion.py:730-736) when a coefficient is 0 in
+                     * two consecutive iterations (0/0): 0 = numpy semantics, NaN never passes -- what the reference's own
+                     * code does once the QP solver returns exact zeros on the bound (cvxopt's interior-point iterates
+                     * never do, SURVEY.md section 7 hard part 1b); 1 (default) = such a coefficient counts as unchanged */
 } bdrt_ridge_opts;
 void bdrt_ridge_default_opts(bdrt_ridge_opts* o);
 
@@ -239,10 +251,12 @@ void bdrt_ridge_default_opts(bdrt_ridge_opts* o);
  * Lmat [3,K,K+2] zero-padded L_o (discrete penalty only, for the lambda update inversion.py:947-954; may be NULL
  *   for the integral penalty);
  * outputs: coef [B,K+2] (scaled units, before the rescaling of inversion.py:875-894), lam [B,3,K+2],
- *   iters [B], converged [B]. */
+ *   iters [B] hyper-iterations, converged [B], n_factor [B] Cholesky factorisations (pivot steps of the QP solver)
+ *   spent on the spectrum; iters / converged / n_factor may be NULL.  Any Nf. */
 int bdrt_ridge_fit(bdrt_ctx* ctx, const bdrt_ridge_opts* opts, const double* WA_re, const double* WA_im,
                    int per_spectrum_W, const double* WZ_re, const double* WZ_im, const double* Pen,
-                   const double* Lmat, int B, int Nf, int K, double* coef, double* lam, int* iters, int* converged);
+                   const double* Lmat, int B, int Nf, int K, double* coef, double* lam, int* iters, int* converged,
+                   int* n_factor);
 
 /* ---- micro-benchmarks used for the roofline denominators (bench.py) ------------------------------------------ */
 /* Achieved FP64 FMA and FP64 DMMA (mma.sync.m8n8k4) throughput in TFLOP/s, measured with CUDA events. */

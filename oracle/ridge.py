@@ -20,7 +20,11 @@ converge to within its own tolerances (abstol 1e-7, reltol 1e-6).
 Stop test of the hyper loop: the reference's ``mean(|(coef - prev)/prev|) < xtol`` evaluated with numpy semantics.
 With an exact solver, coefficients on the bound are exactly 0 in consecutive iterations, 0/0 = NaN, NaN < xtol is
 False, and the loop runs all ``max_iter`` iterations -- the reference only stops early through cvxopt's interior
-jitter (SURVEY section 7 hard part 1b).  The oracle and the CUDA kernel both implement exactly that numpy semantics.
+jitter (SURVEY section 7 hard part 1b).  ``stop_rule='nan'`` is exactly that numpy semantics (what the golden vectors
+of the reference's code with an exact solver were made with); ``stop_rule='unchanged'`` (the CUDA library's default)
+counts a coefficient that is identical in two consecutive iterations -- in particular one that stays on its bound -- as
+unchanged, so that the loop can stop when the free coefficients have converged.  The oracle and the CUDA kernel
+implement both.
 """
 import numpy as np
 
@@ -138,7 +142,7 @@ def prep(freq, Z, basis_freq=None, epsilon=None, penalty='discrete', weights=Non
 
 
 def hyper_loop(WA_re, WA_im, WZ_re, WZ_im, Pen, Lmat, penalty, frac, nonneg, hl_beta, hl_fbeta, lambda_0, L1_penalty,
-               epsilon, xtol, max_iter, fit_inductance, x0=None):
+               epsilon, xtol, max_iter, fit_inductance, x0=None, stop_rule='nan'):
     """The hyper-lambda iteration of ridge_fit (inversion.py:489-753) on an assembled system: lambda update from the
     previous coefficients, P = G0 + sum_o frac_o Lam_o^1/2 Pen_o Lam_o^1/2, QP, stop test.  This is the interface of
     bdrt_ridge_fit (include/bdrt.h).  Returns (coef [K+2] scaled, lam [3, K+2], history, converged)."""
@@ -176,6 +180,8 @@ def hyper_loop(WA_re, WA_im, WZ_re, WZ_im, Pen, Lmat, penalty, frac, nonneg, hl_
         hist.append(coef.copy())
         with np.errstate(all='ignore'):
             delta = (coef - prev) / prev
+            if stop_rule == 'unchanged':
+                delta[coef == prev] = 0.0
             if not fit_inductance:
                 delta[1] = 0
             if np.mean(np.abs(delta)) < xtol:
@@ -205,7 +211,8 @@ def ridge_ReImCV(freq, Z, lambdas=None, **kw):
 
 def ridge_fit(freq, Z, basis_freq=None, epsilon=None, penalty='discrete', reg_ord=2, L1_penalty=0.0, scale_Z=True,
               nonneg=True, weights=None, hl_beta=2.5, lambda_0=1e-2, xtol=1e-3, max_iter=20, fit_inductance=True,
-              preset=None, x0=None, return_history=False, part='both', hl_fbeta=None, cv_lambdas=None):
+              preset=None, x0=None, return_history=False, part='both', hl_fbeta=None, cv_lambdas=None,
+              stop_rule='nan'):
     """Hyper-lambda path of Inverter.ridge_fit.  Returns dict(coef [K], R_inf, inductance, scaled_coef [K+2],
     lam [3, K+2], iters, converged).  ``part`` 'real' / 'imag' fits one part only (_convex_opt :1047-1052) and then
     sets the parameter that part cannot see by least squares on the other part (:855-873)."""
@@ -220,7 +227,8 @@ def ridge_fit(freq, Z, basis_freq=None, epsilon=None, penalty='discrete', reg_or
         lambda_0, cv_table = ridge_ReImCV(freq, Z, lambdas=cv_lambdas, basis_freq=basis_freq, epsilon=epsilon,
                                           penalty=penalty, reg_ord=reg_ord, L1_penalty=L1_penalty, scale_Z=scale_Z,
                                           nonneg=nonneg, weights=weights, hl_beta=hl_beta, xtol=xtol,
-                                          max_iter=max_iter, fit_inductance=fit_inductance, x0=x0, hl_fbeta=hl_fbeta)
+                                          max_iter=max_iter, fit_inductance=fit_inductance, x0=x0, hl_fbeta=hl_fbeta,
+                                          stop_rule=stop_rule)
     p = prep(freq, Z, basis_freq, epsilon, penalty, weights, scale_Z, fit_inductance)
     n = p['K'] + 2
     frac = np.zeros(3)
@@ -233,7 +241,8 @@ def ridge_fit(freq, Z, basis_freq=None, epsilon=None, penalty='discrete', reg_or
     use_re, use_im = float(part != 'imag'), float(part != 'real')
     coef, lam, hist, converged = hyper_loop(use_re * p['WA_re'], use_im * p['WA_im'], use_re * p['WZ_re'],
                                             use_im * p['WZ_im'], p['Pen'], p['Lmat'], penalty, frac, nonneg, hl_beta,
-                                            hl_fbeta, lambda_0, L1_penalty, p['epsilon'], xtol, max_iter, fit_inductance, x0)
+                                            hl_fbeta, lambda_0, L1_penalty, p['epsilon'], xtol, max_iter, fit_inductance, x0,
+                                            stop_rule=stop_rule)
     iters = len(hist)
     coef = coef.copy()
     if part == 'imag':  # R_inf from the real part (inversion.py:855-863; a constant's least-squares fit is the mean)

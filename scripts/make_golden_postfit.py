@@ -89,6 +89,7 @@ CASES = {
     'series_sample': (dict(), dict(mode='sample')),
     'series_out_sample': (dict(), dict(mode='sample', outliers=True)),
     'parallel_opt': (dict(distributions={'TP-DDT': dict(TP)}), dict(mode='optimize')),
+    'parallel_sample': (dict(distributions={'TP-DDT': dict(TP)}), dict(mode='sample')),
     'sp_opt': (dict(distributions={'DRT': dict(DRT), 'TP-DDT': dict(TP, x_scale=0.8)}), dict(mode='optimize', nonneg=True)),
     'sp_sample': (dict(distributions={'DRT': dict(DRT), 'TP-DDT': dict(TP, x_scale=0.8)}), dict(mode='sample', nonneg=True)),
     's2p_opt': (dict(distributions={'DRT': dict(DRT), 'TP-DDT': dict(TP, x_scale=0.8), 'BP-DDT': dict(BP)}),
@@ -133,7 +134,12 @@ for case, (ikw, fkw) in CASES.items():
     out[p + 'outlier_idx_z1'] = np.asarray(inv.check_outliers(freq, Z, threshold=1.0, use_existing_fit=True)).ravel()
     if fkw['mode'] == 'sample':
         out[p + 'Z_pred_p25'] = inv.predict_Z(f_pred, percentile=25)
-    if fkw['mode'] == 'sample' and len(inv.distributions) == 1:
+    if fkw['mode'] == 'sample' and len(inv.distributions) == 1 and not single_drt:
+        # single parallel distribution: percentile bands of the error structure off the training grid go through
+        # predict_Z(percentile=...) with the parallel arithmetic Z = 1 / (A (x / scale)) (inversion.py:2712-2725)
+        s_re, s_im = inv.predict_sigma(f_pred, percentile=60)
+        out[p + 'sigma_pred_p60'] = np.concatenate((s_re, s_im))
+    if fkw['mode'] == 'sample' and single_drt:
         out[p + 'Rp_p75'] = np.float64(inv.predict_Rp(percentile=75))
         s_re, s_im = inv.predict_sigma(f_pred, percentile=60)
         out[p + 'sigma_pred_p60'] = np.concatenate((s_re, s_im))

@@ -55,6 +55,15 @@ class OracleProblem:
             return -lp, -g
         return f
 
+    def logpost_grad(self, u, spec=None, jacobian=False):
+        u = np.asarray(u, dtype=np.float64).reshape(-1, self.D)
+        lp, g = np.empty(len(u)), np.empty_like(u)
+        for i in range(len(u)):
+            d = self.ds[int(spec[i]) if spec is not None else i % self.B]
+            with np.errstate(all='ignore'):
+                lp[i], g[i] = self.mod.logpost(u[i], d, jacobian=jacobian)
+        return torch.tensor(lp), torch.tensor(g)
+
     def map_lbfgs(self, u0, max_iter=2000, **kw):
         u0 = np.asarray(u0, dtype=np.float64).reshape(self.B, self.D)
         rs = [olb.minimize(self._f(d), u0[b], max_iter=max_iter) for b, d in enumerate(self.ds)]
@@ -118,9 +127,20 @@ def install(monkeypatch):
     def summarize(draws, percentiles=(), want_mean=True, device=None):
         q = torch.stack([torch.quantile(draws, float(p) / 100.0, dim=1) for p in percentiles]) if len(percentiles) else None
         return (draws.mean(dim=1) if want_mean else None), q
+    def diagnostics(draws, chains, device=None):
+        d = np.asarray(draws, dtype=np.float64)
+        G, S, P = d.shape
+        x = d.reshape(G, chains, S // chains, P)
+        ess = np.array([[onuts.ess_bulk(x[g, :, :, p]) for p in range(P)] for g in range(G)])
+        h = (S // chains) // 2
+        z = np.concatenate((x[:, :, :h], x[:, :, h:2 * h]), axis=1)  # split chains [G, 2 chains, h, P]
+        W = z.var(axis=2, ddof=1).mean(axis=1)
+        rhat = np.sqrt(((h - 1) / h * W + z.mean(axis=2).var(axis=1, ddof=1)) / W)
+        return torch.tensor(rhat), torch.tensor(ess)
     monkeypatch.setattr(inverter, 'context', lambda device=None: type('Ctx', (), {'device': torch.device('cpu')})())
     monkeypatch.setattr(inverter.capi, 'build_A', build_A)
     monkeypatch.setattr(inverter.capi, 'build_L', build_L)
     monkeypatch.setattr(inverter.capi, 'summarize', summarize)
+    monkeypatch.setattr(inverter.capi, 'diagnostics', diagnostics)
     monkeypatch.setattr(inverter.capi, 'SeriesProblem', OracleProblem)
     return inverter

@@ -261,8 +261,31 @@ def test_fit_per_spectrum_frequency_grids():
     assert (lo <= hi).all()
     Zq = inv2.predict_Z(inv2.f_train, percentile=50)
     assert tuple(Zq.shape) == (2, 81) and float((Zq.cpu() - torch.tensor(Z[1:3])).abs().max()) < 0.05
-    with pytest.raises(NotImplementedError):
-        inv2.fit(freq[:2], Z[:2], init_from_ridge=True)
+    # ridge-initialised MAP and automatic outlier detection on per-spectrum grids (inversion.py:1154-1187 row by row):
+    # the batch splits by Stan program (one row gets the outlier model) and every row equals the same flow run on that
+    # row alone (same global spectrum index, hence the same random part of the start)
+    import warnings
+    inv3 = Inverter()
+    Zo = Z[:3].copy()
+    Zo[1, 30] += 0.15 + 0.15j
+    inv3.fit(freq[:3], Zo, init_from_ridge=True, outliers='auto', polish=True)
+    assert inv3._outlier_model.cpu().tolist() == [False, True, False]
+    assert tuple(np.shape(inv3.distributions['DRT']['tau'])) == (3, 101)  # the whole batch's grids are back in place
+    for b in range(3):
+        one = Inverter()
+        with warnings.catch_warnings():
+            warnings.simplefilter('ignore')
+            one.fit(freq[b:b + 1], Zo[b:b + 1], init_from_ridge=True, outliers='auto', polish=True, spectrum_offset=b)
+        c1, cb = one.distribution_fits['DRT']['coef'][0], inv3.distribution_fits['DRT']['coef'][b]
+        assert bool(one._outlier_model[0]) == (b == 1)
+        # both runs are taken to the exact optimum (polish): an L-BFGS end point alone amplifies last-bit differences of
+        # the inputs (torch's batched std() of |Z| depends on the batch shape) to the percent level
+        # (the outlier model has 2 Nf more parameters, most of them on their bound: its polish stops at max|grad| < 1e-7
+        # a few 1e-3 of the peak apart)
+        tol = 1e-2 if b == 1 else 1e-4
+        assert float((cb - c1).abs().max()) <= tol * float(c1.abs().max()), b
+        assert float((inv3.R_inf[b] - one.R_inf[0]).abs()) <= tol * float(one.R_inf[0])
+    assert 30 in torch.nonzero(inv3.error_fit['sigma_out'][1] > 5 * inv3.error_fit['sigma_out'][1].median())[:, 0].tolist()
     with pytest.raises(ValueError):
         inv2.fit(freq[:2], Z[0])
 
@@ -346,3 +369,32 @@ def test_predict_sigma_off_grid_score_and_weight_forms():
         assert np.isfinite(r1.distribution_fits['DRT']['coef']).all() and abs(r1.predict_Rp() - 1.0) < 0.1
     with pytest.raises(ValueError):
         r1.ridge_fit(freq, Z, weights=np.ones(5))
+
+
+def test_fit_init_shapes_failures_and_diagnostics():
+    """a [B, D] init with several chains starts every chain there; a bad explicit init is an error
+    (Stan: "Initialization failed"); chains * samples beyond what the percentile kernel holds is refused before the
+    sampler runs; HMC fits carry split R-hat and bulk ESS of every coefficient, R_inf and the inductance."""
+    from bayes_drt_b200 import Inverter, synth
+    freq, Z, _ = synth.make_spectra(3, seed=8)
+    _, bf = synth.bench_grid()
+    inv = Inverter(basis_freq=bf.numpy())
+    D = 2 * 100 + 9
+    u = torch.zeros(3, D, dtype=torch.float64)
+    inv.fit(freq, Z, mode='sample', chains=3, warmup=30, samples=20, init=u, check_outliers=False)
+    st = inv._sample_stats
+    assert tuple(st['rhat'].shape) == (3, 102) and tuple(st['ess_bulk'].shape) == (3, 102)
+    assert torch.isfinite(st['rhat']).all() and (st['ess_bulk'] > 0).all()
+    with pytest.raises(ValueError, match='init must be'):
+        inv.fit(freq, Z, mode='sample', chains=3, warmup=30, samples=20, init=torch.zeros(3, 2, D, dtype=torch.float64))
+    bad = u.clone()
+    bad[1, 5] = float('nan')
+    with pytest.raises(RuntimeError, match='Initialization failed'):
+        inv.fit(freq, Z, mode='optimize', init=bad)
+    with pytest.raises(ValueError, match='merged draws'):
+        inv.fit(freq, Z, mode='sample', chains=4, warmup=10, samples=5000)
+    # the public preparation hook hands out the same problem / starts that fit() uses
+    prob, u0 = inv.prepare(freq, Z, mode='optimize')
+    r = prob.map_lbfgs(u0, max_iter=50)
+    inv.fit(freq, Z, mode='optimize', max_iter=50, check_outliers=False)
+    assert torch.equal(r['u'], inv._opt_result['u'])

@@ -78,8 +78,10 @@ def test_map_1e5_on_benchmark_batch():
         err_lbfgs[b] = np.max(np.abs(x_lbfgs[b] - xo)) / sc
         if ok[b]:
             assert err_pol[b] <= 1e-5, (b, err_pol[b])
-            assert abs(Rinf_pol[b] - ora[b]['Rinf']) <= 1e-5 * ora[b]['Rinf']
-            assert abs(sres_pol[b] - ora[b]['sigma_res']) <= 1e-5 * ora[b]['sigma_res'] + 1e-9
+            assert abs(Rinf_pol[b] - ora[b]['Rinf']) <= 1e-5 * ora[b]['Rinf'] + 2e-6  # (-> 0 in a few poor optima)
+            # (sigma_res is a lower=0 parameter that goes to its bound for clean RC spectra: compared absolutely there,
+            # on the scale of sigma_min = 0.002)
+            assert abs(sres_pol[b] - ora[b]['sigma_res']) <= 1e-5 * ora[b]['sigma_res'] + 2e-6
             assert abs(pol._opt_result['lp'][b].item() + ora[b]['f']) <= 1e-9 * abs(ora[b]['f'])
     q = lambda a: {p: float(np.percentile(a[ok], p)) for p in (5, 50, 95, 100)}  # noqa: E731
     rep = dict(n=NSPEC, converged_both=int(ok.sum()), polished_rel_err_inf=q(err_pol), lbfgs_rel_err_inf=q(err_lbfgs),

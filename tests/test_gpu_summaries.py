@@ -45,3 +45,42 @@ def test_summarize_errors_and_large_batch():
     assert torch.allclose(quant[0], (S - 1) / 2 + torch.arange(G, dtype=torch.float64, device='cuda')[:, None].expand(G, P))
     assert torch.equal(quant[1][:, 0], S - 1 + torch.arange(G, dtype=torch.float64, device='cuda'))
     assert torch.allclose(mean, quant[0])
+
+
+def test_diagnostics_match_oracle_estimators():
+    """bdrt_diagnostics: split R-hat and rank-normalised bulk ESS of every column against oracle/nuts.py: ess_bulk (the
+    estimator the golden NUTS files and the benchmark's ESS/s are made with) and the textbook split R-hat, on AR(1)
+    chains with different autocorrelations, a stuck chain (ties) and an offset chain (R-hat >> 1)."""
+    from bayes_drt_b200 import capi
+    from oracle.nuts import ess_bulk
+    rng = np.random.RandomState(3)
+    G, chains, n, P = 3, 4, 200, 7
+    x = np.empty((G, chains, n, P))
+    for g in range(G):
+        for p in range(P):
+            phi = [0.0, 0.3, 0.6, 0.9, 0.95, -0.4, 0.5][p]
+            e = rng.standard_normal((chains, n))
+            for c in range(chains):
+                v = np.empty(n)
+                v[0] = e[c, 0]
+                for i in range(1, n):
+                    v[i] = phi * v[i - 1] + np.sqrt(1 - phi * phi) * e[c, i]
+                x[g, c, :, p] = v * (1 + g) + p
+    x[1, 2, :, 3] += 4.0           # one chain elsewhere: R-hat well above 1
+    x[2, 1, 50:120, 5] = x[2, 1, 50, 5]  # a stuck stretch: tied values
+    draws = torch.tensor(x.reshape(G, chains * n, P))
+    rhat, ess = capi.diagnostics(draws, chains)
+    rhat, ess = rhat.cpu().numpy(), ess.cpu().numpy()
+    for g in range(G):
+        for p in range(P):
+            col = x[g, :, :, p]
+            assert ess[g, p] == pytest.approx(ess_bulk(col), rel=1e-9), (g, p)
+            h = n // 2
+            z = np.concatenate((col[:, :h], col[:, h:2 * h]), axis=0)
+            W = z.var(axis=1, ddof=1).mean()
+            ref = np.sqrt(((h - 1) / h * W + z.mean(axis=1).var(ddof=1)) / W)
+            assert rhat[g, p] == pytest.approx(ref, rel=1e-10), (g, p)
+    assert rhat[1, 3] > 1.5 and np.all(np.delete(rhat.ravel(), 1 * P + 3) < 1.3)  # (phi = 0.95: 4 x 200 draws are few)
+    # odd chain length: the last draw is dropped, like the split of the oracle
+    r2, e2 = capi.diagnostics(torch.tensor(x[:, :, :199].reshape(G, chains * 199, P)), chains)
+    assert e2[0, 1].item() == pytest.approx(ess_bulk(x[0, :, :199, 1]), rel=1e-9)

@@ -54,6 +54,10 @@ class Recorder:
         self.D = 2 * (self.K + sum(n_par)) + 6 + 3 * (1 + len(n_par)) + (2 * self.Nf if kw.get('outliers') else 0)
         Recorder.last = self
 
+    def logpost_grad(self, u, spec=None, jacobian=False):
+        """the initial-point check of fit(): every point is accepted here"""
+        return torch.zeros(u.shape[0], dtype=torch.float64), torch.zeros_like(u)
+
     def map_lbfgs(self, *a, **k):
         self.call = ('optimizing', k)
         raise Abort
@@ -311,7 +315,7 @@ def host_ridge(host, monkeypatch):
 
     def ridge_fit(WA_re, WA_im, WZ_re, WZ_im, Pen, Lmat, penalty='discrete', nonneg=True, max_iter=20, xtol=1e-3,
                   hl_beta=2.5, lambda_0=1e-2, reg_ord=(0.0, 0.0, 1.0), L1_penalty=0.0, epsilon=1.0, fit_inductance=True,
-                  hl_fbeta=None, device=None):
+                  hl_fbeta=None, stop_rule=1, device=None):
         B = WZ_re.shape[0]
         coef, lam, iters, conv = [], [], [], []
         for b in range(B):
@@ -320,7 +324,7 @@ def host_ridge(host, monkeypatch):
             c, l, hist, cv = oridge.hyper_loop(war, wai, WZ_re[b].numpy(), WZ_im[b].numpy(), Pen.numpy(),
                                                None if Lmat is None else Lmat.numpy(), penalty, np.asarray(reg_ord),
                                                nonneg, hl_beta, hl_fbeta, lambda_0, L1_penalty, epsilon, xtol, max_iter,
-                                               fit_inductance)
+                                               fit_inductance, stop_rule='unchanged' if stop_rule == 1 else 'nan')
             coef.append(c), lam.append(l.copy()), iters.append(len(hist)), conv.append(int(cv))
         return dict(coef=torch.tensor(np.stack(coef)), lam=torch.tensor(np.stack(lam)),
                     iters=torch.tensor(iters, dtype=torch.int32), converged=torch.tensor(conv, dtype=torch.int32))
@@ -361,7 +365,8 @@ def test_shipped_ridge_fit_reproduces_the_reference(case, host_ridge):
     inv = host_ridge.Inverter()
     with warnings.catch_warnings():
         warnings.simplefilter('ignore')
-        inv.ridge_fit(S[names[0] + '/freq'], Zb, **RIDGE_REFERENCE_CASES[case])
+        # stop_rule='nan': the reference's own loop with an exact QP solver, which the golden vectors were made with
+        inv.ridge_fit(S[names[0] + '/freq'], Zb, stop_rule='nan', **RIDGE_REFERENCE_CASES[case])
     tol = 1e-6 if case in ('fbeta', 'ciucci') else 1e-9
     for b, n in enumerate(names):
         key = f'{n}/{case}'
@@ -401,7 +406,43 @@ def test_per_spectrum_grids_prepare_each_row_like_a_single_fit(host):
         assert np.allclose(inv.distributions['DRT']['tau'][b], one.distributions['DRT']['tau'], rtol=1e-15)
         assert np.max(np.abs(batch.A[b].numpy() - single.A.numpy())) <= 1e-13 * np.abs(single.A.numpy()).max()
         assert np.max(np.abs(batch.L.numpy() - single.L.numpy())) <= 1e-12 * np.abs(single.L.numpy()).max()
-    with pytest.raises(NotImplementedError):
-        host.Inverter().fit(freq, Zb, init_from_ridge=True)
     with pytest.raises(ValueError):
         host.Inverter().fit(freq, Zb[0])
+
+
+def test_per_spectrum_grids_reach_the_ridge_solver_row_by_row(host, monkeypatch):
+    """ridge_fit (and with it init_from_ridge / outliers='auto' / check_outliers) on frequencies [B, Nf]: row b of the
+    weighted augmented system handed to bdrt_ridge_fit is the system of a single-grid fit of row b (pinned to the
+    reference above); the penalty matrices are shared."""
+    from bayes_drt_b200 import ridge
+    rng = np.random.RandomState(5)
+    deltas = np.array([0.0, 0.31, 0.77])
+    freq = 10.0 ** (6 - deltas[:, None] - np.arange(81)[None, :] / 10)
+    Zb = 1.0 + 1.0 / (1 + (2j * np.pi * freq * 10.0 ** rng.uniform(-4, 0, (3, 1))) ** 0.8) \
+        + 0.002 * (rng.randn(3, 81) + 1j * rng.randn(3, 81))
+    rec = {}
+
+    def ridge_fit(WA_re, WA_im, WZ_re, WZ_im, Pen, Lmat, **o):
+        rec.update(WA_re=WA_re, WA_im=WA_im, WZ_re=WZ_re, WZ_im=WZ_im, Pen=Pen, Lmat=Lmat, o=o)
+        raise Abort
+
+    def build_M(freq, eps, order, toeplitz, device=None):
+        return torch.tensor(om.construct_M(np.asarray(freq, dtype=np.float64), order=order, epsilon=float(eps)))
+    monkeypatch.setattr(ridge.capi, 'ridge_fit', ridge_fit)
+    monkeypatch.setattr(ridge.capi, 'build_M', build_M)
+    for kw in (dict(), dict(preset='Huang')):
+        inv = host.Inverter()
+        with pytest.raises(Abort):
+            inv.ridge_fit(freq, Zb, **kw)
+        batch = dict(rec)
+        assert tuple(batch['WA_re'].shape) == (3, 81, 103)
+        for b in range(3):
+            one = host.Inverter()
+            with pytest.raises(Abort):
+                one.ridge_fit(freq[b], Zb[b], **kw)
+            for k in ('WA_re', 'WA_im'):
+                single = rec[k] if rec[k].dim() == 2 else rec[k][0]
+                assert np.max(np.abs(batch[k][b].numpy() - single.numpy())) <= 1e-13 * np.abs(single.numpy()).max(), k
+            for k in ('WZ_re', 'WZ_im'):
+                assert np.allclose(batch[k][b].numpy(), rec[k][0].numpy(), rtol=1e-14, atol=0), k
+            assert np.max(np.abs(batch['Pen'].numpy() - rec['Pen'].numpy())) <= 1e-12 * np.abs(rec['Pen'].numpy()).max()

@@ -25,6 +25,7 @@ CASES = {
     'series_sample': ({'DRT': {'kernel': 'DRT', 'dist_type': 'series'}}, 'Series', 'sample', False),
     'series_out_sample': ({'DRT': {'kernel': 'DRT', 'dist_type': 'series'}}, 'Series', 'sample', True),
     'parallel_opt': ({'TP-DDT': dict(TP)}, 'Parallel', 'optimize', False),
+    'parallel_sample': ({'TP-DDT': dict(TP)}, 'Parallel', 'sample', False),
     'sp_opt': ({'DRT': dict(DRT), 'TP-DDT': dict(TP, x_scale=0.8)}, 'Series-Parallel', 'optimize', False),
     'sp_sample': ({'DRT': dict(DRT), 'TP-DDT': dict(TP, x_scale=0.8)}, 'Series-Parallel', 'sample', False),
     's2p_opt': ({'DRT': dict(DRT), 'TP-DDT': dict(TP, x_scale=0.8), 'BP-DDT': dict(BP)}, 'Series-2Parallel', 'optimize',
@@ -107,6 +108,9 @@ def test_extraction_and_queries_match_the_reference(case):
     assert np.array_equal(idx[:, 1].numpy(), G[p + 'outlier_idx_z1'])
     if p + 'Z_pred_p25' in G.files:  # single- and multi-distribution fits (:2705-2737)
         assert close(inv.predict_Z(F_PRED, percentile=25)[0], G[p + 'Z_pred_p25'], 1e-10)
+    if p + 'sigma_pred_p60' in G.files and p + 'Rp_p75' not in G.files:  # single parallel distribution (:2712-2725)
+        s_re, s_im = inv.predict_sigma(F_PRED, percentile=60)
+        assert close(torch.cat((s_re[0], s_im[0])), G[p + 'sigma_pred_p60'], 1e-10)
     if p + 'Rp_p75' in G.files:
         assert float(inv.predict_Rp(percentile=75)[0]) == pytest.approx(float(G[p + 'Rp_p75']), rel=1e-12)
         s_re, s_im = inv.predict_sigma(inv.f_train, percentile=60)
