@@ -14,7 +14,8 @@ LIB_PATH = os.environ.get('BDRT_LIB') or os.path.join(_HERE, 'libbdrt.so')  # BD
 # symbols declared in include/bdrt.h (tests check that every one is exported)
 SYMBOLS = [
     'bdrt_version', 'bdrt_ctx_create', 'bdrt_ctx_destroy', 'bdrt_last_error', 'bdrt_launch_count',
-    'bdrt_build_A', 'bdrt_build_L', 'bdrt_build_M', 'bdrt_num_params', 'bdrt_num_outputs', 'bdrt_logpost_grad',
+    'bdrt_build_A', 'bdrt_build_L', 'bdrt_build_M', 'bdrt_num_params', 'bdrt_num_outputs', 'bdrt_series_analyze',
+    'bdrt_logpost_grad',
     'bdrt_lbfgs_default_opts', 'bdrt_map_lbfgs', 'bdrt_newton_default_opts', 'bdrt_map_newton',
     'bdrt_nuts_default_opts', 'bdrt_nuts', 'bdrt_constrain', 'bdrt_summarize', 'bdrt_diagnostics', 'bdrt_qp_bound', 'bdrt_ridge_default_opts',
     'bdrt_ridge_fit', 'bdrt_peak_fp64',
@@ -30,6 +31,11 @@ TERM_NAMES = {0: 'running', 10: 'absx', 20: 'absf', 21: 'relf', 30: 'absgrad', 3
               -1: 'lsfail', -2: 'badinit'}
 
 
+class SeriesInfo(C.Structure):
+    _fields_ = [('valid', C.c_int), ('toepA', C.c_int), ('bw', C.c_int * 3), ('toepL', C.c_int * 3),
+                ('taps', C.c_double * 13 * 3 * 3)]
+
+
 class SeriesData(C.Structure):
     _fields_ = [('model', C.c_int), ('Nf', C.c_int), ('K', C.c_int), ('B', C.c_int), ('per_spectrum_grid', C.c_int),
                 ('A', C.c_void_p), ('Z', C.c_void_p), ('freq', C.c_void_p), ('L', C.c_void_p),
@@ -38,7 +44,7 @@ class SeriesData(C.Structure):
                 ('sigma_out_beta', C.c_double),
                 ('Kp', C.c_int), ('Ap', C.c_void_p), ('Lp', C.c_void_p), ('x_sum_invscale', C.c_double),
                 ('xp_scale', C.c_double), ('Kp2', C.c_int), ('Ap2', C.c_void_p), ('Lp2', C.c_void_p),
-                ('xp2_scale', C.c_double)]
+                ('xp2_scale', C.c_double), ('info', C.POINTER(SeriesInfo))]
 
 
 class LbfgsOpts(C.Structure):

@@ -7,7 +7,7 @@ import ctypes as C
 import torch
 
 from . import _lib
-from ._lib import BdrtError, LbfgsOpts, NewtonOpts, NutsOpts, RidgeOpts, SeriesData, context, f64, ptr
+from ._lib import BdrtError, LbfgsOpts, NewtonOpts, NutsOpts, RidgeOpts, SeriesData, SeriesInfo, context, f64, ptr
 
 
 def build_A(freq, tau, epsilon, kernel='DRT', dist_type='series', symmetry='planar', bc='transmissive', ct=False,
@@ -124,6 +124,11 @@ class SeriesProblem:
                 raise ValueError('inconsistent shapes of the second parallel distribution in SeriesProblem')
             d.Kp2, d.Ap2, d.Lp2, d.xp2_scale = self.Kp2, self.Ap2.data_ptr(), self.Lp2.data_ptr(), float(xp2_scale)
         self.c = d
+        # structure of the matrices (Toeplitz / band flags, taps), found once: the solver calls then only enqueue work
+        self.info = SeriesInfo()
+        if self.B > 0:
+            self.ctx.check(self.ctx.lib.bdrt_series_analyze(self.ctx._h, C.byref(d), C.byref(self.info)))
+            d.info = C.pointer(self.info)
         self.nonneg, self.outliers = bool(nonneg), bool(outliers)
         self.D = int(self.ctx.lib.bdrt_num_params(C.byref(d)))
         self.P = int(self.ctx.lib.bdrt_num_outputs(C.byref(d)))

@@ -354,7 +354,7 @@ __device__ inline void engine_load_slot(const BdrtModel& m, double* sm, long lon
 // 3 Series-2Parallel: fixes the number of distributions and which of them are parallel at compile time); FAST
 // register-tiled per-slot phases.
 template <int TOEP, int MK, int FAST>
-__device__ inline double engine_eval(const BdrtModel& m, double* sm, bool active, const double* u, double* grad,
+__device__ __forceinline__ double engine_eval(const BdrtModel& m, double* sm, bool active, const double* u, double* grad,
                                      const double* Zs, int jacobian, const volatile int* nact = nullptr,
                                      int* snap = nullptr) {
   constexpr int ND = MK == 0 ? 1 : MK;
@@ -1215,7 +1215,9 @@ __device__ inline double engine_eval(const BdrtModel& m, double* sm, bool active
 // allow_wmode: 0 the calling kernel only has the cooperative instantiations (engine_eval<0 / 1, ..>: Newton);
 // 1 it has all three (the log_prob test hook: warp mode whenever the operands are Toeplitz, BDRT_COOP=1 in the
 // environment selects the cooperative Toeplitz products instead, so that the tests cover them);
-// 2 it has warp mode and the dense layout only (the L-BFGS and NUTS drivers: BDRT_COOP is ignored)
+// 2 it has warp mode and the dense layout only (the NUTS driver: BDRT_COOP is ignored);
+// 3 it has all three and prefers the cooperative products when the grid is shared (the L-BFGS driver: see the note in
+//   bdrt_model_prepare; per-spectrum grids use warp mode, eight spectra with their own tables per CTA)
 int bdrt_model_prepare(bdrt_ctx* ctx, const bdrt_series_data* data, BdrtModel* m, size_t extra_ws_bytes,
                        void** extra_ws, int allow_wmode = 0);
 

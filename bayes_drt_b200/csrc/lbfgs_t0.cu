@@ -1,0 +1,7 @@
+// Explicit instantiations of lbfgs_kernel for resident-operand layout TOEP = 0 (see lbfgs_kernel.cuh).
+#include "lbfgs_kernel.cuh"
+
+template __global__ void lbfgs_kernel<0, 0, 0>(BdrtModel, bdrt_lbfgs_opts, double*, double*, int*, int*, int*, int*, double*, double*, int, int);
+template __global__ void lbfgs_kernel<0, 1, 0>(BdrtModel, bdrt_lbfgs_opts, double*, double*, int*, int*, int*, int*, double*, double*, int, int);
+template __global__ void lbfgs_kernel<0, 2, 0>(BdrtModel, bdrt_lbfgs_opts, double*, double*, int*, int*, int*, int*, double*, double*, int, int);
+template __global__ void lbfgs_kernel<0, 3, 0>(BdrtModel, bdrt_lbfgs_opts, double*, double*, int*, int*, int*, int*, double*, double*, int, int);

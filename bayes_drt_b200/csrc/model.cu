@@ -139,8 +139,7 @@ __global__ void toep_check_kernel(const double* A0, long long stride, int Nf, in
   if (!ok) atomicAnd(&info[2], 0);
 }
 
-int bdrt_model_prepare(bdrt_ctx* ctx, const bdrt_series_data* d, BdrtModel* m, size_t extra_ws_bytes,
-                       void** extra_ws, int allow_wmode) {
+static int bdrt_check_data(bdrt_ctx* ctx, const bdrt_series_data* d, int* nd_out) {
   if (!d) BDRT_FAIL(ctx, BDRT_E_NULL, "null data");
   if (!d->A || !d->Z || !d->freq || !d->L) BDRT_FAIL(ctx, BDRT_E_NULL, "bdrt_series_data: null matrix pointer");
   const int base = d->model & 15;
@@ -166,6 +165,83 @@ int bdrt_model_prepare(bdrt_ctx* ctx, const bdrt_series_data* d, BdrtModel* m, s
   }
   if (!(d->sigma_min >= 0) || !(d->ups_alpha > 0) || !(d->ups_beta > 0) || !(d->induc_scale > 0))
     BDRT_FAIL(ctx, BDRT_E_SIZE, "model constants must be positive");
+  *nd_out = nd;
+  return BDRT_OK;
+}
+
+// workspace layout shared by the analysis and by every solver call: [info (256 B) | Lb of every distribution | extra]
+static size_t bdrt_lb_offsets(const bdrt_series_data* d, int nd, size_t* lb_off) {
+  const int Ks[MAXD] = {d->K, d->Kp, d->Kp2};
+  size_t head = 256;
+  for (int i = 0; i < nd; ++i) {
+    lb_off[i] = head;
+    head += ((size_t)3 * Ks[i] * LBW * sizeof(double) + 255) & ~(size_t)255;
+  }
+  return head;
+}
+
+// The structure of the matrices (bandwidth / Toeplitz flags / taps): device kernels, then two read-backs that wait
+// for the stream.  Done once per problem by bdrt_series_analyze, or per call when the caller passes no info.
+static int bdrt_analyze(bdrt_ctx* ctx, const bdrt_series_data* d, int nd, bdrt_series_info* out) {
+  const int Ks[MAXD] = {d->K, d->Kp, d->Kp2};
+  const double* As[MAXD] = {d->A, d->Ap, d->Ap2};
+  const double* Ls[MAXD] = {d->L, d->Lp, d->Lp2};
+  size_t lb_off[MAXD];
+  const size_t head = bdrt_lb_offsets(d, nd, lb_off);
+  int rc = bdrt_ws_reserve(ctx, head);
+  if (rc) return rc;
+  int* info = (int*)ctx->ws;
+  const int init[12] = {0, 1, 1, 0, 0, 1, 0, 0, 0, 1, 0, 0};  // per distribution i: info[4i] = bw, info[4i+1] = L Toeplitz
+  BDRT_CUDA(ctx, cudaMemcpyAsync(info, init, sizeof(init), cudaMemcpyHostToDevice, ctx->stream));
+  for (int i = 0; i < nd; ++i) {
+    double* Lb = (double*)((char*)ctx->ws + lb_off[i]);
+    band_prep_kernel<<<3, 256, 0, ctx->stream>>>(Ls[i], Ks[i], Lb, info + 4 * i);
+    ctx->launches++;
+    if (d->B > 0) {
+      const long long stride = d->per_spectrum_grid ? (long long)2 * d->Nf * Ks[i] : 0;
+      toep_check_kernel<<<d->per_spectrum_grid ? d->B : 1, 512, 0, ctx->stream>>>(As[i], stride, d->Nf, Ks[i], info);
+      ctx->launches++;
+    }
+  }
+  BDRT_CUDA(ctx, cudaGetLastError());
+  int hinfo[12];
+  BDRT_CUDA(ctx, cudaMemcpyAsync(hinfo, info, sizeof(hinfo), cudaMemcpyDeviceToHost, ctx->stream));
+  BDRT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  memset(out, 0, sizeof(*out));
+  out->toepA = hinfo[2];
+  for (int i = 0; i < nd; ++i) {
+    out->bw[i] = hinfo[4 * i];
+    out->toepL[i] = hinfo[4 * i + 1];
+    if (hinfo[4 * i] <= MAXBW && Ks[i] >= 2 * FBW + 1) {  // taps = row K/2 of the banded copies
+      const double* Lb = (const double*)((char*)ctx->ws + lb_off[i]);
+      double row[3][LBW];
+      for (int j = 0; j < 3; ++j)
+        BDRT_CUDA(ctx, cudaMemcpyAsync(row[j], Lb + ((size_t)j * Ks[i] + Ks[i] / 2) * LBW, LBW * sizeof(double),
+                                       cudaMemcpyDeviceToHost, ctx->stream));
+      BDRT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+      for (int j = 0; j < 3; ++j)
+        for (int t = 0; t < 2 * FBW + 1; ++t) out->taps[i][j][t] = row[j][MAXBW - FBW + t];
+    }
+  }
+  out->valid = 1;
+  return BDRT_OK;
+}
+
+extern "C" int bdrt_series_analyze(bdrt_ctx* ctx, const bdrt_series_data* data, bdrt_series_info* info) {
+  if (!ctx) return BDRT_E_NULL;
+  if (!info) BDRT_FAIL(ctx, BDRT_E_NULL, "bdrt_series_analyze: null info");
+  int nd = 0;
+  int rc = bdrt_check_data(ctx, data, &nd);
+  if (rc) return rc;
+  return bdrt_analyze(ctx, data, nd, info);
+}
+
+int bdrt_model_prepare(bdrt_ctx* ctx, const bdrt_series_data* d, BdrtModel* m, size_t extra_ws_bytes,
+                       void** extra_ws, int allow_wmode) {
+  int nd = 0;
+  int rc = bdrt_check_data(ctx, d, &nd);
+  if (rc) return rc;
+  const int base = d->model & 15;
   memset(m, 0, sizeof(*m));
   m->flags = ((d->model & BDRT_MODEL_POS) ? F_POS : 0) | ((d->model & BDRT_MODEL_OUTLIERS) ? F_OUT : 0);
   m->ND = nd;
@@ -207,47 +283,40 @@ int bdrt_model_prepare(bdrt_ctx* ctx, const bdrt_series_data* d, BdrtModel* m, s
   m->so_lambda = d->sigma_out_lambda;
   m->so_alpha = d->sigma_out_alpha;
   m->so_beta = d->sigma_out_beta;
-  // workspace: [info (256 B) | Lb of every distribution | extra]
-  size_t lb_off[MAXD], head = 256;
-  for (int i = 0; i < nd; ++i) {
-    lb_off[i] = head;
-    head += ((size_t)3 * Ks[i] * LBW * sizeof(double) + 255) & ~(size_t)255;
+  // structure of the matrices: from the caller (bdrt_series_analyze, no synchronisation here) or found now
+  bdrt_series_info local;
+  const bdrt_series_info* si = d->info;
+  if (!si || !si->valid) {
+    rc = bdrt_analyze(ctx, d, nd, &local);
+    if (rc) return rc;
+    si = &local;
   }
-  int rc = bdrt_ws_reserve(ctx, head + extra_ws_bytes);
+  size_t lb_off[MAXD];
+  const size_t head = bdrt_lb_offsets(d, nd, lb_off);
+  rc = bdrt_ws_reserve(ctx, head + extra_ws_bytes);
   if (rc) return rc;
-  int* info = (int*)ctx->ws;
-  // BDRT_FORCE_DENSE=1 keeps the dense-resident A path even for Toeplitz grids (used by the tests to cover both)
-  const char* fd = getenv("BDRT_FORCE_DENSE");
-  const int try_toep = !(fd && fd[0] == '1');
-  const int init[12] = {0, 1, try_toep, 0, 0, 1, 0, 0, 0, 1, 0, 0};  // per distribution i: info[4i] = bw, info[4i+1] = L Toeplitz
-  BDRT_CUDA(ctx, cudaMemcpyAsync(info, init, sizeof(init), cudaMemcpyHostToDevice, ctx->stream));
+  // banded copies of the penalty matrices (device work only; the flags it recomputes are not read back)
   for (int i = 0; i < nd; ++i) {
     double* Lb = (double*)((char*)ctx->ws + lb_off[i]);
-    band_prep_kernel<<<3, 256, 0, ctx->stream>>>(Ls[i], Ks[i], Lb, info + 4 * i);
+    band_prep_kernel<<<3, 256, 0, ctx->stream>>>(Ls[i], Ks[i], Lb, (int*)ctx->ws + 4 * i);
     ctx->launches++;
     m->d[i].Lb = Lb;
-    if (try_toep && d->B > 0) {
-      toep_check_kernel<<<d->per_spectrum_grid ? (d->B > 0 ? d->B : 1) : 1, 512, 0, ctx->stream>>>(
-          As[i], m->d[i].A_stride, d->Nf, Ks[i], info);
-      ctx->launches++;
-    }
   }
   BDRT_CUDA(ctx, cudaGetLastError());
-  int hinfo[12];
-  BDRT_CUDA(ctx, cudaMemcpyAsync(hinfo, info, sizeof(hinfo), cudaMemcpyDeviceToHost, ctx->stream));
-  BDRT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   int bw = 0;
   for (int i = 0; i < nd; ++i) {
-    if (hinfo[4 * i] > MAXBW)
+    if (si->bw[i] > MAXBW)
       BDRT_FAIL(ctx, BDRT_E_UNSUPPORTED,
                 "penalty matrices L0/L1/L2 are not banded within %d off-diagonals (found %d): epsilon is too small "
                 "relative to the basis spacing for this build",
-                MAXBW, hinfo[4 * i]);
-    if (hinfo[4 * i] > bw) bw = hinfo[4 * i];
+                MAXBW, si->bw[i]);
+    if (si->bw[i] > bw) bw = si->bw[i];
   }
   m->bw = bw;
-  for (int i = 0; i < nd; ++i) m->d[i].toepL = hinfo[4 * i + 1] && (Ks[i] >= 2 * bw + 1);
-  m->toepA = hinfo[2];
+  for (int i = 0; i < nd; ++i) m->d[i].toepL = si->toepL[i] && (Ks[i] >= 2 * bw + 1);
+  // BDRT_FORCE_DENSE=1 keeps the dense-resident A path even for Toeplitz grids (used by the tests to cover both)
+  const char* fd = getenv("BDRT_FORCE_DENSE");
+  m->toepA = si->toepA && !(fd && fd[0] == '1');
 #ifdef BDRT_PHASE_CLOCKS
   if (!ctx->dbg_clk) {
     BDRT_CUDA(ctx, cudaMalloc(&ctx->dbg_clk, 16 * sizeof(unsigned long long)));
@@ -255,24 +324,25 @@ int bdrt_model_prepare(bdrt_ctx* ctx, const bdrt_series_data* d, BdrtModel* m, s
   }
   m->dbg_clk = ctx->dbg_clk;
 #endif
+  // which Toeplitz engine: warp mode (no CTA rendezvous, per-slot tables) or the cooperative products (8 warps in
+  // lockstep -- they share instruction-cache lines, which the 250 kB L-BFGS kernel needs more than it minds the barriers:
+  // measured +8 % on the benchmark batch, +14 % at uniform work; NUTS is 2 % faster in warp mode).  BDRT_COOP=1 /
+  // BDRT_WARP=1 override the default where the kernel has both instantiations (A/B measurements, tests).
   const char* fc = getenv("BDRT_COOP");
-  m->wmode = m->toepA && allow_wmode && !(allow_wmode == 1 && fc && fc[0] == '1');
+  const char* fw = getenv("BDRT_WARP");
+  const bool force_coop = fc && fc[0] == '1', force_warp = fw && fw[0] == '1';
+  m->wmode = m->toepA && allow_wmode && !((allow_wmode == 1 || allow_wmode == 3) && force_coop);
+  if (allow_wmode == 3 && !d->per_spectrum_grid && !force_warp) m->wmode = 0;
   m->pslot = m->wmode && d->per_spectrum_grid;
   // register-tiled per-slot phases: every distribution has Toeplitz L within FBW off-diagonals and K <= 128
   // (BDRT_FORCE_GENERIC=1 keeps the generic per-slot code, for tests)
   const char* fg = getenv("BDRT_FORCE_GENERIC");
   m->fast = m->toepA && bw <= FBW && !(fg && fg[0] == '1');
   for (int i = 0; i < nd; ++i) m->fast = m->fast && m->d[i].toepL && Ks[i] <= 128 && Ks[i] >= 2 * FBW + 1;
-  if (m->fast) {  // taps = row K/2 of the banded copies, into the kernel parameter bank
-    for (int i = 0; i < nd; ++i) {
-      double row[3][LBW];
+  if (m->fast) {  // taps into the kernel parameter bank
+    for (int i = 0; i < nd; ++i)
       for (int j = 0; j < 3; ++j)
-        BDRT_CUDA(ctx, cudaMemcpyAsync(row[j], m->d[i].Lb + ((size_t)j * Ks[i] + Ks[i] / 2) * LBW, LBW * sizeof(double),
-                                       cudaMemcpyDeviceToHost, ctx->stream));
-      BDRT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-      for (int j = 0; j < 3; ++j)
-        for (int t = 0; t < 2 * FBW + 1; ++t) m->d[i].tapc[j][t] = row[j][MAXBW - FBW + t];
-    }
+        for (int t = 0; t < 2 * FBW + 1; ++t) m->d[i].tapc[j][t] = si->taps[i][j][t];
   }
   const int eng = bdrt_model_layout(m);
   if ((size_t)eng * 8 > (size_t)ctx->smem_optin)

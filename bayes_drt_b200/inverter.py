@@ -246,10 +246,11 @@ class Inverter:
             init_from_ridge=False, ridge_kw={}, sigma_min=0.002, inductance_scale=1, outlier_lambda=None,
             mode='optimize', random_seed=1234, max_iter=50000, warmup=200, samples=200, chains=2,
             add_stan_data={}, model_str=None, fitY=False, SA=False, SASY=False,
-            init=None, polish=False, spectrum_offset=0, keep_draws=True):
+            init=None, polish=False, spectrum_offset=0, spectrum_ids=None, keep_draws=True):
         """Same arguments as the reference plus: ``init`` (explicit unconstrained initial points [B, D] or
         [B, chains, D]; Stan accepts an init dict the same way), ``polish`` (damped-Newton refinement of the MAP
-        estimate to the exact optimum), ``spectrum_offset`` (global index of the first spectrum, for sharded batches),
+        estimate to the exact optimum), ``spectrum_offset`` (global index of the first spectrum, for sharded batches) or
+        ``spectrum_ids`` (global index of every spectrum: strided shards, ``distributed.shard_indices``),
         ``keep_draws`` (keep the HMC draws for percentile queries)."""
         if part != 'both':
             raise NotImplementedError("part != 'both' is not implemented (and is inconsistent in the reference's "
@@ -274,7 +275,7 @@ class Inverter:
         freq, Zb = self._to_batch(frequencies, Z)
         single = self._single
         B = Zb.shape[0]
-        ids = torch.arange(spectrum_offset, spectrum_offset + B, dtype=torch.int64, device=self.device)
+        ids = self._global_ids(B, spectrum_offset, spectrum_ids)
         # ---- ridge initialisation and automatic outlier detection (inversion.py:1154-1187)
         ridge_init, flags, init_flags = None, None, None
         if init_from_ridge:
@@ -351,7 +352,8 @@ class Inverter:
                                   "reference (its Stan file is not shipped) and is not implemented")
 
     def prepare(self, frequencies, Z, mode='optimize', nonneg=False, outliers=False, scale_Z=True, sigma_min=0.002,
-                inductance_scale=1, outlier_lambda=None, random_seed=1234, chains=2, spectrum_offset=0):
+                inductance_scale=1, outlier_lambda=None, random_seed=1234, chains=2, spectrum_offset=0,
+                spectrum_ids=None):
         """Everything ``fit`` does before it calls a solver, as a public hook (bench.py times the solver alone with it):
         sorting, scaling, kernel / penalty matrices, the Stan data of the selected program, Stan-style random initial
         points.  Returns (problem, u0): a ``capi.SeriesProblem`` (``map_lbfgs`` / ``map_newton`` / ``nuts`` /
@@ -364,12 +366,20 @@ class Inverter:
         self.f_train, self.Z_train = freq.numpy(), Zb
         Zs = self._scale_Z(Zb, scale_Z, fit_type='map' if mode == 'optimize' else 'bayes')
         B = Zs.shape[0]
-        ids = torch.arange(spectrum_offset, spectrum_offset + B, dtype=torch.int64, device=self.device)
+        ids = self._global_ids(B, spectrum_offset, spectrum_ids)
         prob = self._build_problem(freq, Zs, model_type, name, par, mode, nonneg, bool(outliers), sigma_min,
                                    inductance_scale, outlier_lambda)
         nch = 1 if mode == 'optimize' else chains
         u0 = self._initial_points(prob, ids, nch, random_seed, 0)
         return prob, (u0.reshape(B, prob.D) if mode == 'optimize' else u0)
+
+    def _global_ids(self, B, spectrum_offset, spectrum_ids):
+        if spectrum_ids is None:
+            return torch.arange(spectrum_offset, spectrum_offset + B, dtype=torch.int64, device=self.device)
+        ids = torch.as_tensor(spectrum_ids, dtype=torch.int64, device=self.device).reshape(-1)
+        if ids.shape[0] != B:
+            raise ValueError(f'spectrum_ids must have one entry per spectrum ({B})')
+        return ids
 
     def _build_problem(self, freq, Zs, model_type, name, par, mode, nonneg, outliers, sigma_min, inductance_scale,
                        outlier_lambda):

@@ -104,6 +104,18 @@ int bdrt_build_M(bdrt_ctx* ctx, const double* freq, int n_grids, int K, double e
  * One bdrt_series_data describes a batch of B spectra fitted with one Stan program of the 'Series' family
  * (single DRT).  Matrices are those of _prep_stan_data: A = [A_re; A_im] stacked (2Nf x K), Z = [Z'; Z''] of the
  * *scaled* spectrum, L0/L1/L2 already multiplied by the per-mode constants. */
+/* Structure of the matrices of a problem, found once by bdrt_series_analyze (which waits for the device) and handed
+ * back through bdrt_series_data.info: with it every solver call below only enqueues work on the context's stream; without
+ * it (info == NULL) each call repeats the analysis and synchronises the stream twice while doing so. */
+#define BDRT_INFO_TAPS 13 /* Toeplitz taps kept per penalty matrix: |n - m| <= 6 (the reference's default epsilon) */
+typedef struct {
+  int valid;    /* set by bdrt_series_analyze */
+  int toepA;    /* every kernel matrix is Toeplitz in each part (log-uniform grids of equal spacing, matrices.py:145-242) */
+  int bw[3];    /* per distribution: half bandwidth of L0/L1/L2 (entries below 1e-18 of the largest dropped) */
+  int toepL[3]; /* per distribution: L0/L1/L2 are Toeplitz */
+  double taps[3][3][BDRT_INFO_TAPS]; /* per distribution and derivative order: the taps L[K/2][K/2 - 6 .. K/2 + 6] */
+} bdrt_series_info;
+
 typedef struct {
   int model;  /* BDRT_MODEL_SERIES [| BDRT_MODEL_POS] [| BDRT_MODEL_OUTLIERS] */
   int Nf;     /* measured frequencies per spectrum */
@@ -128,7 +140,12 @@ typedef struct {
   const double* Ap2;  /* [2Nf,Kp2] or [B,2Nf,Kp2] */
   const double* Lp2;  /* [3,Kp2,Kp2] */
   double xp2_scale;
+  const bdrt_series_info* info; /* HOST pointer, result of bdrt_series_analyze for these matrices; NULL: analyse per call */
 } bdrt_series_data;
+
+/* Looks at A / L (/ Ap, Lp, Ap2, Lp2) of `data` on the device and fills *info (host memory).  Synchronises the context's
+ * stream.  The result stays valid as long as the matrices keep their contents and shapes. */
+int bdrt_series_analyze(bdrt_ctx* ctx, const bdrt_series_data* data, bdrt_series_info* info);
 
 /* number of unconstrained parameters D of the model: Series 2K+9 (+2Nf with outliers);
  * Series-Parallel 2(Ks+Kp)+12; Series-2Parallel 2(Ks+Kp1+Kp2)+15 */

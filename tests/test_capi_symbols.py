@@ -60,7 +60,8 @@ def test_ctypes_structs_mirror_the_header():
     """The ctypes Structures the Python host passes by reference must have the header's fields in the header's order."""
     from bayes_drt_b200 import _lib
     hdr = open(os.path.join(ROOT, 'include', 'bdrt.h')).read()
-    for cname, cls in (('bdrt_series_data', _lib.SeriesData), ('bdrt_lbfgs_opts', _lib.LbfgsOpts),
+    for cname, cls in (('bdrt_series_info', _lib.SeriesInfo), ('bdrt_series_data', _lib.SeriesData),
+                       ('bdrt_lbfgs_opts', _lib.LbfgsOpts),
                        ('bdrt_newton_opts', _lib.NewtonOpts), ('bdrt_nuts_opts', _lib.NutsOpts),
                        ('bdrt_ridge_opts', _lib.RidgeOpts)):
         assert _struct_fields(hdr, cname) == [f[0] for f in cls._fields_], cname

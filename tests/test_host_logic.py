@@ -34,6 +34,44 @@ def _worker(rank, ws, port, q):
     dist.destroy_process_group()
 
 
+def test_shard_indices_strided_and_block():
+    from bayes_drt_b200.distributed import shard_indices, shard_range
+    for n in (0, 1, 7, 11, 1000):
+        for ws in (1, 2, 3, 8):
+            parts = [shard_indices(n, k, ws) for k in range(ws)]
+            assert sorted(sum((p.tolist() for p in parts), [])) == list(range(n))
+            assert all(p.tolist() == list(range(k, n, ws)) for k, p in enumerate(parts))
+            assert max(len(p) for p in parts) - min(len(p) for p in parts) <= 1
+            for k in range(ws):
+                a, b = shard_range(n, k, ws)
+                assert shard_indices(n, k, ws, mode='block').tolist() == list(range(a, b))
+
+
+def _worker_strided(rank, ws, port, q):
+    sys.path.insert(0, ROOT)
+    import torch.distributed as dist
+    from bayes_drt_b200.distributed import gather_results, shard_indices
+    dist.init_process_group('gloo', init_method=f'tcp://127.0.0.1:{port}', rank=rank, world_size=ws)
+    n_total = 11  # ragged: rank 0 holds 6 rows, rank 1 holds 5
+    idx = shard_indices(n_total)
+    local = idx.to(torch.float64)[:, None] * torch.ones(1, 3, dtype=torch.float64)
+    out = gather_results(local, n_total, indices=idx)
+    q.put((rank, out[:, 0].tolist()))
+    dist.destroy_process_group()
+
+
+def test_gather_results_strided_world2_gloo():
+    ctx = mp.get_context('spawn')
+    q = ctx.Queue()
+    port = 31500 + os.getpid() % 2000
+    ps = [ctx.Process(target=_worker_strided, args=(r, 2, port, q)) for r in range(2)]
+    [p.start() for p in ps]
+    res = [q.get(timeout=120) for _ in range(2)]
+    [p.join(60) for p in ps]
+    for rank, vals in res:
+        assert vals == [float(i) for i in range(11)]
+
+
 def test_gather_results_world2_gloo():
     ctx = mp.get_context('spawn')
     q = ctx.Queue()
