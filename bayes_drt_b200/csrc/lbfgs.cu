@@ -46,7 +46,7 @@ extern "C" int bdrt_map_lbfgs(bdrt_ctx* ctx, const bdrt_series_data* data, const
     if (!data) BDRT_FAIL(ctx, BDRT_E_NULL, "null data");
   }
   const int D = bdrt_num_params(data);
-  const int Dpad = (D + 1) & ~1;
+  const int Dpad = (D + 223) / 224 * 224;  // zero-padded work vectors: the sweeps of the kernel have no bounds checks
   const int max_ctas = 2 * ctx->sm_count;  // scratch is sized for the two-CTAs-per-SM (Toeplitz) plan
   const int groups = data->per_spectrum_grid ? data->B : (data->B + NSLOT - 1) / NSLOT;
   const int grid_max = data->B == 0 ? 0 : (groups < max_ctas ? groups : max_ctas);

@@ -88,7 +88,7 @@ __device__ __forceinline__ double two_loop(const double* S, const double* Y, con
 #pragma unroll
   for (int c = 0; c < NCC; ++c) {
     const int i = lane + 32 * c;
-    pr[c] = (i < D) ? -gk[i] : 0.0;
+    pr[c] = -gk[i];
   }
   // history entry -> registers (both vectors of the entry in one go: one L2 round trip)
   auto fetch = [&](int h, double (&sv)[NCC], double (&yv)[NCC]) {
@@ -97,8 +97,8 @@ __device__ __forceinline__ double two_loop(const double* S, const double* Y, con
 #pragma unroll
     for (int c = 0; c < NCC; ++c) {
       const int i = lane + 32 * c;
-      sv[c] = (i < D) ? Sh[i] : 0.0;
-      yv[c] = (i < D) ? Yh[i] : 0.0;
+      sv[c] = Sh[i];
+      yv[c] = Yh[i];
     }
   };
   auto hidx = [&](int j) { return head - 1 - j + (head - 1 - j < 0 ? H : 0); };  // j < nh <= H
@@ -139,10 +139,8 @@ __device__ __forceinline__ double two_loop(const double* S, const double* Y, con
 #pragma unroll
   for (int c = 0; c < NCC; ++c) {
     const int i = lane + 32 * c;
-    if (i < D) {
-      pk[i] = pr[c];
-      gp = fma(gk[i], pr[c], gp);
-    }
+    pk[i] = pr[c];
+    gp = fma(gk[i], pr[c], gp);
   }
   __syncwarp();
   return warp_sum(gp);
@@ -156,7 +154,8 @@ lbfgs_kernel(BdrtModel m, bdrt_lbfgs_opts o, double* __restrict__ U, double* lp_
              int* status_out, int* queue, double* hist, double* gvec, int nvec_smem, int Dpad) {
   extern __shared__ __align__(16) double sm[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int D = m.D;
+  const int Dtrue = m.D;
+  const int D = Dpad;  // every work vector is zero-padded to a multiple of 224 coordinates: no sweep has a bounds check
   const int H = o.history;
   volatile int* n_active = (volatile int*)(sm + m.oUser);
   double* suser = sm + m.oUser + 2;
@@ -210,8 +209,14 @@ lbfgs_kernel(BdrtModel m, bdrt_lbfgs_opts o, double* __restrict__ U, double* lp_
 
   auto run_spectrum = [&](int b) {
     Zs = m.Z + (long long)b * m.N2;
-    double* ub = U + (long long)b * D;
-    for (int i = lane; i < D; i += 32) { xn[i] = ub[i]; pk[i] = 0.0; }  // pk: read (unused) by the first evaluation
+    double* ub = U + (long long)b * Dtrue;
+    for (int i = lane; i < D; i += 32) {  // zero padding of every vector; pk is read (unused) by the first evaluation
+      xn[i] = i < Dtrue ? ub[i] : 0.0;
+      gn[i] = 0.0;
+      pk[i] = 0.0;
+      xk[i] = 0.0;
+      gk[i] = 0.0;
+    }
     __syncwarp();
     neval = 0;
     double fk = nan("");
@@ -345,7 +350,14 @@ lbfgs_kernel(BdrtModel m, bdrt_lbfgs_opts o, double* __restrict__ U, double* lp_
           ss = fma(s, s, ss);
           gg = fma(gv, gv, gg);
         }
-        skyk = warp_sum(skyk); yy = warp_sum(yy); ss = warp_sum(ss); gg = warp_sum(gg);
+        {  // one batched butterfly: value i ends up in lanes 8 i .. 8 i + 7
+          double four[4] = {skyk, yy, ss, gg};
+          const double tot = warp_sum_multi<4>(four, lane);
+          skyk = __shfl_sync(0xffffffffu, tot, 0);
+          yy = __shfl_sync(0xffffffffu, tot, 8);
+          ss = __shfl_sync(0xffffffffu, tot, 16);
+          gg = __shfl_sync(0xffffffffu, tot, 24);
+        }
         const double gradNorm = sqrt(gg), stepNorm = sqrt(ss);
         dfp_new = newDFp;
         if (reset) {
@@ -370,10 +382,10 @@ lbfgs_kernel(BdrtModel m, bdrt_lbfgs_opts o, double* __restrict__ U, double* lp_
         __threadfence_block();
         // ---------------- two-loop recursion -> pk
         double gp;
-        if (D <= 32 * 7)
+        if (D == 32 * 7)
           gp = two_loop<7>(S, Y, rho, al, gn, pk, D, Dpad, nh, head, H, gamma, lane);
-        else if (D <= 32 * 12)
-          gp = two_loop<12>(S, Y, rho, al, gn, pk, D, Dpad, nh, head, H, gamma, lane);
+        else if (D == 32 * 14)
+          gp = two_loop<14>(S, Y, rho, al, gn, pk, D, Dpad, nh, head, H, gamma, lane);
         else
           gp = two_loop<0>(S, Y, rho, al, gn, pk, D, Dpad, nh, head, H, gamma, lane);
         // ---------------- convergence tests, Stan's order
@@ -392,7 +404,7 @@ lbfgs_kernel(BdrtModel m, bdrt_lbfgs_opts o, double* __restrict__ U, double* lp_
         else if (it >= o.max_iter)
           code = BDRT_TERM_MAXIT;
       }
-      for (int i = lane; i < D; i += 32) ub[i] = xk[i];
+      for (int i = lane; i < Dtrue; i += 32) ub[i] = xk[i];
     }
     if (lane == 0) {
       if (lp_out) lp_out[b] = -fk;
