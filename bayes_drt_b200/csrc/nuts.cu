@@ -46,7 +46,7 @@ extern "C" int bdrt_nuts(bdrt_ctx* ctx, const bdrt_series_data* data, const bdrt
   if (opts->max_treedepth < 1 || opts->max_treedepth > MAXDEPTH)
     BDRT_FAIL(ctx, BDRT_E_SIZE, "max_treedepth must be in 1..%d", MAXDEPTH);
   const int D = bdrt_num_params(data);
-  const int Dpad = (D + 1) & ~1;
+  const int Dpad = (D + 223) / 224 * 224;  // zero-padded work vectors: the hot sweeps of the kernel have no bounds checks
   const long long n_work = (long long)data->B * opts->chains;
   if (n_work > 2000000000LL) BDRT_FAIL(ctx, BDRT_E_SIZE, "too many chains in one call");
   const long long groups = data->per_spectrum_grid ? data->B : (n_work + NSLOT - 1) / NSLOT;

@@ -20,6 +20,12 @@
 #define NV 15  // per-slot work vectors
 enum { V_ZQ, V_ZP, V_ZG, V_RSUB, V_MINV, V_RHO, V_OQ, V_OP, V_OG, V_SQ, V_SG, V_PQ, V_PG, V_WMEAN, V_WM2 };
 #define MAXDEPTH 12
+#define NCHN 7  // columns per lane and sweep chunk
+// Sweep over a work vector: every vector is zero-padded to a multiple of 32 * NCHN coordinates (Dpad), so the hot sweeps
+// have no bounds checks and unroll into NCHN independent element operations per lane
+#define NUTS_SWEEP(i)                                             \
+  for (int i0_ = lane; i0_ < Dpad; i0_ += 32 * NCHN)             \
+    _Pragma("unroll") for (int c_ = 0, i = i0_; c_ < NCHN; ++c_, i += 32)
 
 namespace {
 
@@ -91,7 +97,7 @@ nuts_kernel(BdrtModel m, bdrt_nuts_opts o, const double* __restrict__ U0, double
   auto leapfrog = [&](double eps) -> double {
     double *q = v[V_ZQ], *p = v[V_ZP], *g = v[V_ZG];
     const double* mi = v[V_MINV];
-    for (int i = lane; i < D; i += 32) {
+    NUTS_SWEEP(i) {
       const double pi = fma(0.5 * eps, g[i], p[i]);
       p[i] = pi;
       q[i] = fma(eps * mi[i], pi, q[i]);
@@ -100,7 +106,7 @@ nuts_kernel(BdrtModel m, bdrt_nuts_opts o, const double* __restrict__ U0, double
     const double lp = engine_eval<TOEP, MK, FAST>(m, sm, true, q, g, Zs, 1);
     ++n_grad;
     double ks = 0.0;
-    for (int i = lane; i < D; i += 32) {
+    NUTS_SWEEP(i) {
       const double pi = fma(0.5 * eps, g[i], p[i]);
       p[i] = pi;
       ks = fma(mi[i] * pi, pi, ks);
@@ -112,11 +118,11 @@ nuts_kernel(BdrtModel m, bdrt_nuts_opts o, const double* __restrict__ U0, double
   auto kinetic = [&](const double* p) -> double {
     const double* mi = v[V_MINV];
     double s = 0.0;
-    for (int i = lane; i < D; i += 32) s = fma(mi[i] * p[i], p[i], s);
+    NUTS_SWEEP(i) s = fma(mi[i] * p[i], p[i], s);
     return 0.5 * warp_sum(s);
   };
   auto vcopy = [&](double* dst, const double* src) {
-    for (int i = lane; i < D; i += 32) dst[i] = src[i];
+    NUTS_SWEEP(i) dst[i] = src[i];
   };
 
   // one adaptive chain: work item wi = spectrum * chains + chain
@@ -131,8 +137,11 @@ nuts_kernel(BdrtModel m, bdrt_nuts_opts o, const double* __restrict__ U0, double
     n_grad = 0;
 
     // ---- initial point
-    vcopy(v[V_SQ], U0 + wi * D);
-    for (int i = lane; i < D; i += 32) v[V_MINV][i] = 1.0;
+    for (int i = lane; i < Dpad; i += 32) {  // zero padding of every work vector (the metric's is 1)
+      for (int k = 0; k < NV; ++k) v[k][i] = 0.0;
+      v[V_SQ][i] = i < D ? U0[wi * D + i] : 0.0;
+      v[V_MINV][i] = 1.0;
+    }
     __syncwarp();
     double s_lp = engine_eval<TOEP, MK, FAST>(m, sm, true, v[V_SQ], v[V_SG], Zs, 1);
     ++n_grad;
@@ -160,6 +169,7 @@ nuts_kernel(BdrtModel m, bdrt_nuts_opts o, const double* __restrict__ U0, double
         vcopy(v[V_ZQ], v[V_SQ]);
         vcopy(v[V_ZG], v[V_SG]);
         for (int i = lane; i < D; i += 32) v[V_ZP][i] = rng.normal(0xffffffffu, hdraw * 4096u + i, 2) * rsqrt(v[V_MINV][i]);
+        // (the padding of V_ZP stays 0)
         ++hdraw;
         __syncwarp();
         const double H0 = -s_lp + kinetic(v[V_ZP]);
@@ -193,8 +203,8 @@ nuts_kernel(BdrtModel m, bdrt_nuts_opts o, const double* __restrict__ U0, double
       }
       // ---------------------------------------------------------------- one NUTS transition from (SQ, SG, s_lp)
       unsigned udraw = 0;
-      for (int i = lane; i < D; i += 32) {
-        const double p = rng.normal(it, i, 0) * rsqrt(v[V_MINV][i]);
+      NUTS_SWEEP(i) {
+        const double p = i < D ? rng.normal(it, i, 0) * rsqrt(v[V_MINV][i]) : 0.0;
         v[V_ZP][i] = p;
         v[V_OP][i] = p;
         v[V_RHO][i] = p;
@@ -213,7 +223,7 @@ nuts_kernel(BdrtModel m, bdrt_nuts_opts o, const double* __restrict__ U0, double
       while (depth < o.max_treedepth) {
         const int dir = (rng.uniform(it, udraw++, 1) > 0.5) ? 1 : -1;
         if (dir != active_dir) {  // bring the other end of the trajectory into the working vectors
-          for (int i = lane; i < D; i += 32) {
+          NUTS_SWEEP(i) {
             double t_;
             t_ = v[V_ZQ][i]; v[V_ZQ][i] = v[V_OQ][i]; v[V_OQ][i] = t_;
             t_ = v[V_ZP][i]; v[V_ZP][i] = v[V_OP][i]; v[V_OP][i] = t_;
@@ -223,7 +233,7 @@ nuts_kernel(BdrtModel m, bdrt_nuts_opts o, const double* __restrict__ U0, double
           active_dir = dir;
           __syncwarp();
         }
-        for (int i = lane; i < D; i += 32) v[V_RSUB][i] = 0.0;
+        NUTS_SWEEP(i) v[V_RSUB][i] = 0.0;
         __syncwarp();
         double lsw_sub = -INFINITY, p_lp = 0.0;
         bool valid = true;
@@ -240,7 +250,7 @@ nuts_kernel(BdrtModel m, bdrt_nuts_opts o, const double* __restrict__ U0, double
           // uniform-over-weights (multinomial) proposal inside the sub-tree by reservoir sampling
           const bool take = (leaf == 0) || (rng.uniform(it, udraw++, 1) < exp(w - lsw_new));
           lsw_sub = lsw_new;
-          for (int i = lane; i < D; i += 32) {
+          NUTS_SWEEP(i) {
             v[V_RSUB][i] += v[V_ZP][i];
             if (take) {
               v[V_PQ][i] = v[V_ZQ][i];
@@ -253,14 +263,14 @@ nuts_kernel(BdrtModel m, bdrt_nuts_opts o, const double* __restrict__ U0, double
           if ((leaf & 1) == 0) {
             const int idx = __popc(leaf >> 1);
             double *cp = CP + (long long)idx * Dpad, *cr = CR + (long long)idx * Dpad;
-            for (int i = lane; i < D; i += 32) { cp[i] = v[V_ZP][i]; cr[i] = v[V_RSUB][i]; }
+            NUTS_SWEEP(i) { cp[i] = v[V_ZP][i]; cr[i] = v[V_RSUB][i]; }
           } else {
             const int nsub = __ffs(~leaf) - 1;  // trailing ones: sub-trees of size 2, 4, .., 2^nsub end at this leaf
             const int idx_max = __popc(leaf >> 1);
             for (int idx = idx_max; idx > idx_max - nsub; --idx) {
               const double *cp = CP + (long long)idx * Dpad, *cr = CR + (long long)idx * Dpad;
               double d_s = 0.0, d_e = 0.0;
-              for (int i = lane; i < D; i += 32) {
+              NUTS_SWEEP(i) {
                 const double rho_s = v[V_RSUB][i] - cr[i] + cp[i];
                 const double mi = v[V_MINV][i];
                 d_s = fma(mi * cp[i], rho_s, d_s);
@@ -289,7 +299,7 @@ nuts_kernel(BdrtModel m, bdrt_nuts_opts o, const double* __restrict__ U0, double
         }
         lsw = logaddexp(lsw, lsw_sub);
         double d_z = 0.0, d_o = 0.0;
-        for (int i = lane; i < D; i += 32) {
+        NUTS_SWEEP(i) {
           const double r = v[V_RHO][i] + v[V_RSUB][i];
           v[V_RHO][i] = r;
           const double mi = v[V_MINV][i];
