@@ -250,14 +250,14 @@ nuts_kernel(BdrtModel m, bdrt_nuts_opts o, const double* __restrict__ U0, double
           // uniform-over-weights (multinomial) proposal inside the sub-tree by reservoir sampling
           const bool take = (leaf == 0) || (rng.uniform(it, udraw++, 1) < exp(w - lsw_new));
           lsw_sub = lsw_new;
-          NUTS_SWEEP(i) {
-            v[V_RSUB][i] += v[V_ZP][i];
-            if (take) {
+          NUTS_SWEEP(i) v[V_RSUB][i] += v[V_ZP][i];
+          if (take) {  // warp-uniform, and rare deep in a sub-tree (probability ~ 1 / leaf)
+            NUTS_SWEEP(i) {
               v[V_PQ][i] = v[V_ZQ][i];
               v[V_PG][i] = v[V_ZG][i];
             }
+            p_lp = z_lp;
           }
-          if (take) p_lp = z_lp;
           __syncwarp();
           if (divergent) { valid = false; break; }
           if ((leaf & 1) == 0) {
