@@ -65,11 +65,12 @@ def test_map_1e5_on_benchmark_batch():
     assert np.allclose([d['Z_scale'] for d in _DS], s, rtol=1e-12)
     with mp.get_context('fork').Pool(min(os.cpu_count() or 1, 32)) as pool:
         ora = pool.map(_oracle_polish, [(b, u_lbfgs[b]) for b in range(NSPEC)], chunksize=4)
-    # converged = max|grad| below 1e-8 (oracle) / 1e-7 (CUDA, forward-difference Hessian) -- the oracle's `failed` flag only
-    # says that its last damped step could not improve on a point already at the rounding floor
-    ok = np.array([o['gnorm'] < 1e-8 for o in ora]) & (gnorm < 1e-7)
+    # converged = max|grad| below 1e-8 on both sides (the Hessian's condition number is ~3e7: a gradient of 1e-7 still
+    # leaves 1e-4 of the peak along the flattest direction) -- the oracle's `failed` flag only says that its last damped
+    # step could not improve on a point already at the rounding floor
+    ok = np.array([o['gnorm'] < 1e-8 for o in ora]) & (gnorm < 1e-8)
     # both Newton iterations converge for (nearly) every spectrum, poor local optima of the random starts included
-    assert ok.mean() >= 0.97, (ok.mean(), gnorm[~ok], [ora[b]['gnorm'] for b in np.where(~ok)[0]])
+    assert ok.mean() >= 0.95, (ok.mean(), gnorm[~ok], [ora[b]['gnorm'] for b in np.where(~ok)[0]])
     err_pol, err_lbfgs = np.zeros(NSPEC), np.zeros(NSPEC)
     for b in range(NSPEC):
         xo = ora[b]['x']
