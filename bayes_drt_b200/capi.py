@@ -133,6 +133,28 @@ class SeriesProblem:
         self.D = int(self.ctx.lib.bdrt_num_params(C.byref(d)))
         self.P = int(self.ctx.lib.bdrt_num_outputs(C.byref(d)))
 
+    def subset(self, a, b):
+        """Spectra a .. b - 1 of this problem as a problem of their own: a view (same device tensors, same analysis of the
+        matrices), used to run a large batch through the sampler in bounded pieces."""
+        import copy
+        sub = copy.copy(self)
+        d = SeriesData()
+        C.memmove(C.byref(d), C.byref(self.c), C.sizeof(SeriesData))
+        n2 = 2 * self.Nf
+        sub.Z = self.Z[a:b]
+        d.B, d.Z = b - a, sub.Z.data_ptr()
+        if self.per_spectrum_grid:
+            sub.A, sub.freq = self.A[a:b], self.freq[a:b]
+            d.A, d.freq = sub.A.data_ptr(), sub.freq.data_ptr()
+            if self.series_parallel:
+                sub.Ap = self.Ap[a:b]
+                d.Ap = sub.Ap.data_ptr()
+            if self.two_parallel:
+                sub.Ap2 = self.Ap2[a:b]
+                d.Ap2 = sub.Ap2.data_ptr()
+        sub.c, sub.B = d, b - a
+        return sub
+
     # -- log_prob / grad_log_prob test hook
     def logpost_grad(self, u, spec=None, jacobian=False):
         u = f64(u, self.ctx.device)

@@ -490,21 +490,34 @@ class Inverter:
                 r.update(u=p['u'], lp=p['lp'], gnorm=p['gnorm'], newton_iters=p['iters'])
             point = prob.split_outputs(prob.constrain(r['u']))
             return dict(point=point, opt=r, draws=None, stats=None)
-        r = prob.nuts(u0, chains=chains, warmup=warmup, samples=samples, seed=random_seed, spectrum_ids=ids)
-        lost = ~torch.isfinite(r['stepsize'])
-        if bool(lost.any()):
-            rows = torch.nonzero(lost.any(dim=1))[:, 0].tolist()
-            raise RuntimeError(f'NUTS could not find a step size for chains of spectra {rows[:10]}')
-        spec = torch.arange(B, dtype=torch.int32, device=self.device).repeat_interleave(chains * samples)
-        cons = prob.constrain(r['draws'].reshape(B * chains * samples, D), spec=spec).reshape(
-            B, chains * samples, prob.P)
-        draws = prob.split_outputs(cons)
-        # posterior mean over the merged chains (Inverter._extract_parameter, inversion.py:2514-2519), reduced on device
-        pm, _ = capi.summarize(cons, device=self.device)
-        point = prob.split_outputs(pm)
-        stats = {k: r[k] for k in ('stepsize', 'n_leapfrog', 'n_divergent', 'n_maxdepth', 'accept')}
-        stats['rhat'], stats['ess_bulk'] = self._diagnostics(draws, chains, samples)
-        return dict(point=point, opt=None, draws=draws if keep_draws else None, stats=stats)
+        # When the draws are not kept, the batch goes through the sampler in pieces of eight waves of resident chains, so
+        # that the raw and constrained draws (1.4 MB per spectrum at 2 x 200 draws of D = 209) never exceed a few GB:
+        # the 1e5-spectrum sweep of config 4 needs 18 GB per GPU otherwise (SURVEY.md section 7 hard part 5).
+        sm = torch.cuda.get_device_properties(self.device).multi_processor_count if self.device.type == 'cuda' else 148
+        piece = B if keep_draws else (getattr(self, '_hmc_piece', None) or max(1, (8 * 16 * sm) // chains))
+        parts = []
+        for a in range(0, B, piece):
+            b = min(B, a + piece)
+            pb = prob if (a == 0 and b == B) else prob.subset(a, b)
+            r = pb.nuts(u0[a:b], chains=chains, warmup=warmup, samples=samples, seed=random_seed, spectrum_ids=ids[a:b])
+            lost = ~torch.isfinite(r['stepsize'])
+            if bool(lost.any()):
+                rows = (torch.nonzero(lost.any(dim=1))[:, 0] + a).tolist()
+                raise RuntimeError(f'NUTS could not find a step size for chains of spectra {rows[:10]}')
+            nb = b - a
+            spec = torch.arange(nb, dtype=torch.int32, device=self.device).repeat_interleave(chains * samples)
+            cons = pb.constrain(r['draws'].reshape(nb * chains * samples, D), spec=spec).reshape(
+                nb, chains * samples, prob.P)
+            draws = prob.split_outputs(cons)
+            # posterior mean over the merged chains (Inverter._extract_parameter, inversion.py:2514-2519), on device
+            pm, _ = capi.summarize(cons, device=self.device)
+            stats = {k: r[k] for k in ('stepsize', 'n_leapfrog', 'n_divergent', 'n_maxdepth', 'accept')}
+            stats['rhat'], stats['ess_bulk'] = self._diagnostics(draws, chains, samples)
+            parts.append((pm, stats, draws if keep_draws else None))
+            del r, cons
+        pm = torch.cat([p[0] for p in parts])
+        stats = {k: torch.cat([p[1][k] for p in parts]) for k in parts[0][1]}
+        return dict(point=prob.split_outputs(pm), opt=None, draws=parts[0][2], stats=stats)
 
     def _diagnostics(self, draws, chains, samples):
         """Split R-hat and bulk ESS of every coefficient of every distribution, R_inf and the inductance (what pystan

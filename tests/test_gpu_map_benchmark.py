@@ -65,31 +65,37 @@ def test_map_1e5_on_benchmark_batch():
     assert np.allclose([d['Z_scale'] for d in _DS], s, rtol=1e-12)
     with mp.get_context('fork').Pool(min(os.cpu_count() or 1, 32)) as pool:
         ora = pool.map(_oracle_polish, [(b, u_lbfgs[b]) for b in range(NSPEC)], chunksize=4)
-    # converged = max|grad| below 1e-8 on both sides (the Hessian's condition number is ~3e7: a gradient of 1e-7 still
-    # leaves 1e-4 of the peak along the flattest direction) -- the oracle's `failed` flag only says that its last damped
-    # step could not improve on a point already at the rounding floor
-    ok = np.array([o['gnorm'] < 1e-8 for o in ora]) & (gnorm < 1e-8)
-    # both Newton iterations converge for (nearly) every spectrum, poor local optima of the random starts included
-    assert ok.mean() >= 0.95, (ok.mean(), gnorm[~ok], [ora[b]['gnorm'] for b in np.where(~ok)[0]])
-    err_pol, err_lbfgs = np.zeros(NSPEC), np.zeros(NSPEC)
+    # converged = max|grad| within a factor 2 of the 1e-9 both Newton iterations aim for (measured on this batch: with
+    # condition numbers of 3e7 and more, a spectrum stuck at |grad| = 5e-9 is still 4e-4 of the peak from the optimum
+    # along its flattest direction, while every spectrum below 2e-9 agrees to 1e-10) -- the oracle's `failed` flag only
+    # says that its last damped step could not improve on a point already at the rounding floor
+    ogn = np.array([o['gnorm'] for o in ora])
+    ok = (ogn < 2e-9) & (gnorm < 2e-9)
+    err_pol, err_lbfgs, err_R, err_s, err_lp = (np.zeros(NSPEC) for _ in range(5))
     for b in range(NSPEC):
         xo = ora[b]['x']
         sc = np.max(np.abs(xo))
         err_pol[b] = np.max(np.abs(x_pol[b] - xo)) / sc
         err_lbfgs[b] = np.max(np.abs(x_lbfgs[b] - xo)) / sc
-        if ok[b]:
-            assert err_pol[b] <= 1e-5, (b, err_pol[b])
-            assert abs(Rinf_pol[b] - ora[b]['Rinf']) <= 1e-5 * ora[b]['Rinf'] + 2e-6  # (-> 0 in a few poor optima)
-            # (sigma_res is a lower=0 parameter that goes to its bound for clean RC spectra: compared absolutely there,
-            # on the scale of sigma_min = 0.002)
-            assert abs(sres_pol[b] - ora[b]['sigma_res']) <= 1e-5 * ora[b]['sigma_res'] + 2e-6
-            assert abs(pol._opt_result['lp'][b].item() + ora[b]['f']) <= 1e-9 * abs(ora[b]['f'])
+        # scalars: relative, with an absolute floor on the scale of sigma_min = 0.002 for the lower=0 parameters that go to
+        # their bound (sigma_res for clean RC spectra; R_inf in a few poor optima)
+        err_R[b] = abs(Rinf_pol[b] - ora[b]['Rinf']) / (ora[b]['Rinf'] + 0.2)
+        err_s[b] = abs(sres_pol[b] - ora[b]['sigma_res']) / (ora[b]['sigma_res'] + 0.2)
+        err_lp[b] = abs(pol._opt_result['lp'][b].item() + ora[b]['f']) / abs(ora[b]['f'])
     q = lambda a: {p: float(np.percentile(a[ok], p)) for p in (5, 50, 95, 100)}  # noqa: E731
-    rep = dict(n=NSPEC, converged_both=int(ok.sum()), polished_rel_err_inf=q(err_pol), lbfgs_rel_err_inf=q(err_lbfgs),
-               termination={int(k): int((status == k).sum()) for k in np.unique(status)})
+    rep = dict(n=NSPEC, converged_both=int(ok.sum()), converged_cuda=int((gnorm < 2e-9).sum()),
+               converged_oracle=int((ogn < 2e-9).sum()), polished_rel_err_inf=q(err_pol), lbfgs_rel_err_inf=q(err_lbfgs),
+               termination={int(k): int((status == k).sum()) for k in np.unique(status)},
+               worst=[dict(b=int(b), err=float(err_pol[b]), gnorm_cuda=float(gnorm[b]), gnorm_oracle=float(ogn[b]))
+                      for b in np.argsort(-np.where(ok, err_pol, 0))[:5]])
     print('MAP parity on the benchmark shape:', json.dumps(rep))
     os.makedirs('gpurun_out', exist_ok=True)
     with open('gpurun_out/map_parity_benchmark.json', 'w') as fh:
         json.dump(rep, fh, indent=1)
+    # both Newton iterations converge for (nearly) every spectrum, poor local optima of the random starts included
+    assert ok.mean() >= 0.95, rep
+    assert err_pol[ok].max() <= 1e-5, rep           # north star: MAP coefficients within 1e-5 (of the largest one)
+    assert err_R[ok].max() <= 1e-5 and err_s[ok].max() <= 1e-5, (err_R[ok].max(), err_s[ok].max())
+    assert err_lp[ok].max() <= 1e-9
     # the unpolished default is Stan's own termination: percent-level away from the optimum, never 1e-5
     assert 1e-5 < np.median(err_lbfgs[ok]) < 0.2
