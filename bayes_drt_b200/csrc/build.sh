@@ -8,7 +8,11 @@ OUT=../libbdrt.so
 FLAGS="-gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -Xcompiler -fPIC -Xptxas -v -static-global-template-stub=false"
 mkdir -p build
 pids=()
+newest_hdr=$(ls -t *.cuh ../../include/*.h build.sh | head -1)
 for f in *.cu; do
+  o="build/${f%.cu}.o"
+  # incremental: skip a file whose object is newer than its source and every header (BDRT_REBUILD=1 or extra flags force)
+  if [ -z "$BDRT_REBUILD" ] && [ $# -eq 0 ] && [ -f "$o" ] && [ "$o" -nt "$f" ] && [ "$o" -nt "$newest_hdr" ]; then continue; fi
   ( $NVCC $FLAGS "$@" -c "$f" -o "build/${f%.cu}.o" > "build/${f%.cu}.log" 2>&1 ) &
   pids+=($!)
 done

@@ -63,6 +63,8 @@ struct BdrtDist {
   int toepL;                  // L0/L1/L2 are Toeplitz: use the tap table
   const double* A;            // [2Nf, K] or [B, 2Nf, K]
   long long A_stride;         // per-spectrum stride (0: shared)
+  const double* Ag;           // global-dense mode: padded, scaled copy [n2p][lda] (+ 8) per grid, in the workspace
+  long long Ag_stride;        // per-spectrum stride of Ag (0: shared)
   const double* Lb;           // [3][K][LBW] banded copies of the scaled L0, L1, L2
   double ascale;              // the resident operand is A * ascale (xp = xp_raw * xp_scale, Series-Parallel :52)
   double tapc[3][2 * FBW + 1]; // Toeplitz taps of L0/L1/L2 for |d| <= FBW, read straight from the parameter bank
@@ -75,6 +77,9 @@ struct BdrtModel {
   int nfp;    // Nf rounded up to a multiple of 8
   int n2p;    // 2 * nfp
   int toepA;  // Toeplitz-resident operands
+  int gdense; // dense operands that do not fit in shared memory (two / three distributions on general grids): the products
+              // read the padded copies d[].Ag through L1 / L2 instead; oCur holds the CTA's current spectrum
+  int oCur;
   int wmode;  // warp mode: Toeplitz operands, warp-private Hankel products (engine_eval<2, ..>), no CTA barriers
   int pslot;  // warp mode with per-spectrum grids: tables and omega live in the slot's scratch
   int vim;    // offset of the imaginary part inside a V row (nfp; warp mode: nfp + 12, zero gap for the sliding window)
@@ -173,7 +178,7 @@ static inline int bdrt_model_layout(BdrtModel* m) {
   for (int i = 0; i < m->ND; ++i) {
     m->d[i].oA = o;
     if (m->wmode) o += m->pslot ? 0 : 2 * m->d[i].lt2;
-    else o += m->toepA ? 2 * m->d[i].lt : m->n2p * m->d[i].lda + 8;
+    else if (!m->gdense) o += m->toepA ? 2 * m->d[i].lt : m->n2p * m->d[i].lda + 8;
   }
   m->oXV = o;  o += m->ND * NSLOT * m->ldxv;
   m->oZG = o;  // (no region of its own: see sd above)
@@ -181,6 +186,7 @@ static inline int bdrt_model_layout(BdrtModel* m) {
   for (int i = 0; i < m->ND; ++i) { m->d[i].oTap = o; o += 3 * LBW; }
   m->oOm = o;  o += m->Nf;
   o = (o + 1) & ~1;
+  m->oCur = o;  o += 2;
   m->oUser = o;
   return o;
 }
@@ -311,7 +317,7 @@ __device__ inline void engine_load(const BdrtModel& m, double* sm, long long spe
         else if (d < 0 && -d < m.Nf) v = gA[((long long)p * m.Nf - d) * D.K];
         sA[i] = v * D.ascale;
       }
-    } else {
+    } else if (!m.gdense) {
       for (int i = tid; i < m.n2p * D.lda + 8; i += NTHREADS) {
         const int rp = i / D.lda, c = i - rp * D.lda;
         const int p = rp >= m.nfp, r = rp - p * m.nfp;  // padded row -> (part, row)
@@ -328,6 +334,7 @@ __device__ inline void engine_load(const BdrtModel& m, double* sm, long long spe
   for (int i = tid; i < NSLOT * m.st; i += NTHREADS) sm[m.oSt + i] = 0.0;
   const double* f = m.freq + spec * m.f_stride;
   for (int i = tid; i < m.Nf; i += NTHREADS) sm[m.oOm + i] = 2.0 * M_PI * f[i];
+  if (tid == 0) *reinterpret_cast<long long*>(sm + m.oCur) = spec;
   cta_sync();
 }
 
@@ -368,6 +375,8 @@ __device__ __forceinline__ double engine_eval(const BdrtModel& m, double* sm, bo
   double* sSo = sTh + 16;         // sigma_out_raw [Nf], sigma_out_scale [Nf]
   const double* sOm = (TOEP == 2 && m.pslot) ? sSt + m.oOmS : sm + m.oOm;
   const double jac = jacobian ? 1.0 : 0.0;
+  // global-dense operands: the spectrum whose grids the CTA has loaded (engine_load)
+  const long long gsp = (TOEP == 0 && m.gdense) ? *reinterpret_cast<const long long*>(sm + m.oCur) : 0;
   if (TOEP == 2) {
     if (!active) return 0.0;  // warp mode: nobody else needs this warp
     __syncwarp();
@@ -825,31 +834,34 @@ __device__ __forceinline__ double engine_eval(const BdrtModel& m, double* sm, bo
       const int da = (ND > 1) ? ti / nmt : 0, db = (ND > 1) ? tj / nmt : 0;
       const int mt = ti - da * nmt, mt2 = tj - db * nmt;
       const BdrtDist &Da = m.d[da], &Db = m.d[db];
-      const double *a0p, *a1p;
-      if (TOEP) {  // A_p[row][col] = T_p[col - row + nfp - 1]
-        const int r0 = mt * 8 + g, r1 = mt2 * 8 + g;
-        const int p0 = r0 >= nfp, p1 = r1 >= nfp;
-        a0p = sm + Da.oA + p0 * Da.lt + (nfp - 1) - (r0 - p0 * nfp) + t;
-        a1p = sm + Db.oA + p1 * Db.lt + (nfp - 1) - (r1 - p1 * nfp) + t;
-      } else {
-        a0p = sm + Da.oA + (mt * 8 + g) * Da.lda + t;
-        a1p = sm + Db.oA + (mt2 * 8 + g) * Db.lda + t;
-      }
       const double* b0p = sm + m.oXV + (da * NSLOT + g) * m.ldxv + m.xoff + t;
       const double* b1p = sm + m.oXV + (db * NSLOT + g) * m.ldxv + m.xoff + t;
       double c00 = 0, c01 = 0, c10 = 0, c11 = 0;
-      if (ND == 1 || (da == db && Da.kpad4 == Db.kpad4)) {
+      // (a lambda, so that the shared-memory and the global-dense call sites each keep their own address space)
+      auto prod = [&](const double* a0p, const double* a1p) {
+        if (ND == 1 || (da == db && Da.kpad4 == Db.kpad4)) {
 #pragma unroll 5
-        for (int kk = 0; kk < Da.kpad4; kk += 4) {
-          const double b = b0p[kk];
-          dmma(c00, c01, a0p[kk], b);
-          dmma(c10, c11, a1p[kk], b);
+          for (int kk = 0; kk < Da.kpad4; kk += 4) {
+            const double b = b0p[kk];
+            dmma(c00, c01, a0p[kk], b);
+            dmma(c10, c11, a1p[kk], b);
+          }
+        } else {
+#pragma unroll 5
+          for (int kk = 0; kk < Da.kpad4; kk += 4) dmma(c00, c01, a0p[kk], b0p[kk]);
+#pragma unroll 5
+          for (int kk = 0; kk < Db.kpad4; kk += 4) dmma(c10, c11, a1p[kk], b1p[kk]);
         }
+      };
+      if (TOEP) {  // A_p[row][col] = T_p[col - row + nfp - 1]
+        const int r0 = mt * 8 + g, r1 = mt2 * 8 + g;
+        const int p0 = r0 >= nfp, p1 = r1 >= nfp;
+        prod(sm + Da.oA + p0 * Da.lt + (nfp - 1) - (r0 - p0 * nfp) + t,
+             sm + Db.oA + p1 * Db.lt + (nfp - 1) - (r1 - p1 * nfp) + t);
+      } else if (m.gdense) {
+        prod(Da.Ag + gsp * Da.Ag_stride + (mt * 8 + g) * Da.lda + t, Db.Ag + gsp * Db.Ag_stride + (mt2 * 8 + g) * Db.lda + t);
       } else {
-#pragma unroll 5
-        for (int kk = 0; kk < Da.kpad4; kk += 4) dmma(c00, c01, a0p[kk], b0p[kk]);
-#pragma unroll 5
-        for (int kk = 0; kk < Db.kpad4; kk += 4) dmma(c10, c11, a1p[kk], b1p[kk]);
+        prod(sm + Da.oA + (mt * 8 + g) * Da.lda + t, sm + Db.oA + (mt2 * 8 + g) * Db.lda + t);
       }
       double* z0 = sm + m.oSt + da * m.sd;  // column (slot) 2 t, 2 t + 1 -> that slot's Z / G row
       z0[(2 * t) * m.st + mt * 8 + g] = c00;
@@ -1130,24 +1142,31 @@ __device__ __forceinline__ double engine_eval(const BdrtModel& m, double* sm, bo
       const int step0 = TOEP ? -4 : 4 * Da.lda, step1 = TOEP ? -4 : 4 * Db.lda;
 #pragma unroll
       for (int p = 0; p < 2; ++p) {  // A^T[col][row] = A_p[row][col], rows of part p
-        const double* a0p = (TOEP ? sm + Da.oA + p * Da.lt + (nfp - 1) - t : sm + Da.oA + (p * nfp + t) * Da.lda) + col0;
-        const double* a1p = (TOEP ? sm + Db.oA + p * Db.lt + (nfp - 1) - t : sm + Db.oA + (p * nfp + t) * Db.lda) + col1;
         const double* bq0 = b0p + p * nfp;
         const double* bq1 = b1p + p * nfp;
-        if (ND == 1) {
+        auto prod = [&](const double* a0p, const double* a1p) {
+          if (ND == 1) {
 #pragma unroll 3
-          for (int i0 = 0, ao = 0; i0 < nfp; i0 += 4, ao += step0) {
-            const double b = bq0[i0];
-            dmma(c00, c01, a0p[ao], b);
-            dmma(c10, c11, a1p[ao], b);
-          }
-        } else {
+            for (int i0 = 0, ao = 0; i0 < nfp; i0 += 4, ao += step0) {
+              const double b = bq0[i0];
+              dmma(c00, c01, a0p[ao], b);
+              dmma(c10, c11, a1p[ao], b);
+            }
+          } else {
 #pragma unroll 3
-          for (int i0 = 0, ao0 = 0, ao1 = 0; i0 < nfp; i0 += 4, ao0 += step0, ao1 += step1) {
-            dmma(c00, c01, a0p[ao0], bq0[i0]);
-            dmma(c10, c11, a1p[ao1], bq1[i0]);
+            for (int i0 = 0, ao0 = 0, ao1 = 0; i0 < nfp; i0 += 4, ao0 += step0, ao1 += step1) {
+              dmma(c00, c01, a0p[ao0], bq0[i0]);
+              dmma(c10, c11, a1p[ao1], bq1[i0]);
+            }
           }
-        }
+        };
+        if (TOEP)
+          prod(sm + Da.oA + p * Da.lt + (nfp - 1) - t + col0, sm + Db.oA + p * Db.lt + (nfp - 1) - t + col1);
+        else if (m.gdense)
+          prod(Da.Ag + gsp * Da.Ag_stride + (p * nfp + t) * Da.lda + col0,
+               Db.Ag + gsp * Db.Ag_stride + (p * nfp + t) * Db.lda + col1);
+        else
+          prod(sm + Da.oA + (p * nfp + t) * Da.lda + col0, sm + Db.oA + (p * nfp + t) * Db.lda + col1);
       }
       double* z0 = sm + m.oSt + da * m.sd;  // column (slot) 2 t, 2 t + 1 -> that slot's Z / G row
       z0[(2 * t) * m.st + mt * 8 + g] = c00;

@@ -236,6 +236,20 @@ extern "C" int bdrt_series_analyze(bdrt_ctx* ctx, const bdrt_series_data* data, 
   return bdrt_analyze(ctx, data, nd, info);
 }
 
+// Global-dense mode: the padded, scaled copy of one distribution's kernel matrices in the layout the dense products
+// index (rows [re: nfp | im: nfp], pitch lda, zeros in the padding), one per grid.
+__global__ void pad_A_kernel(const double* __restrict__ A, long long A_stride, double* __restrict__ Ag, long long ngrid,
+                             long long per, int Nf, int nfp, int n2p, int K, int lda, double ascale) {
+  const long long tot = ngrid * per;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < tot; i += (long long)gridDim.x * blockDim.x) {
+    const long long s = i / per;
+    const int e = (int)(i - s * per);
+    const int rp = e / lda, c = e - rp * lda;
+    const int p = rp >= nfp, r = rp - p * nfp;
+    Ag[i] = (rp < n2p && r < Nf && c < K) ? A[s * A_stride + ((long long)p * Nf + r) * K + c] * ascale : 0.0;
+  }
+}
+
 int bdrt_model_prepare(bdrt_ctx* ctx, const bdrt_series_data* d, BdrtModel* m, size_t extra_ws_bytes,
                        void** extra_ws, int allow_wmode) {
   int nd = 0;
@@ -291,18 +305,6 @@ int bdrt_model_prepare(bdrt_ctx* ctx, const bdrt_series_data* d, BdrtModel* m, s
     if (rc) return rc;
     si = &local;
   }
-  size_t lb_off[MAXD];
-  const size_t head = bdrt_lb_offsets(d, nd, lb_off);
-  rc = bdrt_ws_reserve(ctx, head + extra_ws_bytes);
-  if (rc) return rc;
-  // banded copies of the penalty matrices (device work only; the flags it recomputes are not read back)
-  for (int i = 0; i < nd; ++i) {
-    double* Lb = (double*)((char*)ctx->ws + lb_off[i]);
-    band_prep_kernel<<<3, 256, 0, ctx->stream>>>(Ls[i], Ks[i], Lb, (int*)ctx->ws + 4 * i);
-    ctx->launches++;
-    m->d[i].Lb = Lb;
-  }
-  BDRT_CUDA(ctx, cudaGetLastError());
   int bw = 0;
   for (int i = 0; i < nd; ++i) {
     if (si->bw[i] > MAXBW)
@@ -344,11 +346,50 @@ int bdrt_model_prepare(bdrt_ctx* ctx, const bdrt_series_data* d, BdrtModel* m, s
       for (int j = 0; j < 3; ++j)
         for (int t = 0; t < 2 * FBW + 1; ++t) m->d[i].tapc[j][t] = si->taps[i][j][t];
   }
-  const int eng = bdrt_model_layout(m);
+  int eng = bdrt_model_layout(m);
+  // dense operands that do not fit next to the engine's working set (two or three distributions on general grids,
+  // matrices.py:243-263): keep padded copies in the workspace and let the products read them through L1 / L2
+  // (BDRT_FORCE_GDENSE=1 takes this path whenever the operands are dense, for tests)
+  const char* fgd = getenv("BDRT_FORCE_GDENSE");
+  if (!m->toepA && ((size_t)eng * 8 > (size_t)ctx->smem_optin || (fgd && fgd[0] == '1'))) {
+    m->gdense = 1;
+    eng = bdrt_model_layout(m);
+  }
   if ((size_t)eng * 8 > (size_t)ctx->smem_optin)
-    BDRT_FAIL(ctx, BDRT_E_SMEM, "problem needs %zu B of shared memory per CTA, device offers %d%s", (size_t)eng * 8,
-              ctx->smem_optin,
-              m->toepA ? "" : " (dense-resident kernel matrices; log-uniform grids with equal spacing need far less)");
+    BDRT_FAIL(ctx, BDRT_E_SMEM, "problem needs %zu B of shared memory per CTA, device offers %d", (size_t)eng * 8,
+              ctx->smem_optin);
+  size_t lb_off[MAXD], ag_off[MAXD];
+  size_t head = bdrt_lb_offsets(d, nd, lb_off);
+  const long long ngrid = d->per_spectrum_grid ? d->B : 1;
+  if (m->gdense) {
+    for (int i = 0; i < nd; ++i) {
+      ag_off[i] = head;
+      m->d[i].Ag_stride = d->per_spectrum_grid ? (long long)m->n2p * m->d[i].lda + 8 : 0;
+      head += ((size_t)ngrid * ((size_t)m->n2p * m->d[i].lda + 8) * sizeof(double) + 255) & ~(size_t)255;
+    }
+  }
+  rc = bdrt_ws_reserve(ctx, head + extra_ws_bytes);
+  if (rc) return rc;
+  // banded copies of the penalty matrices (device work only; the flags it recomputes are not read back)
+  for (int i = 0; i < nd; ++i) {
+    double* Lb = (double*)((char*)ctx->ws + lb_off[i]);
+    band_prep_kernel<<<3, 256, 0, ctx->stream>>>(Ls[i], Ks[i], Lb, (int*)ctx->ws + 4 * i);
+    ctx->launches++;
+    m->d[i].Lb = Lb;
+  }
+  if (m->gdense && d->B > 0) {
+    for (int i = 0; i < nd; ++i) {
+      double* Ag = (double*)((char*)ctx->ws + ag_off[i]);
+      const long long per = (long long)m->n2p * m->d[i].lda + 8;
+      const long long tot = ngrid * per;
+      const int nblk = (int)((tot + 255) / 256 < 65535LL * 16 ? (tot + 255) / 256 : 65535LL * 16);
+      pad_A_kernel<<<nblk, 256, 0, ctx->stream>>>(m->d[i].A, m->d[i].A_stride, Ag, ngrid, per, m->Nf, m->nfp, m->n2p,
+                                                   m->d[i].K, m->d[i].lda, m->d[i].ascale);
+      ctx->launches++;
+      m->d[i].Ag = Ag;
+    }
+  }
+  BDRT_CUDA(ctx, cudaGetLastError());
   if (extra_ws) *extra_ws = (char*)ctx->ws + head;
   return BDRT_OK;
 }

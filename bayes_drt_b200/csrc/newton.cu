@@ -9,10 +9,19 @@
 // cooperative engine_eval(), so one Hessian is ceil(D/8) evaluations; the packed D(D+1)/2 factorisation overlays the
 // CTA's shared memory when it fits (the resident A is simply re-loaded afterwards), else it lives in L2-resident scratch.
 //
-// Parameters whose optimum is on the boundary of a lower=0 constraint (theta = exp(u) -> 0, e.g. inductance or
-// alpha_im for most spectra) have no finite optimum in u: Newton moves them by -1 per iteration.  Once the Newton step
-// of such a coordinate is < -0.5 and it is already below exp(-6), it is sent to u = -40 (theta ~ 4e-18, i.e. 0 to
-// double precision in every formula) and frozen; it is released again if its gradient ever asks for a larger theta.
+// Parameters whose optimum is on the boundary of a lower=0 constraint (theta = exp(u) -> 0, e.g. alpha_im or sigma_res
+// for most spectra) have no finite optimum in u: Newton moves them by -1 (f ~ f0 + c theta) or -1/2 (f ~ f0 + c theta^2:
+// the error-model scales enter squared) per iteration for ever.  Once the Newton step of such a coordinate is < -0.5
+// and it is already below exp(-6), it is sent to u = -40 (theta ~ 4e-18, i.e. 0 to double precision in every formula)
+// and frozen.  The rule also catches interior optima at a tiny theta (the scaled inductance sits near exp(-21) for many
+// spectra; approached from above their steps look the same), so a frozen coordinate is checked at the next iteration:
+// if d lp / d theta is positive there -- its sign survives the factor theta of the chain rule -- the coordinate goes back
+// to where it was and is never frozen again.  (The first version released on g < -gtol, which a gradient scaled by
+// theta = 4e-18 never meets: 2 of 256 benchmark spectra ended with x 4e-4 .. 2e-3 of its peak from the optimum.)
+//
+// Termination: max|g| < gtol over the free coordinates, the iteration cap, or the rounding floor of the gradient (see
+// the loop).  gnorm reports the last max|g|; whether a spectrum's optimum is determined to a given accuracy is a
+// property of its Hessian (flattest direction) and not of this number alone.
 #include "engine.cuh"
 
 #define U_FLOOR (-40.0)
@@ -70,8 +79,8 @@ newton_kernel(BdrtModel m, bdrt_newton_opts o, double* __restrict__ U, double* l
   extern __shared__ __align__(16) double sm[];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int D = m.D;
-  // per-CTA global scratch: H rows [D*Dpad] | packed factor [D(D+1)/2] | u g step utry gtry [5 Dpad] | slot vectors
-  // [8 * 2 * Dpad] | frozen [Dpad ints]
+  // per-CTA global scratch: H rows [D*Dpad] | packed factor [D(D+1)/2] | u g step utry gtry ujump [6 Dpad] | slot
+  // vectors [8 * 2 * Dpad] | frozen [Dpad ints] (0 free, 1 at the floor, 2 free for good)
   double* sc = scratch + (long long)blockIdx.x * scratch_per_cta;
   double* H = sc;
   double* Hp_g = H + (long long)D * Dpad;
@@ -80,7 +89,8 @@ newton_kernel(BdrtModel m, bdrt_newton_opts o, double* __restrict__ U, double* l
   double* step = g + Dpad;
   double* utry = step + Dpad;
   double* gtry = utry + Dpad;
-  double* sv = gtry + Dpad;
+  double* ujump = gtry + Dpad;  // value of a frozen coordinate before it was sent to the floor
+  double* sv = ujump + Dpad;
   double* my_u = sv + (long long)warp * 2 * Dpad;
   double* my_g = my_u + Dpad;
   int* frozen = (int*)(sv + (long long)NSLOT * 2 * Dpad);
@@ -93,8 +103,8 @@ newton_kernel(BdrtModel m, bdrt_newton_opts o, double* __restrict__ U, double* l
     const double* Zs = m.Z + (long long)b * m.N2;
     for (int i = tid; i < D; i += NTHREADS) { u[i] = U[(long long)b * D + i]; frozen[i] = 0; }
     __syncthreads();
-    double mu = 1e-6, f = 0.0, gmax = 0.0;
-    int it = 0, neval = 0;
+    double mu = 1e-6, f = 0.0, gmax = 0.0, gbest = INFINITY;
+    int it = 0, neval = 0, nstall = 0;
     bool stop = false;
     // f, g at u (slot 0 evaluates; the other slots idle through the barriers)
     {
@@ -108,12 +118,25 @@ newton_kernel(BdrtModel m, bdrt_newton_opts o, double* __restrict__ U, double* l
     }
     if (!isfinite(f)) stop = true;
     while (!stop) {
-      // ---- convergence test on the non-frozen coordinates; release frozen ones whose gradient points inward
-      double mymax = 0.0;
-      for (int i = tid; i < D; i += NTHREADS) {
-        if (frozen[i] && g[i] < -o.gtol) frozen[i] = 0;
-        if (!frozen[i]) mymax = fmax(mymax, fabs(g[i]));
+      // ---- release frozen coordinates whose gradient points inward (they return to where they were; new f, g)
+      int rel = 0;
+      for (int i = tid; i < D; i += NTHREADS)
+        if (frozen[i] == 1 && g[i] < 0.0) { frozen[i] = 2; u[i] = ujump[i]; rel = 1; }
+      rel = __syncthreads_or(rel);
+      if (rel) {
+        const double lp = engine_eval<TOEP, MK, FAST>(m, sm, warp == 0, u, g, Zs, 0);
+        ++neval;
+        if (tid == 0) s_val[0] = -lp;
+        __syncthreads();
+        f = s_val[0];
+        for (int i = tid; i < D; i += NTHREADS) g[i] = -g[i];
+        __syncthreads();
+        if (!isfinite(f)) break;
       }
+      // ---- convergence test on the non-frozen coordinates
+      double mymax = 0.0;
+      for (int i = tid; i < D; i += NTHREADS)
+        if (frozen[i] != 1) mymax = fmax(mymax, fabs(g[i]));
       mymax = warp_max(mymax);
       __syncthreads();
       if (lane == 0) s_val[warp] = mymax;
@@ -122,11 +145,21 @@ newton_kernel(BdrtModel m, bdrt_newton_opts o, double* __restrict__ U, double* l
       for (int w = 0; w < NWARP; ++w) gmax = fmax(gmax, s_val[w]);
       __syncthreads();
       if (gmax < o.gtol || it >= o.max_iter) break;
+      // The rounding floor of the gradient differs between spectra (1e-10 .. 1e-8, set by the size of the cancelling prior
+      // and likelihood terms); below it steps are still accepted but max|g| only wanders.  Stop after six iterations
+      // that did not halve the best value (CPU emulation of this loop on the oracle model: the points reached agree with
+      // the tightly converged optimum to 1e-10; without the rule 13 % of a benchmark batch ran all 200 iterations).
+      if (gmax < 0.5 * gbest) {
+        gbest = gmax;
+        nstall = 0;
+      } else if (gmax < 1e-6 && ++nstall >= 6) {
+        break;
+      }
       ++it;
       // ---- forward-difference Hessian, 8 columns per cooperative evaluation: H[j][:] = (g(u + h e_j) - g(u)) / h
       for (int j0 = 0; j0 < D; j0 += NSLOT) {
         const int j = j0 + warp;
-        const bool act = (j < D) && !frozen[j];
+        const bool act = (j < D) && frozen[j] != 1;
         double h = 0.0;
         if (act) {
           for (int i = lane; i < D; i += 32) my_u[i] = u[i];
@@ -157,7 +190,7 @@ newton_kernel(BdrtModel m, bdrt_newton_opts o, double* __restrict__ U, double* l
           while ((i + 1) * (i + 2) / 2 <= idx) ++i;
           const int k = idx - i * (i + 1) / 2;
           double v;
-          if (frozen[i] || frozen[k])
+          if (frozen[i] == 1 || frozen[k] == 1)
             v = (i == k) ? 1.0 : 0.0;
           else {
             v = 0.5 * (H[(long long)i * Dpad + k] + H[(long long)k * Dpad + i]);
@@ -165,7 +198,7 @@ newton_kernel(BdrtModel m, bdrt_newton_opts o, double* __restrict__ U, double* l
           }
           Hp[idx] = v;
         }
-        for (int i = tid; i < D; i += NTHREADS) step[i] = frozen[i] ? 0.0 : -g[i];
+        for (int i = tid; i < D; i += NTHREADS) step[i] = frozen[i] == 1 ? 0.0 : -g[i];
         if (tid == 0) s_flag[0] = 0;
         __syncthreads();
         chol_solve_packed(Hp, D, step, s_flag);
@@ -176,10 +209,10 @@ newton_kernel(BdrtModel m, bdrt_newton_opts o, double* __restrict__ U, double* l
         for (int i = tid; i < D; i += NTHREADS) {
           const bool expc = bdrt_is_exp(m, i);
           double s = step[i];
-          int jump = 0;
-          if (expc && !frozen[i] && s < -0.5 && u[i] + s < -6.0) { s = U_FLOOR - u[i]; jump = 1; }
+          const bool jump = expc && frozen[i] == 0 && s < -0.5 && u[i] + s < -6.0;
+          if (jump) s = U_FLOOR - u[i];
           utry[i] = u[i] + s;
-          gtry[i] = (double)jump;  // temporarily: jump flags
+          gtry[i] = jump ? 1.0 : 0.0;  // temporarily: jump flags
         }
         __syncthreads();
         double gd = 0.0;
@@ -199,11 +232,27 @@ newton_kernel(BdrtModel m, bdrt_newton_opts o, double* __restrict__ U, double* l
         __syncthreads();
         const double ftry = s_val[0];
         __syncthreads();
-        if (isfinite(ftry) && ftry <= f + 1e-4 * gd + 1e-13 * fabs(f)) {
+        // max |g| of the trial point over the coordinates that stay free
+        double mt = 0.0;
+        for (int i = tid; i < D; i += NTHREADS)
+          if (frozen[i] != 1 && step[i] != 1.0) mt = fmax(mt, fabs(gtry[i]));
+        mt = warp_max(mt);
+        if (lane == 0) s_val[warp] = mt;
+        __syncthreads();
+        double gtmax = 0.0;
+        for (int w = 0; w < NWARP; ++w) gtmax = fmax(gtmax, s_val[w]);
+        __syncthreads();
+        // sufficient decrease, or -- at the rounding floor of f (|f| ~ 1e3, decrements ~ |g|^2), where the Armijo test is
+        // decided by noise -- a halved gradient norm: Newton's quadratic phase by its own measure (as oracle/newton.py)
+        if (isfinite(ftry) && (ftry <= f + 1e-4 * gd + 1e-13 * fabs(f) ||
+                               (gmax < 1e-5 && gtmax < 0.5 * gmax && ftry < f + 1e-9 * fabs(f)))) {
           for (int i = tid; i < D; i += NTHREADS) {
+            if (step[i] == 1.0) {
+              ujump[i] = u[i];
+              frozen[i] = 1;
+            }
             u[i] = utry[i];
             g[i] = -gtry[i];
-            if (step[i] != 0.0) frozen[i] = 1;
           }
           f = ftry;
           mu = fmax(mu * 0.1, 1e-12);
@@ -242,8 +291,8 @@ extern "C" int bdrt_map_newton(bdrt_ctx* ctx, const bdrt_series_data* data, cons
   const int D = bdrt_num_params(data);
   const int Dpad = (D + 1) & ~1;
   const int grid = data->B < ctx->sm_count ? data->B : ctx->sm_count;
-  const long long per_cta = (long long)D * Dpad + (long long)D * (D + 1) / 2 + 2 + 5LL * Dpad + (long long)NSLOT * 2 * Dpad +
-                            Dpad;  // doubles (frozen ints fit in the last Dpad doubles)
+  const long long per_cta = (long long)D * Dpad + (long long)D * (D + 1) / 2 + 2 + 6LL * Dpad + (long long)NSLOT * 2 * Dpad +
+                            Dpad;  // doubles (the frozen ints fit in the last Dpad doubles)
   BdrtModel m;
   void* extra = nullptr;
   int rc = bdrt_model_prepare(ctx, data, &m, (size_t)(grid > 0 ? grid : 1) * per_cta * sizeof(double), &extra);

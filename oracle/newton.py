@@ -6,7 +6,7 @@ Not part of the reference: Stan's L-BFGS stops on a relative-objective / relativ
 optimum of this ill-conditioned posterior (cond ~3e7, SURVEY section 7 hard part 1), so "MAP parity" is defined
 against the *tightly converged* optimum.  This is the oracle's way to get there: Levenberg-damped Newton on
 f = -log_prob(jacobian=False) with a central finite-difference Hessian of the analytic gradient.
-The CUDA counterpart is csrc/newton.cu (forward-difference Hessian, same damping rule).
+The CUDA counterpart is csrc/newton.cu (same differences, damping and acceptance rules; nothing shared).
 """
 import numpy as np
 

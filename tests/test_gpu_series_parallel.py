@@ -44,12 +44,22 @@ def test_sp_logpost_matches_oracle(nonneg, mode, resident_A):
         assert lp[0].item() == -np.inf
 
 
-def test_sp_dense_too_large_fails_loudly(monkeypatch):
-    from bayes_drt_b200._lib import BdrtError
+def test_sp_dense_too_large_goes_global(monkeypatch):
+    """Two dense 176 x 84 operands exceed one SM's shared memory: the engine switches to the padded global copies by
+    itself (no environment override for that) -- the reference's general path, matrices.py:243-263."""
+    for k in ('BDRT_FORCE_GENERIC', 'BDRT_COOP', 'BDRT_WARP', 'BDRT_FORCE_GDENSE'):
+        monkeypatch.delenv(k, raising=False)
     monkeypatch.setenv('BDRT_FORCE_DENSE', '1')
-    prob = gpu_problem_sp(_data('optimize', True, nspec=1))
-    with pytest.raises(BdrtError, match='shared memory'):
-        prob.logpost_grad(torch.zeros(1, prob.D, dtype=torch.float64))
+    ds = _data('optimize', True, nspec=2)
+    prob = gpu_problem_sp(ds)
+    rng = np.random.RandomState(7)
+    u = rng.uniform(-1.5, 1.5, (5, prob.D))
+    spec = rng.randint(0, 2, 5)
+    lp, grad = prob.logpost_grad(torch.tensor(u), spec=spec)
+    for c in range(5):
+        lo, go = osp.logpost(u[c], ds[spec[c]])
+        assert abs(lp[c].item() - lo) <= 1e-11 * abs(lo)
+        assert np.max(np.abs(grad[c].cpu().numpy() - go)) <= 1e-9 * np.max(np.abs(go))
 
 
 def test_sp_constrain_and_map(resident_A):
