@@ -102,21 +102,6 @@ __device__ __forceinline__ double two_loop(const double* S, const double* Y, con
     }
   };
   auto hidx = [&](int j) { return head - 1 - j + (head - 1 - j < 0 ? H : 0); };  // j < nh <= H
-#ifndef BDRT_NO_HIST_PREFETCH
-  // L1 prefetch of a history entry one step ahead of its use: a hint, no registers (the entry was written at least one
-  // iteration ago; the newest one is only prefetched after the first loop has loaded it)
-  auto prefetch = [&](int h) {
-    const double* Sh = S + (long long)h * Dpad;
-    const double* Yh = Y + (long long)h * Dpad;
-#pragma unroll
-    for (int c = 0; c < NCC; ++c) {
-      asm volatile("prefetch.global.L1 [%0];" ::"l"(Sh + lane + 32 * c));
-      asm volatile("prefetch.global.L1 [%0];" ::"l"(Yh + lane + 32 * c));
-    }
-  };
-#else
-  auto prefetch = [&](int) {};
-#endif
   // (prefetching the next entry, or just the next entry's first vector, into another register buffer was measured
   // slower: it spills under the 128-register cap of the two-CTAs-per-SM kernels -- 52.9 M resp. 61 M vs 72 M
   // gradients/s)
@@ -140,14 +125,12 @@ __device__ __forceinline__ double two_loop(const double* S, const double* Y, con
   };
   {
     for (int j = 0; j < nh; ++j) {
-      if (j + 1 < nh) prefetch(hidx(j + 1));
       fetch(hidx(j), sa, ya);
       first(hidx(j), sa, ya);
     }
 #pragma unroll
     for (int c = 0; c < NCC; ++c) pr[c] *= gamma;
     for (int j = nh - 1; j >= 0; --j) {
-      if (j > 0) prefetch(hidx(j - 1));
       fetch(hidx(j), sa, ya);
       second(hidx(j), sa, ya);
     }
@@ -206,16 +189,6 @@ lbfgs_kernel(BdrtModel m, bdrt_lbfgs_opts o, double* __restrict__ U, double* lp_
   auto feval = [&](double& f, double& slope) -> bool {
     const double lp = engine_eval<TOEP, MK, FAST>(m, sm, true, xn, gn, Zs, 0);
     ++neval;
-#ifndef BDRT_NO_HIST_PREFETCH
-    // the update pass of an accepted point reads xk and gk next: when they live in global scratch, start them towards L1
-    // now (they were last written an iteration ago)
-    if (nvec_smem < 5) {
-      for (int i = lane; i < D; i += 32) {
-        if (nvec_smem < 4) asm volatile("prefetch.global.L1 [%0];" ::"l"(xk + i));
-        asm volatile("prefetch.global.L1 [%0];" ::"l"(gk + i));
-      }
-    }
-#endif
     int fin = isfinite(lp);
     double d = 0.0;
     for (int i = lane; i < D; i += 32) {

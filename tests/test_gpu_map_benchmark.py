@@ -33,8 +33,9 @@ def _func(d):
 
 def _oracle_polish(args):
     """Oracle optimum from the L-BFGS end point u, and Newton's own error estimate of both polished points: the largest
-    coefficient change of one more (undamped) Newton step, |H^-1 g|_inf over x relative to max|x|, with the oracle's
-    gradient at either point and the oracle's central-difference Hessian at its optimum.  (Coordinates sent to the floor of
+    change of a compared quantity by one more (undamped) Newton step -- |H^-1 g|_inf over x relative to max|x|, and the
+    change of R_inf and sigma_res on the scale they are compared on below -- with the oracle's gradient at either point
+    and the oracle's central-difference Hessian at its optimum.  (Coordinates sent to the floor of
     a lower=0 constraint are held; a point with a coordinate at the floor whose d lp / d theta is positive is not a
     constrained optimum at all and gets an infinite estimate -- the sign of that derivative survives the factor theta.)  The rounding floor of the gradient is
     1e-10 .. 1e-8 depending on the spectrum, and what it means for x is decided by the flattest direction of H --
@@ -48,7 +49,8 @@ def _oracle_polish(args):
         H[held, :] = 0
         H[:, held] = 0
         H[held, held] = 1
-        sl = omod.param_slices(_DS[b])['x']
+        ps = omod.param_slices(_DS[b])
+        sl = ps['x']
         est = []
         for pt in (o['x'], u_cuda):
             r = f(pt)
@@ -57,9 +59,15 @@ def _oracle_polish(args):
                 continue
             g = np.where(held, 0.0, r[1])
             try:
-                est.append(float(np.max(np.abs(np.linalg.solve(H, g)[sl])) / np.max(np.abs(o['x'][sl]))))
+                st = np.linalg.solve(H, g)
             except np.linalg.LinAlgError:
                 est.append(np.inf)
+                continue
+            e = float(np.max(np.abs(st[sl])) / np.max(np.abs(o['x'][sl])))
+            cpt = omod.constrain(pt, _DS[b])
+            for raw, name in (('Rinf_raw', 'Rinf'), ('sigma_res_raw', 'sigma_res')):  # theta ~ exp(u): d theta = theta du
+                e = max(e, float(abs(st[ps[raw]][0]) * cpt[name] / (cpt[name] + 0.2)))
+            est.append(e)
     c = omod.constrain(o['x'], _DS[b])
     return dict(x=c['x'], Rinf=c['Rinf'], sigma_res=c['sigma_res'], f=o['f'], gnorm=o['gnorm'], failed=o['failed'],
                 est_oracle=est[0], est_cuda=est[1])
