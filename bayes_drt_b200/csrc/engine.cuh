@@ -82,6 +82,8 @@ struct BdrtModel {
   int oCur;
   int wmode;  // warp mode: Toeplitz operands, warp-private Hankel products (engine_eval<2, ..>), no CTA barriers
   int pslot;  // warp mode with per-spectrum grids: tables and omega live in the slot's scratch
+  int wsync;  // warp mode, solver kernels: one CTA barrier at the entry of every evaluation (none inside) keeps the eight
+              // warps of a CTA in step through the straight-line engine code, so that they share instruction-cache lines
   int vim;    // offset of the imaginary part inside a V row (nfp; warp mode: nfp + 12, zero gap for the sliding window)
   int xz;     // phase 1 zeroes x[K .. xz)
   int oOmS;   // pslot: offset of the slot's omega [Nf] inside its scratch
@@ -378,6 +380,11 @@ __device__ __forceinline__ double engine_eval(const BdrtModel& m, double* sm, bo
   // global-dense operands: the spectrum whose grids the CTA has loaded (engine_load)
   const long long gsp = (TOEP == 0 && m.gdense) ? *reinterpret_cast<const long long*>(sm + m.oCur) : 0;
   if (TOEP == 2) {
+    if (m.wsync && snap) {
+      // synchronised warp mode: every warp of the CTA calls in every round (finished ones with active = false) and the
+      // barrier itself counts the slots that still work -- the same number in every warp
+      *snap = __syncthreads_count(active ? 1 : 0);
+    }
     if (!active) return 0.0;  // warp mode: nobody else needs this warp
     __syncwarp();
   }

@@ -187,7 +187,7 @@ lbfgs_kernel(BdrtModel m, bdrt_lbfgs_opts o, double* __restrict__ U, double* lp_
   // f(xn) -> f, gn = grad f ; returns false when not finite
   // also returns the slope gn . pk along the current direction (same summation order as vdot): one pass instead of two
   auto feval = [&](double& f, double& slope) -> bool {
-    const double lp = engine_eval<TOEP, MK, FAST>(m, sm, true, xn, gn, Zs, 0);
+    const double lp = engine_eval<TOEP, MK, FAST>(m, sm, true, xn, gn, Zs, 0, n_active, TOEP == 2 ? &snap : nullptr);
     ++neval;
     int fin = isfinite(lp);
     double d = 0.0;
@@ -427,6 +427,11 @@ lbfgs_kernel(BdrtModel m, bdrt_lbfgs_opts o, double* __restrict__ U, double* lp_
       if (b >= m.B) break;
       if (m.pslot) engine_load_slot(m, sm, b);
       run_spectrum(b);
+    }
+    if (m.wsync) {  // synchronised warp mode: keep answering the barrier until every slot of the CTA is done
+      do {
+        engine_eval<TOEP, MK, FAST>(m, sm, false, nullptr, nullptr, nullptr, 0, n_active, &snap);
+      } while (snap != 0);
     }
   } else {
   const bool per_spec = m.d[0].A_stride != 0;

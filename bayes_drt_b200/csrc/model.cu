@@ -336,6 +336,10 @@ int bdrt_model_prepare(bdrt_ctx* ctx, const bdrt_series_data* d, BdrtModel* m, s
   m->wmode = m->toepA && allow_wmode && !((allow_wmode == 1 || allow_wmode == 3) && force_coop);
   if (allow_wmode == 3 && !d->per_spectrum_grid && !force_warp) m->wmode = 0;
   m->pslot = m->wmode && d->per_spectrum_grid;
+  {  // BDRT_WSYNC=1: synchronised warp mode in the solver kernels (A/B measurements)
+    const char* fs = getenv("BDRT_WSYNC");
+    m->wsync = m->wmode && fs && fs[0] == '1';
+  }
   // register-tiled per-slot phases: every distribution has Toeplitz L within FBW off-diagonals and K <= 128
   // (BDRT_FORCE_GENERIC=1 keeps the generic per-slot code, for tests)
   const char* fg = getenv("BDRT_FORCE_GENERIC");

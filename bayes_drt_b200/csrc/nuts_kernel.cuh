@@ -103,7 +103,8 @@ nuts_kernel(BdrtModel m, bdrt_nuts_opts o, const double* __restrict__ U0, double
       q[i] = fma(eps * mi[i], pi, q[i]);
     }
     __syncwarp();
-    const double lp = engine_eval<TOEP, MK, FAST>(m, sm, true, q, g, Zs, 1);
+    int rsnap;
+    const double lp = engine_eval<TOEP, MK, FAST>(m, sm, true, q, g, Zs, 1, n_active, TOEP == 2 ? &rsnap : nullptr);
     ++n_grad;
     double ks = 0.0;
     NUTS_SWEEP(i) {
@@ -143,7 +144,8 @@ nuts_kernel(BdrtModel m, bdrt_nuts_opts o, const double* __restrict__ U0, double
       v[V_MINV][i] = 1.0;
     }
     __syncwarp();
-    double s_lp = engine_eval<TOEP, MK, FAST>(m, sm, true, v[V_SQ], v[V_SG], Zs, 1);
+    int rsnap0;
+    double s_lp = engine_eval<TOEP, MK, FAST>(m, sm, true, v[V_SQ], v[V_SG], Zs, 1, n_active, TOEP == 2 ? &rsnap0 : nullptr);
     ++n_grad;
     bool bad = !isfinite(s_lp);
 
@@ -404,6 +406,12 @@ nuts_kernel(BdrtModel m, bdrt_nuts_opts o, const double* __restrict__ U0, double
         engine_load_slot(m, sm, loaded);
       }
       run_chain(wi);
+    }
+    if (m.wsync) {  // keep answering the barrier until every slot of the CTA is done
+      int snap;
+      do {
+        engine_eval<TOEP, MK, FAST>(m, sm, false, nullptr, nullptr, nullptr, 0, n_active, &snap);
+      } while (snap != 0);
     }
   } else {
   const bool per_spec = m.d[0].A_stride != 0;
