@@ -5,7 +5,8 @@ paper's data sets, what ``StanModel.optimizing`` (pystan 2.19, Stan's L-BFGS) re
 transformed parameter of the Stan program (``_opt_result``) -- next to the kernel / penalty matrices the fit used
 (``distribution_matrices``), the frequency grid, the scaling factor and the distribution settings.  pystan is not
 installable here, so these files are the only numbers in the tree that Stan itself computed.  This script reads them
-in place (build container only) together with the spectra ``data/simulated/Z_<name>.csv`` and writes
+in place (build container only) together with the spectra (``data/simulated/Z_<name>.csv``, three files of
+``data/experimental/``) and writes
 ``tests/golden/stan_map.npz``:
 
   <name>/model            Stan program (file name the reference pickled)
@@ -22,7 +23,7 @@ The Stan programs of that version of the package differ from the current ones on
 instead of ``induc_raw * induc_scale`` (diff of stan_model_files/*_modelcode.txt against
 code_EchemActa/bayes-drt_20201113/stan_model_files/), i.e. not at all for the default ``induc_scale = 1``.
 
-    python scripts/make_golden_stan_map.py            (writes the fixture and prints what the oracle makes of it)
+    python scripts/make_golden_stan_map.py
 """
 import glob
 import json
@@ -64,6 +65,29 @@ def proj_vectors(n_rows, n_cols):
     return rng.standard_normal(n_rows), rng.standard_normal(n_cols)
 
 
+EXPERIMENTAL = {'PDAC': 'PDAC_COM3_02109_Contact10_2065C_500C.txt', 'LIB_data': 'DRTtools_LIB_data.txt',
+                'LIB_data_qtr': 'DRTtools_LIB_data_qtr.csv'}
+
+
+def read_experimental(path):
+    """Freq, Z of the three experimental files the paper fits (a Gamry table, a 3-column text file, a csv)."""
+    import pandas as pd
+    if path.endswith('.csv'):
+        df = pd.read_csv(path)
+        return df['Freq'].values, df['Zreal'].values + 1j * df['Zimag'].values
+    with open(path, encoding='latin-1') as fh:
+        lines = fh.read().splitlines()
+    hdr = [i for i, ln in enumerate(lines) if 'Freq' in ln.split('\t') and 'Zreal' in ln.split('\t')]
+    if hdr:  # Gamry: header row, units row, data rows (leading tab)
+        cols = lines[hdr[0]].split('\t')
+        iF, iR, iI = cols.index('Freq'), cols.index('Zreal'), cols.index('Zimag')
+        rows = [ln.split('\t') for ln in lines[hdr[0] + 2:] if ln.strip()]
+        a = np.array([[float(r[iF]), float(r[iR]), float(r[iI])] for r in rows])
+    else:
+        a = np.array([[float(v) for v in ln.split()] for ln in lines if ln.strip()])
+    return a[:, 0], a[:, 1] + 1j * a[:, 2]
+
+
 KEEP = ('Rinf_raw', 'induc', 'induc_raw', 'x', 'xs', 'xp_raw', 'xp1_raw', 'xp2_raw', 'sigma_res_raw', 'alpha_prop_raw',
         'alpha_re_raw', 'alpha_im_raw', 'ups_raw', 'ups_s_raw', 'ups_p_raw', 'ups_p1_raw', 'ups_p2_raw', 'd0_strength',
         'd1_strength', 'd2_strength', 'd0s_strength', 'd1s_strength', 'd2s_strength', 'd0p_strength', 'd1p_strength',
@@ -79,15 +103,20 @@ def main():
     names = []
     for path in sorted(glob.glob(os.path.join(REF, 'code_EchemActa/map_results/obj_*.pkl'))):
         name = os.path.basename(path)[4:-4]
-        csv = os.path.join(REF, 'data/simulated', f'Z_{name}.csv')
-        if not os.path.exists(csv):
-            continue  # experimental data sets (other file formats, loaders out of scope)
         d = load_obj(path)
-        if 'outliers' in d['stan_model_name'] and 'Parallel' in d['stan_model_name']:
-            continue  # *_outliers of the parallel families: not implemented
-        df = pd.read_csv(csv)
-        f_all = df['Freq'].values
-        Z_all = df['Zreal'].values + 1j * df['Zimag'].values
+        if 'outliers' in d['stan_model_name']:
+            # the outlier programs of that version differ from the current ones (one sigma_out per stacked element, no
+            # sigma_out_scale: diff of Series_outliers_modelcode.txt), so their results are not results of today's program
+            continue
+        csv = os.path.join(REF, 'data/simulated', f'Z_{name}.csv')
+        if os.path.exists(csv):
+            df = pd.read_csv(csv)
+            f_all = df['Freq'].values
+            Z_all = df['Zreal'].values + 1j * df['Zimag'].values
+        elif name in EXPERIMENTAL:
+            f_all, Z_all = read_experimental(os.path.join(REF, 'data/experimental', EXPERIMENTAL[name]))
+        else:
+            continue  # two-distribution fits of the experimental spectra: settings not recoverable from the object
         ft = np.asarray(d['f_train'], dtype=np.float64)
         idx = [int(np.argmin(np.abs(np.log(f_all) - np.log(f)))) for f in ft]
         if not np.allclose(f_all[idx], ft, rtol=1e-9):

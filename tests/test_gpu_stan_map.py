@@ -3,7 +3,7 @@ tests/golden/stan_map.npz, see test_oracle_stan_map.py).  At the parameter value
 kernel / penalty matrices built by the CUDA kernels for the stored grids:
 
   * ``bdrt_constrain`` reproduces Stan's transformed parameters (sigma_tot -- which contains Z_hat --, R_inf, xp) to 1e-9
-    for all 23 fits: 'Series', 'Series_pos', 'Series-Parallel_pos' and 'Series-2Parallel_pos' programs;
+    for all 25 fits: 'Series', 'Series_pos', 'Series-Parallel_pos' and 'Series-2Parallel_pos' programs;
   * the fused log density / gradient equals the oracle's there (1e-11 / 1e-9), so the stationarity statements of
     test_oracle_stan_map.py carry over;
   * where Stan converged tightly, ``bdrt_map_newton`` started from Stan's end point stays there: x within 1e-2 of its
