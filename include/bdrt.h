@@ -174,7 +174,10 @@ int bdrt_map_lbfgs(bdrt_ctx* ctx, const bdrt_series_data* data, const bdrt_lbfgs
                    int* iters, int* n_eval, int* status);
 
 /* Damped-Newton polish of MAP estimates (not in the reference: brings both sides of the parity test to the unique
- * optimum, SURVEY.md section 7 hard part 1).  u [B,D] in/out; gnorm [B] = max|grad| at the result. */
+ * optimum, SURVEY.md section 7 hard part 1).  u [B,D] in/out; gnorm [B] = max|grad| over the free coordinates at the
+ * result.  Stops on max|grad| < gtol, on max_iter, or at the rounding floor of the gradient (six iterations that did
+ * not halve the best max|grad| below 1e-6: the floor is 1e-10 .. 1e-8 depending on the spectrum).  lower=0 parameters
+ * whose optimum is theta = 0 are returned at u = -40 (theta = 4e-18). */
 typedef struct {
   int max_iter;   /* Newton iterations (default 200) */
   double gtol;    /* stop when max|grad| < gtol (default 1e-9) */
