@@ -1,0 +1,142 @@
+"""CPU: the exact QP solver and the hyper-lambda update against REAL cvxopt output -- 55 quadratic programs from nine
+hyper-parametric ridge fits the reference's authors saved for their paper (every hyper-iteration's lambda vector, the
+solution ``cvxopt.solvers.qp`` returned, its primal objective and duality gap; fixture tests/golden/cvxopt_ridge.npz,
+made by scripts/make_golden_cvxopt_ridge.py, which also asserts that each stored objective is reproduced to 1e-11 by
+the program it reads into the object).  cvxopt is not installable here: these are the only QP solutions in the tree that
+cvxopt computed.
+
+  * the oracle's kernel / penalty matrices are the ones those fits used (that version's conventions: columns
+    [R_inf, inductance, basis], imaginary part stored for -Z'');
+  * oracle.ridge.qp_bound solves 45 of the 55 programs at its tight tolerances to a KKT residual below 1e-9, and there its
+    objective is never above cvxopt's and never more than cvxopt's own duality gap below it: the exact solution is the
+    point cvxopt's interior iterates were converging to (inversion.py:1043-1067); the other ten are near-singular
+    (condition 1e11 .. 1e17: lambda_0 from cross-validation is tiny) and finish after the sign tolerances were relaxed,
+    within 2e-4 relative of cvxopt's objective;
+  * the programs are flat: cvxopt's solution, optimal to 1e-6 relative in the objective, reproduces the exact solution's
+    fitted impedance to 1e-4 .. 7e-3 but is up to the height of the peak away from it in single coefficients (sharp-peaked
+    circuits under a wide basis) -- measured here, and the reason parity of the ridge path is stated against the exact
+    solution, not against cvxopt's last iterate;
+  * the lambda vector the reference computed from each cvxopt solution is oracle.ridge.hyper_lambda_fbeta of it
+    (inversion.py:956-964), 1e-12."""
+import os
+
+import numpy as np
+import pytest
+
+from oracle import matrices as om, ridge as oridge
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+PROJ_SEED = 20201113
+_G = None
+
+
+def G():
+    global _G
+    if _G is None:
+        with np.load(os.path.join(ROOT, 'tests', 'golden', 'cvxopt_ridge.npz')) as g:
+            _G = {k: g[k] for k in g.files}
+    return _G
+
+
+NAMES = [str(n) for n in np.load(os.path.join(ROOT, 'tests', 'golden', 'cvxopt_ridge.npz'))['names']]
+
+
+def proj_vectors(n_rows, n_cols):
+    rng = np.random.RandomState(PROJ_SEED + 1000 * n_rows + n_cols)
+    return rng.standard_normal(n_rows), rng.standard_normal(n_cols)
+
+
+def matrices(name):
+    g = G()
+    p = name + '/'
+    freq, tau, eps = g[p + 'freq'], g[p + 'tau'], float(g[p + 'eps'])
+    Nf = len(freq)
+    A_re = np.hstack((np.ones((Nf, 1)), np.zeros((Nf, 1)), om.construct_A(freq, 'real', tau=tau, epsilon=eps)))
+    A_im = np.hstack((np.zeros((Nf, 1)), -2 * np.pi * freq[:, None], -om.construct_A(freq, 'imag', tau=tau, epsilon=eps)))
+    L2 = np.hstack((np.zeros((len(tau), 2)), om.construct_L(1 / (2 * np.pi * tau), tau=tau, epsilon=eps, order=2)))
+    return A_re, A_im, L2
+
+
+def programs(name):
+    """-> L2 (padded), list of (P, q, cvxopt coef, cvxopt objective, cvxopt gap, lambda_next)"""
+    g = G()
+    p = name + '/'
+    L2 = matrices(name)[2]
+    Gm = L2.T @ L2
+    q = g[p + 'q']
+    n = len(q)
+    P0 = np.zeros((n, n))
+    P0[np.triu_indices(n)] = g[p + 'P0_triu']
+    P0 = P0 + np.triu(P0, 1).T
+    out = []
+    for i in range(len(g[p + 'cost'])):
+        s = g[p + 'lam'][i] ** 0.5
+        out.append((P0 + s[:, None] * Gm * s[None, :], q, g[p + 'coef'][i], g[p + 'cost'][i], g[p + 'gap'][i],
+                    g[p + 'lam_next'][i]))
+    return L2, out
+
+
+def data_gram(name):
+    """A_re'A_re + A_im'A_im of that run (the lambda-independent part of P)."""
+    g = G()
+    q = g[name + '/q']
+    n = len(q)
+    P0 = np.zeros((n, n))
+    P0[np.triu_indices(n)] = g[name + '/P0_triu']
+    return P0 + np.triu(P0, 1).T
+
+
+@pytest.mark.parametrize('name', NAMES)
+def test_matrices_are_the_ones_those_fits_used(name):
+    g = G()
+    for mn, M, tol in zip(('A_re', 'A_im', 'L2'), matrices(name), (1e-6, 1e-6, 1e-12)):  # (that version's quadrature: 1e-7 off today's)
+        l, r = proj_vectors(*M.shape)
+        for side, v in (('r', M @ r), ('l', l @ M)):
+            ref = g[name + f'/proj/{mn}/{side}']
+            assert np.max(np.abs(v - ref)) <= tol * np.max(np.abs(ref)), (name, mn, side)
+
+
+@pytest.mark.parametrize('name', NAMES)
+def test_exact_qp_against_cvxopt_solutions(name):
+    L2, progs = programs(name)
+    worst, relaxed, dz = 0.0, 0, 0.0
+    Pdata = data_gram(name)
+    for P, q, c, f_cvx, gap, _ in progs:
+        f = lambda x: 0.5 * x @ P @ x + q @ x  # noqa: E731
+        assert abs(f(c) - f_cvx) <= 1e-10 * abs(f_cvx)  # the program is the one cvxopt solved
+        assert c.min() >= 0.0
+        x, y, F, it = oridge.qp_bound(P, q, np.zeros(len(q)))
+        scale = np.max(np.abs(q))
+        assert x.min() >= 0.0
+        if it <= 100:  # solved at the tight tolerances
+            assert np.max(np.abs(y[F])) <= 1e-9 * scale and y[~F].min() >= -1e-9 * scale  # KKT
+            assert f(x) <= f_cvx + 1e-12 * abs(f_cvx)        # never worse than cvxopt
+            assert f_cvx - f(x) <= 1.05 * gap, (f_cvx - f(x), gap)  # and within cvxopt's own duality gap of it
+        else:  # near-singular program (condition 1e11 .. 1e17), solved after the tolerances were relaxed
+            relaxed += 1
+            assert y[~F].min() >= -1e-4 * scale
+            assert abs(f(x) - f_cvx) <= 2e-4 * abs(f_cvx)
+        worst = max(worst, np.max(np.abs(x - c)) / np.max(np.abs(c[2:])))
+        # in data space (the norm of the fitted impedance, x'(A'A)x) the two solutions agree
+        dz = max(dz, np.sqrt((x - c) @ Pdata @ (x - c) / (c @ Pdata @ c)))
+    assert dz <= 1e-2, dz
+    # flat programs: a 1e-6-optimal objective leaves the COEFFICIENTS this far from the exact solution (reported, not bounded:
+    # for the sharp-peaked circuits under a wide basis neighbouring basis functions are interchangeable)
+    assert relaxed <= 3, relaxed
+    print(f'{name}: {len(progs)} programs ({relaxed} relaxed), fitted impedance within {dz:.1e}, coefficients up to '
+          f'{worst:.1e} of the peak from the exact solution')
+
+
+@pytest.mark.parametrize('name', NAMES)
+def test_lambda_update_is_the_references(name):
+    g = G()
+    L2, progs = programs(name)
+    fbeta, lam0 = float(g[name + '/fbeta']), float(g[name + '/lambda_0'])
+    n = 0
+    for P, q, c, _, _, nxt in progs:
+        if np.isnan(nxt[0]):
+            continue
+        mine = oridge.hyper_lambda_fbeta(L2[:, 2:], c[2:], fbeta, lam0)
+        assert np.max(np.abs(mine[2:] - nxt[2:]) / nxt[2:]) <= 1e-12
+        n += 1
+    assert n == len(progs) - 1
