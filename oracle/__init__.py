@@ -17,9 +17,18 @@ Parity pinning
   ``scripts/make_golden_matrices.py``; outputs committed in ``tests/golden/matrices.npz``).
 * The Stan programs, Stan's L-BFGS / NUTS and cvxopt's QP are third-party
   natives that are absent from the reference tree and from this image
-  (pystan==2.19.1.1, cvxopt).  The reference ships no test or golden vector
-  for them, so for those parts the oracle is a restatement of the published
-  algorithm anchored on the reference's call sites and on the loose paper
-  outputs in ``code_EchemActa`` -- **parity unpinned** in the strict sense
-  (see DESIGN.md).
+  (pystan==2.19.1.1, cvxopt), and the reference ships no test for them.
+  What the tree does hold are results its authors saved for their paper:
+  - ``code_EchemActa/map_results/obj_*.pkl``: everything ``StanModel.optimizing``
+    returned for 25 MAP fits -> the model arithmetic, the constants handed to
+    Stan and the location of the optimum are pinned to Stan's own numbers
+    (``tests/golden/stan_map.npz``, ``tests/test_oracle_stan_map.py``);
+  - ``code_EchemActa/comparisons/hyper-ridge/results/obj_*.pkl``: every QP
+    solution of nine hyper-lambda ridge fits with cvxopt's objective and gap ->
+    the exact QP solver and the lambda update are pinned to cvxopt in the
+    objective (``tests/golden/cvxopt_ridge.npz``,
+    ``tests/test_oracle_cvxopt_ridge.py``).
+  What stays **unpinned** is the path of Stan's optimiser and its sampler
+  (restatements of the published algorithms, compared with the CUDA drivers
+  statistically / iterate by iterate).
 """

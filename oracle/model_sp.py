@@ -18,8 +18,9 @@ Every parameter is ``lower=0`` (theta = exp(u)) except ``xs`` in the non-_pos va
 ``real<lower=0> x_sum_raw = sum(xs) + sum(xp_raw)`` (:56) is validity-checked by Stan: a negative value rejects the
 point (log density -inf); that can only happen in the non-_pos variant.
 
-**Parity unpinned** (pystan absent, no reference golden vector): checked against the literal autograd transcription
-``oracle.stan_literal.logpost_literal_sp``.
+Pinned to the Stan source text (tests/test_oracle_stan_source.py) and, for Series-Parallel_pos and Series-2Parallel_pos, to
+Stan's own output: at the parameter values of the paper's saved MAP fits ``constrain`` reproduces Stan's transformed
+parameters to 1e-15 (tests/test_oracle_stan_map.py; also fixes the by-name ordering of two parallel distributions).
 """
 import numpy as np
 

@@ -12,7 +12,9 @@ Inverter.ridge_fit (imported from the reference, scripts/make_golden_ridge_refer
 (defaults, presets 'Huang' / 'Ciucci', integral / discrete / cholesky penalties, free sign, mixed orders, one-part fits,
 hl_fbeta, Re-Im cross-validation) and this restatement reproduces them to 1e-9 (1e-6 for the max-normalised hl_fbeta
 rule) -- tests/test_oracle_solvers.py.  The one substitution in that run is the QP solver: cvxopt.solvers.qp
-(third-party, absent here: its own arithmetic stays **unpinned**) is replaced by the exact solver below.  Each QP is
+(third-party, absent here) is replaced by the exact solver below -- which is pinned to real cvxopt output in the
+objective: on 55 programs of the paper's saved hyper-ridge fits it is never above cvxopt's objective and within cvxopt's
+own duality gap of it (tests/test_oracle_cvxopt_ridge.py).  Each QP is
 strictly convex with simple bounds, so its solution is unique; the oracle solves it *exactly* by block principal
 pivoting (active-set with exact Cholesky solves, KKT residual ~1e-13), which is what cvxopt's interior-point iterates
 converge to within its own tolerances (abstol 1e-7, reltol 1e-6).
