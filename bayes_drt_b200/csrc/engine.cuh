@@ -479,15 +479,17 @@ __device__ __forceinline__ double engine_eval(const BdrtModel& m, double* sm, bo
         }
         for (int k = 128 + lane; k < (TOEP == 2 ? m.xz : 128 + FBW + 2); k += 32) sX[k] = 0.0;
         __syncwarp();
-        // 1b. a_j = L_j x, q^2, dups, d lp / d ups, W_j = d_j a_j / ups^2   (lanes past K work on zeros / stale scratch
-        // and store nothing)
+        // 1b. a_j = L_j x, q^2, dups, d lp / d ups, W_j = d_j a_j / ups^2.  Lanes past K load the windows of the last
+        // tile (so that no lane reads beyond the slot's own rows -- the next slot's scratch belongs to another warp),
+        // compute on them and store nothing; every sum is masked by the true index.
+        const int kql = kq < Dd.kpad4 ? kq : Dd.kpad4 - 4;
         const double d0 = sTh[6 + 3 * dd], d1 = sTh[7 + 3 * dd], d2 = sTh[8 + 3 * dd];
         double sa0 = 0, sa1 = 0, sa2 = 0;
         double gu4[4];
         {
           double xw[16];  // x[kq - 6 .. kq + 9]
 #pragma unroll
-          for (int i = 0; i < 8; ++i) ld2(sX + kq - FBW + 2 * i, xw[2 * i], xw[2 * i + 1]);
+          for (int i = 0; i < 8; ++i) ld2(sX + kql - FBW + 2 * i, xw[2 * i], xw[2 * i + 1]);
           double a0[4] = {0, 0, 0, 0}, a1[4] = {0, 0, 0, 0}, a2[4] = {0, 0, 0, 0};
 #pragma unroll
           for (int t = 0; t < 2 * FBW + 1; ++t) {
@@ -501,8 +503,8 @@ __device__ __forceinline__ double engine_eval(const BdrtModel& m, double* sm, bo
           double upw[8], iuw[8];  // ups / (1/ups) [kq - 2 .. kq + 5]; own values at index j + 2
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
-            ld2(sUps + kq - 2 + 2 * i, upw[2 * i], upw[2 * i + 1]);
-            ld2(sIu + kq - 2 + 2 * i, iuw[2 * i], iuw[2 * i + 1]);
+            ld2(sUps + kql - 2 + 2 * i, upw[2 * i], upw[2 * i + 1]);
+            ld2(sIu + kql - 2 + 2 * i, iuw[2 * i], iuw[2 * i + 1]);
           }
           double w0[4], w1[4], w2[4];
 #pragma unroll
@@ -538,7 +540,9 @@ __device__ __forceinline__ double engine_eval(const BdrtModel& m, double* sm, bo
             }
             gu4[j] = gu * upk - (m.ups_alpha + 1.0) + m.ups_beta * 0.15 * iuk + jac;
           }
-          // margins of the three scratch vectors (the previous evaluation's Z / G row was here)
+          // margins of the three scratch vectors (the previous evaluation's Z / G row was here); lane 0's ups window
+          // starts two entries inside the last margin, so the loads above must be complete in every lane first
+          __syncwarp();
 #pragma unroll
           for (int q = 0; q < 3; ++q) {
             if (lane < m.wm) sW[q * m.ws - m.wm + lane] = 0.0;
@@ -566,7 +570,7 @@ __device__ __forceinline__ double engine_eval(const BdrtModel& m, double* sm, bo
           for (int q = 0; q < 3; ++q) {
             double ww[16];  // W_q[kq - 6 .. kq + 9]
 #pragma unroll
-            for (int i = 0; i < 8; ++i) ld2(sW + q * m.ws + kq - FBW + 2 * i, ww[2 * i], ww[2 * i + 1]);
+            for (int i = 0; i < 8; ++i) ld2(sW + q * m.ws + kql - FBW + 2 * i, ww[2 * i], ww[2 * i + 1]);
 #pragma unroll
             for (int j = 0; j < 4; ++j) acc[q][j] = 0.0;
 #pragma unroll

@@ -119,6 +119,7 @@ __device__ void chol8_inv(double* D, int ld, double* Li, int lane, int* flag) {
       row[c] = fma(-row[j], lcj, row[c]);
     }
   }
+  __syncwarp();  // (lanes 8 .. 31 read the same rows as lanes 0 .. 7: their loads come before the write-back)
   if (lane < 8) {
 #pragma unroll
     for (int c = 0; c < 8; ++c) D[r * ld + c] = (c <= r) ? row[c] : 0.0;

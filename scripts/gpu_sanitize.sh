@@ -1,9 +1,13 @@
 #!/bin/bash
 # compute-sanitizer (memcheck, then racecheck on shared memory) over a slice of the GPU tests and over a small run of every
 # solver on every operand layout of the engine.  Output: gpurun_out/sanitize_*.log and a summary on stdout.
+# `bash scripts/gpu_sanitize.sh race` runs the racecheck part only.
 mkdir -p gpurun_out
+ONLY=$1
+if [ "$ONLY" != race ]; then
 T="tests/test_gpu_logpost.py::test_logpost_S_shape tests/test_gpu_logpost.py::test_logpost_non_toeplitz_grid tests/test_gpu_series_parallel.py::test_sp_logpost_matches_oracle tests/test_gpu_series_parallel.py::test_sp_dense_too_large_goes_global tests/test_gpu_summaries.py tests/test_gpu_matrices.py tests/test_gpu_ridge.py::test_qp_bound_random_problems tests/test_gpu_cvxopt_ridge.py tests/test_gpu_stan_map.py::test_cuda_newton_from_stans_optimum_stays_there"
 timeout 1500 compute-sanitizer --tool memcheck --error-exitcode 9 python -m pytest $T -x -q -m gpu > gpurun_out/sanitize_memcheck.log 2>&1; echo "memcheck tests rc=$?"; grep -E "ERROR SUMMARY|passed|failed|Invalid|out of bounds" gpurun_out/sanitize_memcheck.log | head -20
+fi
 cat > /tmp/san_small.py <<'PY'
 import sys, os
 sys.path.insert(0, os.getcwd()); sys.path.insert(0, os.path.join(os.getcwd(), 'tests'))
@@ -32,6 +36,7 @@ inv.ridge_fit(fr, Zb, max_iter=3)
 torch.cuda.synchronize()
 print('ok per-spectrum grids', inv.R_inf.tolist())
 PY
+if [ "$ONLY" != race ]; then
 for mode in default warp dense gdense; do
   unset BDRT_WARP BDRT_FORCE_DENSE BDRT_FORCE_GDENSE
   [ $mode = warp ] && export BDRT_WARP=1
@@ -39,6 +44,7 @@ for mode in default warp dense gdense; do
   [ $mode = gdense ] && export BDRT_FORCE_DENSE=1 BDRT_FORCE_GDENSE=1
   timeout 1500 compute-sanitizer --tool memcheck --error-exitcode 9 python /tmp/san_small.py > gpurun_out/sanitize_solvers_$mode.log 2>&1; echo "memcheck solvers $mode rc=$?"; grep -E "ERROR SUMMARY|^ok|Invalid|out of bounds" gpurun_out/sanitize_solvers_$mode.log | head -6
 done
+fi
 for mode in default warp; do
   unset BDRT_WARP BDRT_FORCE_DENSE BDRT_FORCE_GDENSE
   [ $mode = warp ] && export BDRT_WARP=1
