@@ -17,7 +17,9 @@ cvxopt computed.
     circuits under a wide basis) -- measured here, and the reason parity of the ridge path is stated against the exact
     solution, not against cvxopt's last iterate;
   * the lambda vector the reference computed from each cvxopt solution is oracle.ridge.hyper_lambda_fbeta of it
-    (inversion.py:956-964), 1e-12."""
+    (inversion.py:956-964), 1e-12;
+  * the whole iteration replayed from the first stored lambda vector with the exact solver stays on the trajectory of the
+    reference's run."""
 import os
 
 import numpy as np
@@ -140,3 +142,33 @@ def test_lambda_update_is_the_references(name):
         assert np.max(np.abs(mine[2:] - nxt[2:]) / nxt[2:]) <= 1e-12
         n += 1
     assert n == len(progs) - 1
+
+
+# fits whose programs are not flat enough for cvxopt's tolerance to move the coefficients (and with them the curvature
+# L2 c that drives the next lambda vector) by more than a few per cent
+WELL = ['ZARC_uniform_0.25_fbeta=10', '2RC_uniform_2.5_fbeta=0.1', 'Gerischer_uniform_1.0_fbeta=1',
+        'Gerischer_uniform_0.25_fbeta=100', '2ZARC_uniform_1.0_fbeta=10', 'RC_uniform_0.25_fbeta=0.01']
+
+
+@pytest.mark.parametrize('name', NAMES)
+def test_hyper_loop_replay_tracks_the_references_run(name):
+    """The whole hyper-lambda iteration replayed from the first stored lambda vector with the EXACT solver (QP -> lambda update -> QP ...) next to
+    the trajectory the reference's run took with cvxopt: the objective of every iteration within 3 duality gaps, and --
+    for the six fits that are not flat -- every lambda vector within 5 % of the stored one."""
+    g = G()
+    L2, progs = programs(name)
+    Gm, P0, q = L2.T @ L2, data_gram(name), g[name + '/q']
+    fbeta, lam0 = float(g[name + '/fbeta']), float(g[name + '/lambda_0'])
+    lam = g[name + '/lam'][0].copy()  # the first stored program (its lambda vector already carries one update)
+    for i in range(len(progs)):
+        s = lam ** 0.5
+        P = P0 + s[:, None] * Gm * s[None, :]
+        x = oridge.qp_bound(P, q, np.zeros(len(q)))[0]
+        f = 0.5 * x @ P @ x + q @ x
+        ref_lam, f_cvx, gap = g[name + '/lam'][i], g[name + '/cost'][i], g[name + '/gap'][i]
+        if name in WELL:
+            assert np.max(np.abs(lam[2:] - ref_lam[2:]) / ref_lam[2:]) <= 5e-2, (i, name)
+            assert abs(f - f_cvx) <= 3 * gap, (i, f - f_cvx, gap)
+        else:
+            assert abs(f - f_cvx) <= 2e-4 * abs(f_cvx), (i, f - f_cvx)
+        lam = oridge.hyper_lambda_fbeta(L2[:, 2:], x[2:], fbeta, lam0)
