@@ -72,7 +72,16 @@ class OracleProblem:
                     n_eval=torch.tensor([r['n_eval'] for r in rs], dtype=torch.int32),
                     status=torch.tensor([r['code'] for r in rs], dtype=torch.int32))
 
+    def subset(self, a, b):
+        """spectra a .. b - 1 as a problem of their own (capi.SeriesProblem.subset)"""
+        import copy
+        sub = copy.copy(self)
+        sub.ds, sub.B = self.ds[a:b], b - a
+        return sub
+
     def nuts(self, u0, chains=2, warmup=200, samples=200, seed=0, spectrum_ids=None, **kw):
+        # (random streams keyed by the GLOBAL spectrum index, like the CUDA sampler's Philox key)
+        ids = np.arange(self.B) if spectrum_ids is None else np.asarray(spectrum_ids).reshape(-1)
         u0 = np.asarray(u0, dtype=np.float64).reshape(self.B, chains, self.D)
         draws = np.empty((self.B, chains, samples, self.D))
         st = {k: np.zeros((self.B, chains)) for k in ('stepsize', 'n_leapfrog', 'n_divergent', 'n_maxdepth', 'accept')}
@@ -81,7 +90,8 @@ class OracleProblem:
                 with np.errstate(all='ignore'):
                     return self.mod.logpost(u, d, jacobian=True)
             for c in range(chains):
-                r = onuts.sample_chain(lg, u0[b, c], warmup=warmup, samples=samples, seed=seed * 1000 + b * chains + c)
+                r = onuts.sample_chain(lg, u0[b, c], warmup=warmup, samples=samples,
+                                       seed=seed * 1000 + int(ids[b]) * chains + c)
                 draws[b, c] = r['draws']
                 for k in st:
                     st[k][b, c] = r.get(k, 0.0)

@@ -75,6 +75,29 @@ def test_sample_fit_percentiles_and_draw_queries(inverter):
     assert (s_lo <= s_hi).all()
 
 
+def test_sample_fit_in_pieces_equals_one_batch(inverter):
+    """keep_draws=False runs a large HMC batch through the sampler in bounded pieces (prob.subset) and summarises each
+    before the next: same posterior means, diagnostics and sampler statistics as the one-batch run (the random streams
+    are keyed by the global spectrum index), and no draws are kept."""
+    freq, Z = load_spectrum('ZARC_uniform_0.25')
+    f, Zb = freq[::4], np.stack([Z[::4], 1.1 * Z[::4], 0.9 * Z[::4]])
+    bf = np.logspace(5, -1, 21)
+    u0 = np.zeros((3, 2, 2 * 21 + 9))
+    kw = dict(mode='sample', chains=2, warmup=15, samples=10, init=torch.tensor(u0), check_outliers=False)
+    one = inverter.Inverter(basis_freq=bf)
+    one.fit(f, Zb, **kw)
+    pieces = inverter.Inverter(basis_freq=bf)
+    pieces._hmc_piece = 2  # pieces [0:2] and [2:3]
+    pieces.fit(f, Zb, keep_draws=False, **kw)
+    assert np.allclose(pieces.distribution_fits['DRT']['coef'], one.distribution_fits['DRT']['coef'], rtol=1e-12)
+    assert np.allclose(pieces.R_inf, one.R_inf, rtol=1e-12)
+    for k in ('stepsize', 'n_leapfrog', 'rhat', 'ess_bulk'):
+        assert np.allclose(np.asarray(pieces._sample_stats[k]), np.asarray(one._sample_stats[k]), equal_nan=True), k
+    assert pieces._sample_result is None and one._sample_result is not None
+    with pytest.raises(Exception):
+        pieces.coef_percentile('DRT', 50)
+
+
 def test_multi_distribution_fits_shapes_and_scaling(inverter):
     """Series-Parallel / Series-2Parallel / Parallel through the host code: coefficient blocks per distribution, series
     coefficients scaled up and parallel ones scaled down by Z_scale (inversion.py:2445-2450)."""
