@@ -25,7 +25,6 @@ recoverable from the objects.
   <name>/coef [n, K+2]   cvxopt's solution, <name>/cost [n] its primal objective, <name>/gap [n] its duality gap
   <name>/lam_next [n, K+2]  the lambda vector the reference computed from that solution (NaN for the last one)
 """
-import glob
 import os
 import sys
 
