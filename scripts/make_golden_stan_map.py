@@ -66,7 +66,11 @@ def proj_vectors(n_rows, n_cols):
 
 
 EXPERIMENTAL = {'PDAC': 'PDAC_COM3_02109_Contact10_2065C_500C.txt', 'LIB_data': 'DRTtools_LIB_data.txt',
-                'LIB_data_qtr': 'DRTtools_LIB_data_qtr.csv'}
+                'LIB_data_qtr': 'DRTtools_LIB_data_qtr.csv',
+                # (not PDAC_DRT-TpDDT: on that measured, not exactly log-uniform grid the stored DDT matrix is up to 1.2 % off
+                # today's matrices.construct_A at low frequency x long tau -- that version integrated the general path
+                # differently; today's code is the specification, tests/golden/matrices.npz)
+                'LIB_data_DRT-TpDDT': 'DRTtools_LIB_data.txt', 'LIB_data_qtr_DRT-TpDDT': 'DRTtools_LIB_data_qtr.csv'}
 
 
 def read_experimental(path):
@@ -116,7 +120,7 @@ def main():
         elif name in EXPERIMENTAL:
             f_all, Z_all = read_experimental(os.path.join(REF, 'data/experimental', EXPERIMENTAL[name]))
         else:
-            continue  # two-distribution fits of the experimental spectra: settings not recoverable from the object
+            continue
         ft = np.asarray(d['f_train'], dtype=np.float64)
         idx = [int(np.argmin(np.abs(np.log(f_all) - np.log(f)))) for f in ft]
         if not np.allclose(f_all[idx], ft, rtol=1e-9):
