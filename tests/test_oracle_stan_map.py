@@ -194,3 +194,28 @@ def test_stans_end_point_is_near_stationary_for_the_oracle_density(name):
         xs, xo = mod.constrain(u, d)['x'], mod.constrain(pz['x'], d)['x']
         assert 0.0 <= -pz['f'] - lp <= 0.1, -pz['f'] - lp
         assert np.max(np.abs(xs - xo)) <= 1e-2 * np.max(np.abs(xo))
+
+
+@pytest.mark.parametrize('name', ['RC-ZARC_uniform_2.5', 'RC-ZARC_uniform_1.0'])
+def test_stan_semantics_lbfgs_from_random_starts_finds_stans_optimum(name):
+    """End to end on the data of a saved fit: the restatement of Stan's L-BFGS (oracle/lbfgs.py, the statement
+    csrc/lbfgs_kernel.cuh implements) from Stan-style random starts U(-2, 2) ends where pystan ended -- within 0.05 of
+    its log density and 5e-3 of the peak in x, i.e. within Stan's own termination accuracy -- for at least one of three
+    starts.  (The posterior is multimodal: other starts, like other seeds of pystan, end in other modes; for some of the
+    saved fits every random start here finds a mode with a HIGHER density than the saved one.)"""
+    from oracle import lbfgs as olb
+    d, u, S, mod, meta = build(name)
+    lp_stan = mod.logpost(u, d)[0]
+    x_stan = mod.constrain(u, d)['x']
+
+    def func(z):
+        l, gg = mod.logpost(z, d)
+        return None if (not np.isfinite(l) or not np.all(np.isfinite(gg))) else (-l, -gg)
+    best = None
+    for seed in range(3):
+        with np.errstate(all='ignore'):
+            r = olb.minimize(func, np.random.RandomState(seed).uniform(-2, 2, len(u)), max_iter=50000)
+        dist = np.max(np.abs(mod.constrain(r['x'], d)['x'] - x_stan)) / np.max(np.abs(x_stan))
+        if best is None or dist < best[1]:
+            best = (abs(-r['f'] - lp_stan), dist)
+    assert best[0] <= 0.05 and best[1] <= 5e-3, best
